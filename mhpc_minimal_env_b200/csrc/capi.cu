@@ -1,0 +1,832 @@
+// Host side of the C ABI (include/mhpc_b200.h): problem setup, device memory, and the launch
+// schedule that reproduces MultiPhaseDDP::solve (MultiPhaseDDP.cpp:154-289) for a whole batch with
+// per-instance control flow kept on the device.  No CPU arithmetic of the hot path lives here.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <set>
+#include <string>
+#include <vector>
+
+#include "../../include/mhpc_b200.h"
+#include "kernels.h"
+#include "model.cuh"
+
+namespace mhpc {
+int eval_fn_id(const char* name);
+double measure_fp64_peak_tflops(int device);
+}
+using namespace mhpc;
+
+static thread_local std::string g_err;
+static int fail(const std::string& m) { g_err = m; return -1; }
+#define CK(call)                                                                                         \
+    do {                                                                                                 \
+        cudaError_t e_ = (call);                                                                         \
+        if (e_ != cudaSuccess) return fail(std::string(#call) + ": " + cudaGetErrorString(e_));          \
+    } while (0)
+
+enum { TB_ROLLOUT = 0, TB_LIN, TB_BWS, TB_LS, TB_OTHER, TB_N };
+
+struct mhpc_batch {
+    int n = 0, device = 0, W = 8;
+    cudaStream_t stream = nullptr;
+    bool own_stream = true;
+    Opt opt{};
+    Consts c{};
+    Dev d{};
+    EpsList eps{};
+    bool have_problems = false;
+    std::vector<mhpc_problem> problems;
+    std::vector<int> h_nph, h_nwb, h_nk, h_mode, h_N, h_off;   // host copy of the schedule ([P][npad] for the last three)
+    std::vector<void*> allocs;
+    long long bytes = 0;
+    int* knot_list[CLS_N] = {nullptr};
+    int knot_cnt[CLS_N] = {0};
+    int alloc_KT = 0, alloc_P = 0;
+    // timing
+    bool timing = false;
+    struct Ev { cudaEvent_t a, b; int bucket; };
+    std::vector<Ev> evs;
+    mhpc_timing last{};
+    int launches = 0;
+};
+
+static void fill_opt(Opt& o, const mhpc_hsddp_option& s) {
+    o.alpha = s.alpha; o.gamma = s.gamma; o.update_penalty = s.update_penalty; o.update_relax = s.update_relax;
+    o.update_regularization = s.update_regularization; o.update_ReB = s.update_ReB; o.max_DDP_iter = s.max_DDP_iter;
+    o.max_AL_iter = s.max_AL_iter; o.DDP_thresh = s.DDP_thresh; o.AL_thresh = s.AL_thresh;
+    o.AL_active = s.AL_active; o.ReB_active = s.ReB_active; o.smooth_active = s.smooth_active;
+    o.quu_shift = std::pow(0.1, 9);   // SinglePhase.cpp:202
+}
+static void fill_eps(EpsList& e, double alpha) {   // MultiPhaseDDP.cpp:132-148
+    double eps = 1;
+    e.n = 0;
+    while (eps > std::pow(0.1, 10) && e.n < MAX_TRIALS) { e.eps[e.n++] = eps; eps *= alpha; }
+    for (int i = e.n; i < MAX_TRIALS; ++i) e.eps[i] = 0;
+}
+static void fill_consts(Consts& c) {
+    const double PI = MHPC_PI;
+    const double q[14] = {0, 10, 5, 4, 4, 4, 4, 2, 1, .01, 6, 6, 6, 6};                       // MHPCCost.cpp:30
+    const double qf[4][14] = {{0, 20, 8, 3, 3, 3, 3, 3, 2, 0.01, 5, 5, 0.01, 0.01},           // :32-35
+                              {0, 20, 8, 3, 3, 3, 3, 3, 2, 0.01, 5, 5, 5, 5},
+                              {0, 20, 8, 3, 3, 3, 3, 3, 2, 0.01, 0.01, 0.01, 5, 5},
+                              {0, 20, 8, 3, 3, 3, 3, 3, 2, 0.01, 5, 5, 5, 5}};
+    const double r[4][4] = {{5, 5, 1, 1}, {1, 1, 1, 1}, {1, 1, 5, 5}, {1, 1, 1, 1}};          // :37-40
+    const double s[4][4] = {{0, 0, 0.3, 0.3}, {0, 0, 0, 0}, {0.15, 0.15, 0, 0}, {0, 0, 0, 0}};// :42-44 (s[3] undefined in the reference -> 0)
+    for (int i = 0; i < 14; ++i) c.wbQ[i] = 0.01 * q[i];
+    for (int m = 0; m < 4; ++m) {
+        for (int i = 0; i < 4; ++i) { c.wbR[m][i] = 0.5 * r[m][i]; c.wbS[m][i] = s[m][i]; }
+        for (int i = 0; i < 14; ++i) c.wbQf[m][i] = 100 * qf[m][i];
+    }
+    const double rq[6] = {0, 10, 5, 2, 1, 0.01}, rqf[6] = {1, 20, 8, 3, 1, 0.01};             // :63-64
+    const double rr[4][4] = {{0, 0, 0.01, 0.01}, {0, 0, 0, 0}, {0.01, 0.01, 0, 0}, {0, 0, 0, 0}};
+    for (int i = 0; i < 6; ++i) { c.rbQ[i] = 0.01 * rq[i]; c.rbQf[i] = 100 * rqf[i]; }
+    for (int m = 0; m < 4; ++m) for (int i = 0; i < 4; ++i) c.rbR[m][i] = rr[m][i];
+    const double xt[4][14] = {{0, -0.1432, -PI / 25, 0.35 * PI, -0.65 * PI, 0.35 * PI, -0.6 * PI, 0, 1, 0, 0, 0, 0, 0},   // ReferenceGen.cpp:42-49
+                              {0, -0.1418, PI / 35, 0.2 * PI, -0.58 * PI, 0.25 * PI, -0.7 * PI, 0, -1, 0, 0, 0, 0, 0},
+                              {0, -0.1325, -PI / 40, 0.33 * PI, -0.48 * PI, 0.33 * PI, -0.75 * PI, 0, 1, 0, 0, 0, 0, 0},
+                              {0, -0.1490, -PI / 25, 0.35 * PI, -0.7 * PI, 0.25 * PI, -0.60 * PI, 0, -1, 0, 0, 0, 0, 0}};
+    std::memcpy(c.xterm, xt, sizeof(xt));
+    const double qb[4] = {0.3 * PI, -0.7 * PI, 0.3 * PI, -0.7 * PI};
+    std::memcpy(c.qbias, qb, sizeof(qb));
+    c.GRF = 8.252 * 9.81;
+    const double bj[8] = {PI / 4, -0.1, 1.15 * PI, -0.1, PI, PI - 0.2, .1, PI - 0.2};         // MHPCConstraints.cpp:53-54
+    std::memcpy(c.bjoint, bj, sizeof(bj));
+    c.btorque = 33;
+    c.mu = 0.5f;
+    c.fh_vel = 1.5; c.fh_ground = -0.404;                                                    // MHPCLocomotion.cpp:25
+    c.hip_x = (0.19 * 2) / 2; c.hip_len = 0.209; c.knee_len = 0.195;                         // PlanarQuadruped.cpp:120-138
+    const double qn[4] = {PI / 4, -PI * 7 / 12, PI / 4, -PI * 7 / 12};                       // boundingPDControl.cpp:6
+    std::memcpy(c.qjoint_nom, qn, sizeof(qn));
+    const double kp[4] = {5 * 8.0, 5 * 1.0, 5 * 12.0, 5 * 10.0};
+    std::memcpy(c.kp, kp, sizeof(kp));
+    c.legext_nom = 0.2462; c.kspring = 2200;
+}
+
+template <class T>
+static int dalloc(mhpc_batch* b, T** p, size_t count) {
+    void* q = nullptr;
+    const size_t bytes = std::max<size_t>(count, 1) * sizeof(T);
+    CK(cudaMalloc(&q, bytes));
+    CK(cudaMemsetAsync(q, 0, bytes, b->stream));
+    b->allocs.push_back(q);
+    b->bytes += (long long)bytes;
+    *p = (T*)q;
+    return 0;
+}
+static void free_all(mhpc_batch* b) {
+    for (void* p : b->allocs) cudaFree(p);
+    b->allocs.clear();
+    b->bytes = 0;
+    for (int c = 0; c < CLS_N; ++c) { b->knot_list[c] = nullptr; b->knot_cnt[c] = 0; }
+}
+
+// stage timing helpers
+struct Stage {
+    mhpc_batch* b; int bucket; bool on; cudaEvent_t a{}, e{};
+    Stage(mhpc_batch* b_, int bucket_) : b(b_), bucket(bucket_), on(b_->timing) {
+        if (on) { cudaEventCreate(&a); cudaEventCreate(&e); cudaEventRecord(a, b->stream); }
+    }
+    ~Stage() { if (on) { cudaEventRecord(e, b->stream); b->evs.push_back({a, e, bucket}); } }
+};
+
+static int gait_next(const mhpc_problem& p, int cur) {   // Gait.h:46-53
+    for (int i = 0; i < 4; ++i) if (cur == p.gait_mode[i]) return p.gait_mode[(i + 1) % 4];
+    return cur;
+}
+
+extern "C" {
+
+const char* mhpc_last_error(void) { return g_err.c_str(); }
+
+void mhpc_default_option(mhpc_hsddp_option* o) {
+    o->alpha = 0.1; o->gamma = 0.01; o->update_penalty = 8; o->update_relax = 0.1; o->update_regularization = 2;
+    o->update_ReB = 7; o->max_DDP_iter = 3; o->max_AL_iter = 2; o->DDP_thresh = 1e-03; o->AL_thresh = 1e-03;
+    o->AL_active = 1; o->ReB_active = 1; o->smooth_active = 0;
+}
+void mhpc_default_problem(mhpc_problem* p) {
+    p->n_wbphase = 4; p->n_fbphase = 4; p->dt_wb = .001f; p->dt_fb = .001f; p->cmode = 1; p->groundH = -0.404f;
+    p->vel = 1.5f; p->height = 0; p->roll = 0; p->pitch = 0; p->yaw = 0;
+    const int gm[4] = {1, 2, 3, 4};
+    const float gt[4] = {0.08f, 0.1f, 0.08f, 0.1f};
+    std::memcpy(p->gait_mode, gm, sizeof(gm));
+    std::memcpy(p->gait_timing, gt, sizeof(gt));
+    const double x0[14] = {0.0927, -0.1093, -0.1542, 1.0957, -2.2033, 0.9742, -1.7098,
+                           0.9011, 0.2756, 0.7333, 0.0446, 0.0009, 1.3219, 2.7346};
+    std::memcpy(p->x0, x0, sizeof(x0));
+}
+
+int mhpc_batch_create(int n, const mhpc_hsddp_option* opt, int device, int ls_width, mhpc_batch** out) {
+    if (n <= 0 || !opt || !out) return fail("mhpc_batch_create: bad arguments");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail("mhpc_batch_create: no CUDA device (the hot path has no CPU fallback)");
+    if (device < 0 || device >= ndev) return fail("mhpc_batch_create: bad device index");
+    CK(cudaSetDevice(device));
+    mhpc_batch* b = new mhpc_batch();
+    b->n = n; b->device = device;
+    b->W = ls_width <= 0 ? 8 : std::min(ls_width, (int)MAX_TRIALS);
+    CK(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking));
+    fill_opt(b->opt, *opt);
+    fill_eps(b->eps, b->opt.alpha);
+    fill_consts(b->c);
+    *out = b;
+    return 0;
+}
+void mhpc_batch_destroy(mhpc_batch* b) {
+    if (!b) return;
+    cudaSetDevice(b->device);
+    cudaStreamSynchronize(b->stream);
+    free_all(b);
+    for (auto& e : b->evs) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
+    if (b->own_stream && b->stream) cudaStreamDestroy(b->stream);
+    delete b;
+}
+int mhpc_batch_set_option(mhpc_batch* b, const mhpc_hsddp_option* opt) {
+    fill_opt(b->opt, *opt);
+    fill_eps(b->eps, b->opt.alpha);
+    return 0;
+}
+int mhpc_batch_set_stream(mhpc_batch* b, void* s) {
+    CK(cudaSetDevice(b->device));
+    CK(cudaStreamSynchronize(b->stream));
+    if (b->own_stream && b->stream) cudaStreamDestroy(b->stream);
+    if (s) { b->stream = (cudaStream_t)s; b->own_stream = false; }
+    else { CK(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking)); b->own_stream = true; }
+    return 0;
+}
+int mhpc_batch_synchronize(mhpc_batch* b) {
+    CK(cudaSetDevice(b->device));
+    CK(cudaStreamSynchronize(b->stream));
+    return 0;
+}
+long long mhpc_batch_device_bytes(mhpc_batch* b) { return b->bytes; }
+
+int mhpc_batch_set_problems(mhpc_batch* b, const mhpc_problem* pr) {
+    CK(cudaSetDevice(b->device));
+    const int n = b->n, npad = (n + 31) / 32 * 32, nblk = npad / 32;
+    b->problems.assign(pr, pr + n);
+    int P = 1, KT = 1;
+    for (int i = 0; i < n; ++i) {
+        const int np = pr[i].n_wbphase + pr[i].n_fbphase;
+        if (pr[i].n_wbphase < 1) return fail("set_problems: n_wbphase must be >= 1 (MHPCLocomotion.cpp:176)");
+        if (np > MAXP) return fail("set_problems: too many phases");
+        P = std::max(P, np);
+    }
+    b->h_nph.assign(npad, 0); b->h_nwb.assign(npad, 0); b->h_nk.assign(npad, 0);
+    b->h_mode.assign((size_t)P * npad, 1); b->h_N.assign((size_t)P * npad, 0); b->h_off.assign((size_t)P * npad, 0);
+    std::vector<double> dtw(npad, 0), dtf(npad, 0), vel(npad, 0), hgt(npad, 0), x0((size_t)14 * npad, 0);
+    for (int i = 0; i < n; ++i) {
+        const mhpc_problem& q = pr[i];
+        const int np = q.n_wbphase + q.n_fbphase;
+        b->h_nph[i] = np; b->h_nwb[i] = q.n_wbphase;
+        const double dt_wb = q.dt_wb, dt_fb = q.dt_fb;   // float -> double (MHPCLocomotion.h:59)
+        dtw[i] = dt_wb; dtf[i] = dt_fb; vel[i] = q.vel; hgt[i] = q.height;
+        int mode = q.cmode, off = 0;
+        for (int p = 0; p < np; ++p) {   // Gait.h:55-77, MHPCLocomotion.cpp:76,85
+            if (p > 0) mode = gait_next(q, mode);
+            if (mode < 1 || mode > 4) return fail("set_problems: modes must be 1..4");
+            const float timing = q.gait_timing[mode - 1];
+            const int N = (int)std::round(timing / (p < q.n_wbphase ? dt_wb : dt_fb));
+            if (N < 2) return fail("set_problems: a phase needs at least 2 knots");
+            b->h_mode[(size_t)p * npad + i] = mode; b->h_N[(size_t)p * npad + i] = N; b->h_off[(size_t)p * npad + i] = off;
+            off += N;
+        }
+        b->h_nk[i] = off;
+        KT = std::max(KT, off);
+        for (int e = 0; e < 14; ++e) x0[(size_t)e * npad + i] = q.x0[e];
+    }
+    // (re)allocate when the shape grows
+    if (!b->have_problems || KT > b->alloc_KT || P > b->alloc_P || b->d.npad != npad) {
+        CK(cudaStreamSynchronize(b->stream));
+        free_all(b);
+        Dev& d = b->d;
+        d = Dev{};
+        d.n = n; d.npad = npad; d.nblk = nblk; d.P = P; d.KT = KT; d.W = b->W;
+        d.max_rec = std::max(1, (int)std::floor(b->opt.max_AL_iter) * (int)std::floor(b->opt.max_DDP_iter));
+        d.max_rec = std::max(d.max_rec, 64);
+        int rc = 0;
+        rc |= dalloc(b, &d.n_phases, npad); rc |= dalloc(b, &d.n_wb, npad); rc |= dalloc(b, &d.n_knots, npad);
+        rc |= dalloc(b, &d.ph_mode, (size_t)P * npad); rc |= dalloc(b, &d.ph_N, (size_t)P * npad); rc |= dalloc(b, &d.ph_off, (size_t)P * npad);
+        rc |= dalloc(b, &d.rec_len, (size_t)nblk * KT);
+        rc |= dalloc(b, &d.dt_wb, npad); rc |= dalloc(b, &d.dt_fb, npad); rc |= dalloc(b, &d.vel, npad); rc |= dalloc(b, &d.height, npad);
+        rc |= dalloc(b, &d.x0, (size_t)14 * npad);
+        rc |= dalloc(b, &d.pos_ref, (size_t)KT * npad);
+        rc |= dalloc(b, &d.st_nom, (size_t)KT * ST * npad);
+        rc |= dalloc(b, &d.st_act, (size_t)d.W * KT * ST * npad);
+        rc |= dalloc(b, &d.Kfb, (size_t)KT * KDIM * npad);
+        rc |= dalloc(b, &d.dufb, (size_t)KT * 4 * npad);
+        rc |= dalloc(b, &d.Gv, (size_t)KT * 14 * npad);
+        rc |= dalloc(b, &d.lin, (size_t)nblk * KT * REC * 32);
+        rc |= dalloc(b, &d.par, (size_t)P * NPAR * npad);
+        rc |= dalloc(b, &d.tr_cost, (size_t)d.W * npad); rc |= dalloc(b, &d.tr_viol2, (size_t)d.W * npad);
+        rc |= dalloc(b, &d.tr_h, (size_t)d.W * P * npad);
+        rc |= dalloc(b, &d.sd, (size_t)SD_N * npad); rc |= dalloc(b, &d.si, (size_t)SI_N * npad);
+        rc |= dalloc(b, &d.rec_i, (size_t)d.max_rec * REC_I * npad); rc |= dalloc(b, &d.rec_d, (size_t)d.max_rec * REC_D * npad);
+        rc |= dalloc(b, &d.n_active, 1);
+        for (int c = 0; c < CLS_N; ++c) rc |= dalloc(b, &b->knot_list[c], KT);
+        if (rc) return -1;
+        b->alloc_KT = KT; b->alloc_P = P;
+    }
+    Dev& d = b->d;
+    // record lengths per (block, knot) and knot lists per class
+    std::vector<int> rec_len((size_t)nblk * d.KT, 0);
+    std::set<int> cls_knots[CLS_N];
+    for (int i = 0; i < n; ++i) {
+        const int np = b->h_nph[i], nwb = b->h_nwb[i];
+        for (int p = 0; p < np; ++p) {
+            const int mode = b->h_mode[(size_t)p * npad + i], N = b->h_N[(size_t)p * npad + i], off = b->h_off[(size_t)p * npad + i];
+            const bool wb = p < nwb;
+            for (int k = 0; k < N; ++k) {
+                const bool term = (k == N - 1);
+                int len, cls;
+                if (wb && !term) { len = WB_STEP_LEN; cls = mode == 1 ? CLS_BS : mode == 3 ? CLS_FS : CLS_FL; }
+                else if (wb) { len = WB_TERM_LEN; cls = mode == 2 ? CLS_IMPF : mode == 4 ? CLS_IMPB : CLS_LIGHT; }
+                else if (!term) { len = RB_STEP_LEN; cls = CLS_LIGHT; }
+                else { len = RB_TERM_LEN; cls = CLS_LIGHT; }
+                int& r = rec_len[(size_t)(i >> 5) * d.KT + off + k];
+                r = std::max(r, len);
+                cls_knots[cls].insert(off + k);
+            }
+        }
+    }
+    CK(cudaMemcpyAsync(d.rec_len, rec_len.data(), rec_len.size() * sizeof(int), cudaMemcpyHostToDevice, b->stream));
+    for (int c = 0; c < CLS_N; ++c) {
+        std::vector<int> v(cls_knots[c].begin(), cls_knots[c].end());
+        b->knot_cnt[c] = (int)v.size();
+        if (!v.empty()) CK(cudaMemcpyAsync(b->knot_list[c], v.data(), v.size() * sizeof(int), cudaMemcpyHostToDevice, b->stream));
+        CK(cudaStreamSynchronize(b->stream));
+    }
+    auto up = [&](void* dst, const void* src, size_t bytes) { return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, b->stream); };
+    CK(up(d.n_phases, b->h_nph.data(), npad * sizeof(int))); CK(up(d.n_wb, b->h_nwb.data(), npad * sizeof(int)));
+    CK(up(d.n_knots, b->h_nk.data(), npad * sizeof(int)));
+    // schedule arrays may have been built with a smaller P than allocated: copy row by row
+    for (int p = 0; p < P; ++p) {
+        CK(up(d.ph_mode + (size_t)p * npad, b->h_mode.data() + (size_t)p * npad, npad * sizeof(int)));
+        CK(up(d.ph_N + (size_t)p * npad, b->h_N.data() + (size_t)p * npad, npad * sizeof(int)));
+        CK(up(d.ph_off + (size_t)p * npad, b->h_off.data() + (size_t)p * npad, npad * sizeof(int)));
+    }
+    CK(up(d.dt_wb, dtw.data(), npad * sizeof(double))); CK(up(d.dt_fb, dtf.data(), npad * sizeof(double)));
+    CK(up(d.vel, vel.data(), npad * sizeof(double))); CK(up(d.height, hgt.data(), npad * sizeof(double)));
+    CK(up(d.x0, x0.data(), (size_t)14 * npad * sizeof(double)));
+    CK(cudaStreamSynchronize(b->stream));   // host vectors go out of scope
+    b->have_problems = true;
+    return 0;
+}
+
+static int linearize(mhpc_batch* b, int mask_mode) {
+    Stage st(b, TB_LIN);
+    const Dev& d = b->d;
+    launch_lin_BS(d, b->c, b->opt, mask_mode, b->knot_list[CLS_BS], b->knot_cnt[CLS_BS], b->stream);
+    launch_lin_FS(d, b->c, b->opt, mask_mode, b->knot_list[CLS_FS], b->knot_cnt[CLS_FS], b->stream);
+    launch_lin_FL(d, b->c, b->opt, mask_mode, b->knot_list[CLS_FL], b->knot_cnt[CLS_FL], b->stream);
+    launch_lin_IMPF(d, b->c, b->opt, mask_mode, b->knot_list[CLS_IMPF], b->knot_cnt[CLS_IMPF], b->stream);
+    launch_lin_IMPB(d, b->c, b->opt, mask_mode, b->knot_list[CLS_IMPB], b->knot_cnt[CLS_IMPB], b->stream);
+    launch_lin_LIGHT(d, b->c, b->opt, mask_mode, b->knot_list[CLS_LIGHT], b->knot_cnt[CLS_LIGHT], b->stream);
+    for (int c = 0; c < CLS_N; ++c) b->launches += b->knot_cnt[c] > 0;
+    CK(cudaGetLastError());
+    return 0;
+}
+static int need(mhpc_batch* b) {
+    if (!b || !b->have_problems) return fail("no problems set (call mhpc_batch_set_problems first)");
+    CK(cudaSetDevice(b->device));
+    return 0;
+}
+
+int mhpc_batch_initialization(mhpc_batch* b) {
+    if (need(b)) return -1;
+    Dev& d = b->d;
+    Stage st(b, TB_OTHER);
+    // memory_reset (MHPCLocomotion.cpp:265-290)
+    CK(cudaMemsetAsync(d.st_nom, 0, (size_t)d.KT * ST * d.npad * sizeof(double), b->stream));
+    CK(cudaMemsetAsync(d.st_act, 0, (size_t)d.W * d.KT * ST * d.npad * sizeof(double), b->stream));
+    CK(cudaMemsetAsync(d.Kfb, 0, (size_t)d.KT * KDIM * d.npad * sizeof(double), b->stream));
+    CK(cudaMemsetAsync(d.dufb, 0, (size_t)d.KT * 4 * d.npad * sizeof(double), b->stream));
+    CK(cudaMemsetAsync(d.Gv, 0, (size_t)d.KT * 14 * d.npad * sizeof(double), b->stream));
+    CK(cudaMemsetAsync(d.lin, 0, (size_t)d.nblk * d.KT * REC * 32 * sizeof(double), b->stream));
+    launch_setup(d, b->c, b->stream);                 // build_problem: references + AL/ReB parameters
+    launch_warmstart(d, b->c, b->stream);             // warmstart()
+    launch_copy_nominal(d, MASK_ALL, b->stream);      // update_nominal_trajectory()
+    b->launches += 3;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int mhpc_batch_forward_sweep(mhpc_batch* b, double eps) {
+    if (need(b)) return -1;
+    EpsList one{}; one.n = 1; one.eps[0] = eps;
+    // the step-level API applies the option's ReB flag as is (the solve loop overrides it per AL iteration)
+    CK(cudaMemsetAsync(b->d.si + (size_t)SI_STATUS * b->d.npad, 0, b->d.npad * sizeof(int), b->stream));
+    std::vector<int> reb(b->d.npad, b->opt.ReB_active);
+    CK(cudaMemcpyAsync(b->d.si + (size_t)SI_REB_ON * b->d.npad, reb.data(), reb.size() * sizeof(int), cudaMemcpyHostToDevice, b->stream));
+    CK(cudaStreamSynchronize(b->stream));
+    launch_rollout(b->d, b->c, b->opt, MASK_ALL, 1, 0, one, b->stream);
+    launch_accept_slot0(b->d, MASK_ALL, 2, b->stream);
+    if (linearize(b, MASK_ALL)) return -1;
+    CK(cudaGetLastError());
+    return 0;
+}
+int mhpc_batch_forward_sweep_dynamics_only(mhpc_batch* b, double eps) {
+    if (need(b)) return -1;
+    EpsList one{}; one.n = 1; one.eps[0] = eps;
+    std::vector<int> reb(b->d.npad, b->opt.ReB_active);
+    CK(cudaMemcpyAsync(b->d.si + (size_t)SI_REB_ON * b->d.npad, reb.data(), reb.size() * sizeof(int), cudaMemcpyHostToDevice, b->stream));
+    CK(cudaStreamSynchronize(b->stream));
+    launch_rollout(b->d, b->c, b->opt, MASK_ALL, 1, 0, one, b->stream);
+    launch_accept_slot0(b->d, MASK_ALL, 1, b->stream);
+    CK(cudaGetLastError());
+    return 0;
+}
+int mhpc_batch_forward_sweep_partials_only(mhpc_batch* b) {
+    if (need(b)) return -1;
+    std::vector<int> v(b->d.npad, 1), reb(b->d.npad, b->opt.ReB_active);
+    CK(cudaMemcpyAsync(b->d.si + (size_t)SI_AL_PARTIALS * b->d.npad, v.data(), v.size() * sizeof(int), cudaMemcpyHostToDevice, b->stream));
+    CK(cudaMemcpyAsync(b->d.si + (size_t)SI_REB_ON * b->d.npad, reb.data(), reb.size() * sizeof(int), cudaMemcpyHostToDevice, b->stream));
+    CK(cudaStreamSynchronize(b->stream));
+    return linearize(b, MASK_ALL);
+}
+int mhpc_batch_backward_sweep(mhpc_batch* b, double reg, int* success) {
+    if (need(b)) return -1;
+    std::vector<double> r(b->d.npad, reg);
+    CK(cudaMemcpyAsync(b->d.sd + (size_t)SD_REG * b->d.npad, r.data(), r.size() * sizeof(double), cudaMemcpyHostToDevice, b->stream));
+    CK(cudaStreamSynchronize(b->stream));
+    {
+        Stage st(b, TB_BWS);
+        launch_bws(b->d, b->c, b->opt, MASK_ALL, 1, b->stream);
+    }
+    CK(cudaGetLastError());
+    if (success) {
+        CK(cudaMemcpyAsync(success, b->d.si + (size_t)SI_BWS_OK * b->d.npad, b->n * sizeof(int), cudaMemcpyDeviceToHost, b->stream));
+        CK(cudaStreamSynchronize(b->stream));
+    }
+    return 0;
+}
+static int line_search(mhpc_batch* b, int mask_ls, int mask_sel) {
+    Stage st(b, TB_LS);
+    const Dev& d = b->d;
+    for (int t0 = 0; t0 < b->eps.n; t0 += d.W) {
+        const int ns = std::min(d.W, b->eps.n - t0);
+        const int last = (t0 + ns >= b->eps.n);
+        launch_rollout(d, b->c, b->opt, mask_ls, ns, t0, b->eps, b->stream);
+        launch_select(d, b->opt, mask_sel, t0, ns, last, b->eps, b->stream);
+        b->launches += 2;
+    }
+    CK(cudaGetLastError());
+    return 0;
+}
+int mhpc_batch_forward_iteration(mhpc_batch* b, int* trials) {
+    if (need(b)) return -1;
+    std::vector<int> reb(b->d.npad, b->opt.ReB_active), act(b->d.npad, 1);
+    CK(cudaMemsetAsync(b->d.si + (size_t)SI_STATUS * b->d.npad, 0, b->d.npad * sizeof(int), b->stream));
+    CK(cudaMemcpyAsync(b->d.si + (size_t)SI_REB_ON * b->d.npad, reb.data(), reb.size() * sizeof(int), cudaMemcpyHostToDevice, b->stream));
+    CK(cudaMemcpyAsync(b->d.si + (size_t)SI_DDP_ACTIVE * b->d.npad, act.data(), act.size() * sizeof(int), cudaMemcpyHostToDevice, b->stream));
+    CK(cudaStreamSynchronize(b->stream));
+    launch_ls_begin(b->d, MASK_ALL, b->stream);
+    if (line_search(b, MASK_LS, MASK_ALL)) return -1;
+    if (trials) {
+        CK(cudaMemcpyAsync(trials, b->d.si + (size_t)SI_N_FIT * b->d.npad, b->n * sizeof(int), cudaMemcpyDeviceToHost, b->stream));
+        CK(cudaStreamSynchronize(b->stream));
+    }
+    return 0;
+}
+int mhpc_batch_update_nominal_trajectory(mhpc_batch* b) {
+    if (need(b)) return -1;
+    launch_copy_nominal(b->d, MASK_ALL, b->stream);
+    CK(cudaGetLastError());
+    return 0;
+}
+int mhpc_batch_update_AL_ReB_param(mhpc_batch* b) {
+    if (need(b)) return -1;
+    launch_al_end(b->d, b->opt, b->c, MASK_ALL, 0, b->stream);
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int mhpc_batch_solve(mhpc_batch* b, int sync_early_exit) {
+    if (need(b)) return -1;
+    const Dev& d = b->d;
+    cudaStream_t s = b->stream;
+    const int maxAL = (int)std::floor(b->opt.max_AL_iter), maxDDP = (int)std::floor(b->opt.max_DDP_iter);
+    EpsList zero{}; zero.n = 1; zero.eps[0] = 0.0;
+    b->launches = 0;
+    for (auto& e : b->evs) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
+    b->evs.clear();
+    cudaEvent_t t0 = nullptr, t1 = nullptr;
+    if (b->timing) { cudaEventCreate(&t0); cudaEventCreate(&t1); cudaEventRecord(t0, s); }
+    launch_solve_begin(d, s); b->launches++;
+    for (int al = 1; al <= maxAL; ++al) {
+        { Stage st(b, TB_OTHER); launch_al_begin(d, b->opt, s); b->launches++; }
+        { Stage st(b, TB_ROLLOUT);                                   // forward_sweep(0): rollout ...
+          launch_rollout(d, b->c, b->opt, MASK_RUNNING, 1, 0, zero, s);
+          launch_accept_slot0(d, MASK_RUNNING, 2, s); b->launches += 2; }
+        if (linearize(b, MASK_RUNNING)) return -1;                   // ... and its derivatives
+        { Stage st(b, TB_OTHER); launch_copy_nominal(d, MASK_RUNNING, s); b->launches++; }   // update_nominal_trajectory
+        for (int it = 1; it <= maxDDP; ++it) {
+            { Stage st(b, TB_OTHER); launch_ls_begin(d, MASK_DDP, s); b->launches++; }
+            { Stage st(b, TB_BWS); launch_bws(d, b->c, b->opt, MASK_DDP, 0, s); b->launches++; }
+            if (line_search(b, MASK_LS, MASK_DDP)) return -1;
+            { Stage st(b, TB_OTHER);
+              launch_copy_nominal(d, MASK_DDP, s);
+              launch_ddp_end(d, b->opt, it, s); b->launches += 2; }
+            if (linearize(b, MASK_LIN)) return -1;                   // forward_sweep_partials_only
+        }
+        { Stage st(b, TB_OTHER); launch_al_end(d, b->opt, b->c, MASK_RUNNING, 1, s); b->launches++; }
+        if (sync_early_exit && al < maxAL) {
+            launch_count_active(d, s);
+            int na = 0;
+            CK(cudaMemcpyAsync(&na, d.n_active, sizeof(int), cudaMemcpyDeviceToHost, s));
+            CK(cudaStreamSynchronize(s));
+            if (na == 0) break;
+        }
+    }
+    CK(cudaGetLastError());
+    if (b->timing) {
+        cudaEventRecord(t1, s);
+        CK(cudaStreamSynchronize(s));
+        mhpc_timing t{};
+        cudaEventElapsedTime(&t.total_ms, t0, t1);
+        float acc[TB_N] = {0};
+        for (auto& e : b->evs) { float ms = 0; cudaEventElapsedTime(&ms, e.a, e.b); acc[e.bucket] += ms; }
+        t.rollout_ms = acc[TB_ROLLOUT]; t.linearize_ms = acc[TB_LIN]; t.bws_ms = acc[TB_BWS]; t.linesearch_ms = acc[TB_LS]; t.other_ms = acc[TB_OTHER];
+        t.n_launches = b->launches;
+        b->last = t;
+        cudaEventDestroy(t0); cudaEventDestroy(t1);
+    }
+    return 0;
+}
+
+int mhpc_batch_get_results(mhpc_batch* b, mhpc_result* r) {
+    if (need(b)) return -1;
+    const Dev& d = b->d;
+    std::vector<double> sd((size_t)SD_N * d.npad);
+    std::vector<int> si((size_t)SI_N * d.npad);
+    CK(cudaMemcpyAsync(sd.data(), d.sd, sd.size() * sizeof(double), cudaMemcpyDeviceToHost, b->stream));
+    CK(cudaMemcpyAsync(si.data(), d.si, si.size() * sizeof(int), cudaMemcpyDeviceToHost, b->stream));
+    CK(cudaStreamSynchronize(b->stream));
+    for (int i = 0; i < b->n; ++i) {
+        r[i].cost = sd[(size_t)SD_COST * d.npad + i]; r[i].exp_cost_change = sd[(size_t)SD_DV * d.npad + i];
+        r[i].viol = sd[(size_t)SD_VIOL * d.npad + i]; r[i].status = si[(size_t)SI_STATUS * d.npad + i];
+        r[i].iter_AL = si[(size_t)SI_ITER_AL * d.npad + i]; r[i].n_records = si[(size_t)SI_N_REC * d.npad + i]; r[i].pad = 0;
+    }
+    return 0;
+}
+int mhpc_batch_get_scalars(mhpc_batch* b, double* cost, double* dv, double* viol) {
+    if (need(b)) return -1;
+    const Dev& d = b->d;
+    if (cost) CK(cudaMemcpyAsync(cost, d.sd + (size_t)SD_COST * d.npad, b->n * sizeof(double), cudaMemcpyDeviceToHost, b->stream));
+    if (dv) CK(cudaMemcpyAsync(dv, d.sd + (size_t)SD_DV * d.npad, b->n * sizeof(double), cudaMemcpyDeviceToHost, b->stream));
+    if (viol) CK(cudaMemcpyAsync(viol, d.sd + (size_t)SD_VIOL * d.npad, b->n * sizeof(double), cudaMemcpyDeviceToHost, b->stream));
+    CK(cudaStreamSynchronize(b->stream));
+    return 0;
+}
+int mhpc_batch_get_records(mhpc_batch* b, int inst, mhpc_iter_record* out, int max_records) {
+    if (need(b)) return -1;
+    const Dev& d = b->d;
+    if (inst < 0 || inst >= b->n) return fail("get_records: bad instance");
+    int nrec = 0;
+    CK(cudaMemcpyAsync(&nrec, d.si + (size_t)SI_N_REC * d.npad + inst, sizeof(int), cudaMemcpyDeviceToHost, b->stream));
+    CK(cudaStreamSynchronize(b->stream));
+    nrec = std::min(nrec, std::min(max_records, d.max_rec));
+    if (nrec <= 0) return 0;
+    std::vector<int> ri((size_t)nrec * REC_I);
+    std::vector<double> rd((size_t)nrec * REC_D);
+    CK(cudaMemcpy2DAsync(ri.data(), sizeof(int), d.rec_i + inst, (size_t)d.npad * sizeof(int), sizeof(int), (size_t)nrec * REC_I, cudaMemcpyDeviceToHost, b->stream));
+    CK(cudaMemcpy2DAsync(rd.data(), sizeof(double), d.rec_d + inst, (size_t)d.npad * sizeof(double), sizeof(double), (size_t)nrec * REC_D, cudaMemcpyDeviceToHost, b->stream));
+    CK(cudaStreamSynchronize(b->stream));
+    for (int r = 0; r < nrec; ++r) {
+        out[r].iter_AL = ri[r * REC_I + 0]; out[r].iter_DDP = ri[r * REC_I + 1]; out[r].n_bws = ri[r * REC_I + 2]; out[r].n_fit = ri[r * REC_I + 3];
+        out[r].reg = rd[r * REC_D + 0]; out[r].eps = rd[r * REC_D + 1]; out[r].cost = rd[r * REC_D + 2];
+        out[r].exp_cost_change = rd[r * REC_D + 3]; out[r].viol = rd[r * REC_D + 4]; out[r].cost_prev = rd[r * REC_D + 5];
+    }
+    return nrec;
+}
+int mhpc_batch_n_phases(mhpc_batch* b, int inst) {
+    if (!b || !b->have_problems || inst < 0 || inst >= b->n) return -1;
+    return b->h_nph[inst];
+}
+int mhpc_batch_get_schedule(mhpc_batch* b, int inst, int* mode, int* nk, int* is_wb) {
+    if (!b || !b->have_problems || inst < 0 || inst >= b->n) return fail("get_schedule: bad arguments");
+    const int npad = b->d.npad;
+    for (int p = 0; p < b->h_nph[inst]; ++p) {
+        if (mode) mode[p] = b->h_mode[(size_t)p * npad + inst];
+        if (nk) nk[p] = b->h_N[(size_t)p * npad + inst];
+        if (is_wb) is_wb[p] = p < b->h_nwb[inst];
+    }
+    return 0;
+}
+int mhpc_batch_get_phase_params(mhpc_batch* b, int inst, int phase, double* out9) {
+    if (need(b)) return -1;
+    const Dev& d = b->d;
+    CK(cudaMemcpy2DAsync(out9, sizeof(double), d.par + par_idx(d, phase, 0, inst), (size_t)d.npad * sizeof(double), sizeof(double), NPAR,
+                         cudaMemcpyDeviceToHost, b->stream));
+    CK(cudaStreamSynchronize(b->stream));
+    return 0;
+}
+
+// strided gather of `rows` doubles of one instance out of an [rows][npad] array
+static int pull_rows(mhpc_batch* b, const double* base, int rows, int inst, double* out) {
+    CK(cudaMemcpy2DAsync(out, sizeof(double), base + inst, (size_t)b->d.npad * sizeof(double), sizeof(double), rows, cudaMemcpyDeviceToHost, b->stream));
+    CK(cudaStreamSynchronize(b->stream));
+    return 0;
+}
+
+int mhpc_batch_get_field(mhpc_batch* b, int inst, int phase, int field, double* out) {
+    if (need(b)) return -1;
+    const Dev& d = b->d;
+    if (inst < 0 || inst >= b->n || phase < 0 || phase >= b->h_nph[inst]) return fail("get_field: bad instance/phase");
+    const int npad = d.npad;
+    const bool wb = phase < b->h_nwb[inst];
+    const int nx = wb ? 14 : 6;
+    const int N = b->h_N[(size_t)phase * npad + inst], off = b->h_off[(size_t)phase * npad + inst], mode = b->h_mode[(size_t)phase * npad + inst];
+    const double dt = wb ? (double)b->problems[inst].dt_wb : (double)b->problems[inst].dt_fb;
+    auto state_field = [&](const double* base, int e0, int dim) -> int {
+        if (!out) return dim;
+        std::vector<double> tmp((size_t)N * ST);
+        if (pull_rows(b, base + (size_t)off * ST * npad, N * ST, inst, tmp.data())) return -1;
+        for (int k = 0; k < N; ++k) for (int e = 0; e < dim; ++e) out[(size_t)k * dim + e] = tmp[(size_t)k * ST + e0 + e];
+        return dim;
+    };
+    int slot = 0;
+    if (field <= MHPC_F_Y_ACT) {
+        CK(cudaMemcpyAsync(&slot, d.si + (size_t)SI_ACC_SLOT * npad + inst, sizeof(int), cudaMemcpyDeviceToHost, b->stream));
+        CK(cudaStreamSynchronize(b->stream));
+    }
+    const double* act = d.st_act + (size_t)slot * d.KT * ST * npad;
+    switch (field) {
+        case MHPC_F_X_ACT: return state_field(act, 0, nx);
+        case MHPC_F_U_ACT: return state_field(act, 14, 4);
+        case MHPC_F_Y_ACT: return state_field(act, 18, 4);
+        case MHPC_F_X_NOM: return state_field(d.st_nom, 0, nx);
+        case MHPC_F_U_NOM: return state_field(d.st_nom, 14, 4);
+        case MHPC_F_Y_NOM: return state_field(d.st_nom, 18, 4);
+        case MHPC_F_K: case MHPC_F_DU: case MHPC_F_G: {
+            const int stride = field == MHPC_F_K ? KDIM : field == MHPC_F_DU ? 4 : 14;
+            const int dim = field == MHPC_F_K ? 4 * nx : field == MHPC_F_DU ? 4 : nx;
+            if (!out) return dim;
+            const double* base = field == MHPC_F_K ? d.Kfb : field == MHPC_F_DU ? d.dufb : d.Gv;
+            std::vector<double> tmp((size_t)N * stride);
+            if (pull_rows(b, base + (size_t)off * stride * npad, N * stride, inst, tmp.data())) return -1;
+            for (int k = 0; k < N; ++k) for (int e = 0; e < dim; ++e) out[(size_t)k * dim + e] = tmp[(size_t)k * stride + e];
+            return dim;
+        }
+        case MHPC_F_X_REF: case MHPC_F_U_REF: case MHPC_F_Y_REF: {
+            const int dim = field == MHPC_F_X_REF ? nx : 4;
+            if (!out) return dim;
+            std::vector<double> pos(N);
+            if (pull_rows(b, d.pos_ref + (size_t)off * npad, N, inst, pos.data())) return -1;
+            const double vel = b->problems[inst].vel, hgt = b->problems[inst].height;
+            for (int k = 0; k < N; ++k) {   // ReferenceGen.h:53-91 (the device evaluates these on the fly from pos_ref)
+                double* o = out + (size_t)k * dim;
+                for (int e = 0; e < dim; ++e) o[e] = 0;
+                const bool term = (k == N - 1);
+                if (field == MHPC_F_X_REF) {
+                    if (wb && !term) { o[0] = pos[k]; o[1] = hgt; for (int q = 0; q < 4; ++q) o[3 + q] = b->c.qbias[q]; o[7] = vel; }
+                    else if (wb) { for (int e = 0; e < 14; ++e) o[e] = b->c.xterm[mode - 1][e]; o[0] = pos[k]; o[7] = vel; }
+                    else { o[0] = pos[k]; o[1] = hgt; o[3] = vel; }
+                } else if (field == MHPC_F_Y_REF) {
+                    if (wb && !term) { o[1] = b->c.GRF; o[3] = b->c.GRF; }
+                } else {
+                    if (!wb && !term) { o[1] = b->c.GRF; o[3] = b->c.GRF; }
+                }
+            }
+            return dim;
+        }
+        default: break;
+    }
+    // fields decoded from the AoSoA knot records
+    std::vector<double> recs((size_t)N * REC);
+    {
+        const double* base = d.lin + lin_base(d, inst, off);
+        std::vector<double> blk((size_t)N * REC * 32);
+        CK(cudaMemcpyAsync(blk.data(), base, blk.size() * sizeof(double), cudaMemcpyDeviceToHost, b->stream));
+        CK(cudaStreamSynchronize(b->stream));
+        for (int k = 0; k < N; ++k) for (int e = 0; e < REC; ++e) recs[(size_t)k * REC + e] = blk[((size_t)k * REC + e) * 32 + ((inst + e) & 31)];
+    }
+    auto R = [&](int k, int e) { return recs[(size_t)k * REC + e]; };
+    const int r0 = (mode == 1) ? 2 : 0;
+    const bool stance = (mode == 1 || mode == 3);
+    int dim = 0;
+    switch (field) {
+        case MHPC_F_A: dim = nx * nx; break; case MHPC_F_B: dim = nx * 4; break; case MHPC_F_C: dim = 4 * nx; break; case MHPC_F_D: dim = 16; break;
+        case MHPC_F_LX: dim = nx; break; case MHPC_F_LU: dim = 4; break; case MHPC_F_LY: dim = 4; break;
+        case MHPC_F_LXX: dim = nx * nx; break; case MHPC_F_LUU: dim = 16; break; case MHPC_F_LYY: dim = 16; break;
+        case MHPC_F_PHIX: dim = nx; break; case MHPC_F_PHIXX: dim = nx * nx; break; case MHPC_F_PX: dim = nx * nx; break;
+        default: return fail("get_field: unknown field");
+    }
+    if (!out) return dim;
+    if (field == MHPC_F_PHIX || field == MHPC_F_PHIXX || field == MHPC_F_PX) {
+        const int k = N - 1;
+        for (int e = 0; e < dim; ++e) out[e] = 0;
+        if (field == MHPC_F_PHIX) { for (int e = 0; e < nx; ++e) out[e] = R(k, wb ? R_PHIX + e : R_RPHIX + e); }
+        else if (field == MHPC_F_PHIXX) {
+            for (int e = 0; e < nx; ++e) out[e + nx * e] = wb ? R(k, R_PHIXXD + e) : b->c.rbQf[e];
+            if (wb) for (int cb = 1; cb <= 6; ++cb) for (int a = 1; a <= 6; ++a) out[a + 14 * cb] += R(k, R_PHIXXB + (a - 1) + 6 * (cb - 1));
+        } else {
+            for (int e = 0; e < nx; ++e) out[e + nx * e] = 1.0;
+            if (wb) {
+                for (int e = 7; e < 14; ++e) out[e + 14 * e] = 0.0;
+                for (int cc = 0; cc < 12; ++cc) for (int s = 0; s < 7; ++s) out[(7 + s) + 14 * (2 + cc)] = R(k, R_AB(s, cc));
+            }
+        }
+        return dim;
+    }
+    for (int k = 0; k < N; ++k) {
+        double* o = out + (size_t)k * dim;
+        for (int e = 0; e < dim; ++e) o[e] = 0;
+        if (k == N - 1) continue;   // derivatives exist for knots 0..N-2 only (SinglePhase.cpp:73)
+        if (wb) {
+            switch (field) {
+                case MHPC_F_A:
+                    for (int e = 0; e < 7; ++e) { o[e + 14 * e] = 1.0; o[e + 14 * (7 + e)] = 1.0 * dt; }
+                    for (int cc = 0; cc < 12; ++cc) for (int s = 0; s < 7; ++s) o[(7 + s) + 14 * (2 + cc)] = R(k, R_AB(s, cc));
+                    break;
+                case MHPC_F_B: for (int cc = 0; cc < 4; ++cc) for (int s = 0; s < 7; ++s) o[(7 + s) + 14 * cc] = R(k, R_BB(s, cc)); break;
+                case MHPC_F_C: if (stance) for (int cc = 0; cc < 12; ++cc) for (int t = 0; t < 2; ++t) o[(r0 + t) + 4 * (2 + cc)] = R(k, R_CB(t, cc)); break;
+                case MHPC_F_D: if (stance) for (int cc = 0; cc < 4; ++cc) for (int t = 0; t < 2; ++t) o[(r0 + t) + 4 * cc] = R(k, R_DB(t, cc)); break;
+                case MHPC_F_LX: for (int e = 0; e < 14; ++e) o[e] = R(k, R_LX + e); break;
+                case MHPC_F_LU: for (int e = 0; e < 4; ++e) o[e] = R(k, R_LU + e); break;
+                case MHPC_F_LY: if (stance) { o[r0] = R(k, R_LY); o[r0 + 1] = R(k, R_LY + 1); } break;
+                case MHPC_F_LXX: for (int e = 0; e < 14; ++e) o[e + 14 * e] = (e >= 3 && e < 7) ? R(k, R_LXXQ + e - 3) : (2 * dt) * b->c.wbQ[e]; break;
+                case MHPC_F_LUU: for (int e = 0; e < 4; ++e) o[e + 4 * e] = R(k, R_LUU + e); break;
+                case MHPC_F_LYY:
+                    if (stance) { o[r0 + 4 * r0] = R(k, R_LYY); o[r0 + 4 * (r0 + 1)] = R(k, R_LYY + 1); o[(r0 + 1) + 4 * r0] = R(k, R_LYY + 1); o[(r0 + 1) + 4 * (r0 + 1)] = R(k, R_LYY + 2); }
+                    break;
+            }
+        } else {
+            const int rows[8] = {3, 5, 4, 5, 3, 5, 4, 5}, cols[8] = {0, 0, 1, 1, 2, 2, 3, 3};
+            switch (field) {
+                case MHPC_F_A:
+                    for (int e = 0; e < 6; ++e) o[e + 6 * e] = 1.0;
+                    for (int e = 0; e < 3; ++e) o[e + 6 * (3 + e)] = 1.0 * dt;
+                    o[5 + 6 * 0] = R(k, R_RA); o[5 + 6 * 1] = R(k, R_RA + 1);
+                    break;
+                case MHPC_F_B: for (int q = 0; q < 8; ++q) o[rows[q] + 6 * cols[q]] = R(k, R_RB + q); break;
+                case MHPC_F_LX: for (int e = 0; e < 6; ++e) o[e] = R(k, R_RLX + e); break;
+                case MHPC_F_LU: for (int e = 0; e < 4; ++e) o[e] = R(k, R_RLU + e); break;
+                case MHPC_F_LXX: for (int e = 0; e < 6; ++e) o[e + 6 * e] = (2 * dt) * b->c.rbQ[e]; break;
+                case MHPC_F_LUU: for (int e = 0; e < 4; ++e) o[e + 4 * e] = (2 * dt) * b->c.rbR[mode - 1][e]; break;
+                default: break;
+            }
+        }
+    }
+    return dim;
+}
+
+__global__ void k_results_table(Dev d, double* out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= d.npad) return;
+    const bool v = i < d.n;
+    out[0 * (size_t)d.npad + i] = v ? d.sd[(size_t)SD_COST * d.npad + i] : 0.0;
+    out[1 * (size_t)d.npad + i] = v ? d.sd[(size_t)SD_DV * d.npad + i] : 0.0;
+    out[2 * (size_t)d.npad + i] = v ? d.sd[(size_t)SD_VIOL * d.npad + i] : 0.0;
+    out[3 * (size_t)d.npad + i] = v ? (double)d.si[(size_t)SI_STATUS * d.npad + i] : -1.0;
+    out[4 * (size_t)d.npad + i] = v ? (double)d.si[(size_t)SI_ITER_AL * d.npad + i] : 0.0;
+    out[5 * (size_t)d.npad + i] = v ? (double)d.si[(size_t)SI_N_REC * d.npad + i] : 0.0;
+}
+int mhpc_batch_results_to_device(mhpc_batch* b, double* dev_out, int capacity) {
+    if (need(b)) return -1;
+    if (capacity < 6 * b->d.npad) return fail("results_to_device: buffer too small (need 6*npad doubles)");
+    k_results_table<<<(b->d.npad + 127) / 128, 128, 0, b->stream>>>(b->d, dev_out);
+    CK(cudaGetLastError());
+    return b->d.npad;
+}
+
+int mhpc_batch_solve_host(mhpc_batch* b, const mhpc_problem* problems, mhpc_result* results, int exec_phases,
+                          double* exec_state, double* exec_gain, int exec_knots) {
+    if (!b) return fail("null handle");
+    if (mhpc_batch_set_problems(b, problems)) return -1;
+    if (mhpc_batch_initialization(b)) return -1;
+    if (mhpc_batch_solve(b, 0)) return -1;
+    if (results && mhpc_batch_get_results(b, results)) return -1;
+    if (exec_phases > 0 && exec_knots > 0 && (exec_state || exec_gain)) {
+        // execution bag (MHPCLocomotion.cpp:178-194): nominal x,u,y and K,du of the leading knots, instance-major on the host
+        const Dev& d = b->d;
+        const int kn = std::min(exec_knots, d.KT);
+        std::vector<double> st((size_t)kn * ST * d.npad), kf((size_t)kn * KDIM * d.npad), du((size_t)kn * 4 * d.npad);
+        if (exec_state) CK(cudaMemcpyAsync(st.data(), d.st_nom, st.size() * sizeof(double), cudaMemcpyDeviceToHost, b->stream));
+        if (exec_gain) {
+            CK(cudaMemcpyAsync(kf.data(), d.Kfb, kf.size() * sizeof(double), cudaMemcpyDeviceToHost, b->stream));
+            CK(cudaMemcpyAsync(du.data(), d.dufb, du.size() * sizeof(double), cudaMemcpyDeviceToHost, b->stream));
+        }
+        CK(cudaStreamSynchronize(b->stream));
+        for (int i = 0; i < b->n; ++i)
+            for (int k = 0; k < kn; ++k) {
+                if (exec_state) for (int e = 0; e < ST; ++e) exec_state[((size_t)i * exec_knots + k) * ST + e] = st[((size_t)k * ST + e) * d.npad + i];
+                if (exec_gain) {
+                    for (int e = 0; e < KDIM; ++e) exec_gain[((size_t)i * exec_knots + k) * 60 + e] = kf[((size_t)k * KDIM + e) * d.npad + i];
+                    for (int e = 0; e < 4; ++e) exec_gain[((size_t)i * exec_knots + k) * 60 + 56 + e] = du[((size_t)k * 4 + e) * d.npad + i];
+                }
+            }
+    }
+    return 0;
+}
+
+int mhpc_eval_function(const char* name, int n, int device, const double* in0, const double* in1, const double* in2,
+                       const double* in3, double* o0, double* o1, double* o2, double* o3) {
+    const int fn = eval_fn_id(name);
+    if (fn < 0) return fail(std::string("mhpc_eval_function: '") + name + "' is evaluated through the linearisation path (get_field A/B/C/D/PX)");
+    CK(cudaSetDevice(device));
+    const int isz[11][4] = {{14, 4, 0, 0}, {14, 4, 0, 0}, {14, 4, 0, 0}, {14, 0, 0, 0}, {14, 0, 0, 0}, {6, 4, 4, 2}, {6, 4, 4, 2}, {14, 0, 0, 0}, {14, 0, 0, 0}, {14, 0, 0, 0}, {14, 0, 0, 0}};
+    const int osz[11][4] = {{14, 4, 0, 0}, {14, 4, 0, 0}, {14, 4, 0, 0}, {14, 4, 0, 0}, {14, 4, 0, 0}, {6, 0, 0, 0}, {36, 24, 0, 0}, {1, 14, 196, 0}, {1, 14, 196, 0}, {14, 0, 0, 0}, {14, 0, 0, 0}};
+    const double* hin[4] = {in0, in1, in2, in3};
+    double* hout[4] = {o0, o1, o2, o3};
+    double* din[4] = {nullptr, nullptr, nullptr, nullptr};
+    double* dout[4] = {nullptr, nullptr, nullptr, nullptr};
+    for (int q = 0; q < 4; ++q) {
+        if (isz[fn][q]) { CK(cudaMalloc(&din[q], (size_t)n * isz[fn][q] * sizeof(double))); CK(cudaMemcpy(din[q], hin[q], (size_t)n * isz[fn][q] * sizeof(double), cudaMemcpyHostToDevice)); }
+        if (osz[fn][q]) CK(cudaMalloc(&dout[q], (size_t)n * osz[fn][q] * sizeof(double)));
+    }
+    launch_eval(fn, n, din[0], din[1], din[2], din[3], dout[0], dout[1], dout[2], dout[3], 0);
+    CK(cudaDeviceSynchronize());
+    for (int q = 0; q < 4; ++q) {
+        if (osz[fn][q]) CK(cudaMemcpy(hout[q], dout[q], (size_t)n * osz[fn][q] * sizeof(double), cudaMemcpyDeviceToHost));
+        if (din[q]) cudaFree(din[q]);
+        if (dout[q]) cudaFree(dout[q]);
+    }
+    return 0;
+}
+
+int mhpc_batch_enable_timing(mhpc_batch* b, int on) { b->timing = on != 0; return 0; }
+int mhpc_batch_get_timing(mhpc_batch* b, mhpc_timing* t) { *t = b->last; return 0; }
+
+int mhpc_batch_time_kernel(mhpc_batch* b, int which, int reps, float* ms_per_launch) {
+    if (need(b)) return -1;
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    const bool saved = b->timing;
+    b->timing = false;
+    auto run = [&]() -> int {
+        if (which == 0) {
+            std::vector<int> v(b->d.npad, 1);
+            return linearize(b, MASK_ALL);
+        } else if (which == 1) {
+            launch_bws(b->d, b->c, b->opt, MASK_ALL, 1, b->stream);
+        } else {
+            launch_rollout(b->d, b->c, b->opt, MASK_ALL, std::min(b->d.W, b->eps.n), 0, b->eps, b->stream);
+        }
+        return 0;
+    };
+    if (run()) return -1;   // warm-up
+    CK(cudaStreamSynchronize(b->stream));
+    CK(cudaEventRecord(e0, b->stream));
+    for (int r = 0; r < reps; ++r) if (run()) return -1;
+    CK(cudaEventRecord(e1, b->stream));
+    CK(cudaEventSynchronize(e1));
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    *ms_per_launch = ms / reps;
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    b->timing = saved;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int mhpc_measure_fp64_peak(int device, double* tflops) {
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || device >= ndev) return fail("no CUDA device");
+    *tflops = measure_fp64_peak_tflops(device);
+    return 0;
+}
+
+}  // extern "C"

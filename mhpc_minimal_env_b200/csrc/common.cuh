@@ -1,0 +1,121 @@
+// Device data model of the batched HSDDP path (see DESIGN.md "Data layout in HBM").
+//
+// Trajectory-type data is structure-of-arrays over instances so that the
+// thread-per-instance kernels (rollout, linearise, line-search select) coalesce:
+//     st[(knot * ST + e) * npad + inst]          e: 0..13 x | 14..17 u | 18..21 y
+// Per-knot linearisation records are AoSoA in blocks of 32 instances so that the writer
+// (lane = instance) stores full 256 B rows and the backward sweep (one CTA = the same 32
+// instances) pulls one contiguous chunk per knot into shared memory:
+//     lin[((blk * KT + knot) * REC + e) * 32 + ((j + e) & 31)]      j = inst & 31
+// (the (j + e) rotation makes both the per-instance gather and the broadcast reads of the
+// sweep conflict-free in shared memory).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace mhpc {
+
+constexpr int NXW = 14, NXR = 6, NU = 4, NY = 4;
+constexpr int ST = 22;            // x(14) u(4) y(4) per knot
+constexpr int KDIM = 56;          // K is 4x14 column-major (RB uses the first 24 = 4x6)
+constexpr int REC = 176;          // doubles per knot record
+constexpr int MAXP = 16;          // phases per instance (reference default 8)
+constexpr int MAX_TRIALS = 16;    // line-search step sizes (reference: 10)
+constexpr int NPAR = 9;           // per-phase AL/ReB parameters
+
+// ---- record element indices -------------------------------------------------------------
+// WB step knot: A = I + dt*Ac, B = dt*Bc in the reference (PlanarQuadruped.cpp:51-52); only the
+// dense blocks are stored: Ab = A[7:14, 2:14], Bb = B[7:14, :], Cb/Db = the two stance rows of C/D.
+__host__ __device__ constexpr int R_AB(int s, int c) { return c * 7 + s; }            // 0..83
+__host__ __device__ constexpr int R_BB(int s, int c) { return 84 + c * 7 + s; }       // 84..111
+__host__ __device__ constexpr int R_CB(int t, int c) { return 112 + c * 2 + t; }      // 112..135
+__host__ __device__ constexpr int R_DB(int t, int c) { return 136 + c * 2 + t; }      // 136..143
+constexpr int R_LX = 144;    // 14
+constexpr int R_LU = 158;    // 4
+constexpr int R_LY = 162;    // 2 (stance rows of ly)
+constexpr int R_LXXQ = 164;  // 4 (lxx diagonal at the joint positions 3..6)
+constexpr int R_LUU = 168;   // 4 (luu diagonal)
+constexpr int R_LYY = 172;   // 3 (stance 2x2 block of lyy: 00, 01(=10), 11)
+constexpr int WB_STEP_LEN = 175;
+// WB terminal knot: Pb = Px[7:14, 2:14] of the impact Jacobian (identity pattern for modes 1,3)
+constexpr int R_PHIX = 84;     // 14
+constexpr int R_PHIXXD = 98;   // 14 diagonal of Qf
+constexpr int R_PHIXXB = 112;  // 6x6 AL block on state indices 1..6, column-major
+constexpr int WB_TERM_LEN = 148;
+// RB step knot
+constexpr int R_RA = 0;    // A(5,0), A(5,1)
+constexpr int R_RB = 2;    // 8 non-zeros of B in CCS order (3,0)(5,0)(4,1)(5,1)(3,2)(5,2)(4,3)(5,3)
+constexpr int R_RLX = 10;  // 6
+constexpr int R_RLU = 16;  // 4
+constexpr int RB_STEP_LEN = 20;
+constexpr int R_RPHIX = 0;  // 6
+constexpr int RB_TERM_LEN = 6;
+
+// per-phase parameter slots (AL_REB_PARAMETER, MHPC_CompoundTypes.h:214-235; the reference's
+// delta / eps_ReB vectors are constant within each constraint group: torque, joint, GRF)
+enum { PAR_SIGMA = 0, PAR_LAMBDA, PAR_DELTA_T, PAR_DELTA_J, PAR_DELTA_G, PAR_EPS_T, PAR_EPS_J, PAR_EPS_G, PAR_H };
+
+// per-instance solver scalars
+enum { SD_COST = 0, SD_COST_PREV, SD_DV, SD_VIOL, SD_REG, SD_REG_USED, SD_UPD_PENALTY, SD_EPS_ACC, SD_N };
+enum { SI_STATUS = 0, SI_ITER_AL, SI_ITER_DDP, SI_DDP_ACTIVE, SI_REB_ON, SI_N_BWS, SI_N_FIT, SI_ACC_SLOT, SI_LS_DONE,
+       SI_AL_PARTIALS, SI_N_REC, SI_BWS_OK, SI_N };
+enum { STATUS_RUNNING = 0, STATUS_CONVERGED = 1, STATUS_MAXITER = 2, STATUS_REG_ABORT = 3 };
+constexpr int REC_I = 4, REC_D = 6;  // per-iteration record: ints {iter_AL, iter_DDP, n_bws, n_fit}, doubles {reg, eps, cost, dV, viol, cost_prev}
+
+struct Opt {  // HSDDP_OPTION<double>, MHPC_CompoundTypes.h:196-212
+    double alpha, gamma, update_penalty, update_relax, update_regularization, update_ReB, max_DDP_iter, max_AL_iter,
+        DDP_thresh, AL_thresh;
+    int AL_active, ReB_active, smooth_active;
+    double quu_shift;   // pow(0.1, 9)  (SinglePhase.cpp:202)
+};
+
+struct Dev {
+    int n, npad, nblk;  // instances, padded to 32, blocks of 32
+    int P;              // phase slots per instance
+    int KT;             // knot slots per instance
+    int W;              // line-search trial slots
+    int max_rec;        // iteration records per instance
+    // schedule
+    int *n_phases, *n_wb, *n_knots;     // [npad]
+    int *ph_mode, *ph_N, *ph_off;       // [P][npad]
+    int *rec_len;                       // [nblk][KT] doubles to pull per knot in the sweep
+    double *dt_wb, *dt_fb, *vel, *height;  // [npad]
+    double* x0;                         // [14][npad]
+    double* pos_ref;                    // [KT][npad]
+    // trajectories
+    double* st_nom;  // [KT][ST][npad]
+    double* st_act;  // [W][KT][ST][npad]
+    double* Kfb;     // [KT][56][npad]
+    double* dufb;    // [KT][4][npad]
+    double* Gv;      // [KT][14][npad]
+    double* lin;     // AoSoA records
+    // parameters and solver state
+    double* par;     // [P][NPAR][npad]
+    double* tr_cost; // [W][npad]
+    double* tr_viol2;// [W][npad]
+    double* tr_h;    // [W][P][npad]
+    double* sd;      // [SD_N][npad]
+    int* si;         // [SI_N][npad]
+    int* rec_i;      // [max_rec][REC_I][npad]
+    double* rec_d;   // [max_rec][REC_D][npad]
+    int* n_active;   // [1] device counter for optional host early exit
+};
+
+__host__ __device__ inline size_t st_idx(const Dev& d, int kk, int e, int i) { return ((size_t)kk * ST + e) * d.npad + i; }
+__host__ __device__ inline size_t act_idx(const Dev& d, int w, int kk, int e, int i) {
+    return (((size_t)w * d.KT + kk) * ST + e) * d.npad + i;
+}
+__host__ __device__ inline size_t lin_base(const Dev& d, int i, int kk) { return ((size_t)(i >> 5) * d.KT + kk) * REC * 32; }
+__host__ __device__ inline size_t lin_idx(const Dev& d, int i, int kk, int e) {
+    return lin_base(d, i, kk) + (size_t)e * 32 + ((i + e) & 31);
+}
+__host__ __device__ inline size_t par_idx(const Dev& d, int p, int q, int i) { return ((size_t)p * NPAR + q) * d.npad + i; }
+__host__ __device__ inline size_t ph_idx(const Dev& d, int p, int i) { return (size_t)p * d.npad + i; }
+
+// knot classes for the linearisation launches
+enum { CLS_BS = 0, CLS_FS, CLS_FL, CLS_IMPF, CLS_IMPB, CLS_LIGHT, CLS_N };
+
+// reference constants ---------------------------------------------------------------------
+#define MHPC_PI 3.141592653589793238  /* MHPC_CPPTypes.h:18 */
+
+}  // namespace mhpc

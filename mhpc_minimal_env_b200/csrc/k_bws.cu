@@ -1,0 +1,603 @@
+// Impact-aware Riccati backward sweep (MultiPhaseDDP.cpp:100-127, 300-341; SinglePhase.cpp:183-216;
+// MHPC_CompoundTypes.h:116-144) with the regularisation retry loop of MultiPhaseDDP::solve
+// (MultiPhaseDDP.cpp:209-227) folded in.
+//
+// One CTA = one AoSoA block of 32 instances = 16 warps; a half-warp owns one instance, lane r owns
+// row r of the value Hessian H (registers).  Time is sequential; every knot the CTA pulls one
+// contiguous record chunk (<= 45 KB) into shared memory with cp.async (double buffered, one
+// __syncthreads per knot) and each half-warp consumes its instance's elements from there.
+// The structure of the reference's matrices is used instead of dense 14x14 products:
+//   A = [I7  dt*I7 ; 0(7x2) Ab(7x12)],  B = [0 ; Bb],  C/D = two stance rows,  lxx/luu diagonal,
+// which removes only exact-zero / exact-one terms of the dense sums.
+#include <cuda_pipeline.h>
+
+#include "kernels.h"
+#include "model.cuh"
+
+namespace mhpc {
+
+constexpr int BWS_THREADS = 512;
+constexpr int MQ_LD = 15;
+// per-instance scratch (doubles)
+constexpr int S_G = 0;        // 16
+constexpr int S_MQ = 16;      // 14 x 15 : M = H*A, later Qxx for the symmetrisation
+constexpr int S_N = 226;      // 7 x 4  : rows 7..13 of H*B   (RB: 6 x 4)
+constexpr int S_QUX = 254;    // 4 x 14
+constexpr int S_QUU = 310;    // 16
+constexpr int S_QU = 326;     // 4
+constexpr int S_RA = 330;     // 36 dense RB A
+constexpr int S_RB = 366;     // 24 dense RB B
+constexpr int SCR = 391;
+constexpr size_t BWS_SMEM = (size_t)(2 * REC * 32 + SCR * 32) * sizeof(double);
+
+// Eigen::LDLT<>::isPositive() restated (diagonal pivoting on the largest |a_ii|, sign of D tracked;
+// Eigen/src/Cholesky/LDLT.h); call site SinglePhase.cpp:202-205.
+__device__ inline bool ldlt4_is_positive(double a[4][4]) {
+    int sign = 0;  // 0 zero, 1 pos, 2 neg, 3 indefinite
+    double temp[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        int pv = k;
+        double big = fabs(a[k][k]);
+#pragma unroll
+        for (int i = k + 1; i < 4; ++i)
+            if (fabs(a[i][i]) > big) { big = fabs(a[i][i]); pv = i; }
+        if (pv != k) {
+            for (int jj = 0; jj < k; ++jj) { double t = a[k][jj]; a[k][jj] = a[pv][jj]; a[pv][jj] = t; }
+            for (int i = pv + 1; i < 4; ++i) { double t = a[i][k]; a[i][k] = a[i][pv]; a[i][pv] = t; }
+            { double t = a[k][k]; a[k][k] = a[pv][pv]; a[pv][pv] = t; }
+            for (int i = k + 1; i < pv; ++i) { double t = a[i][k]; a[i][k] = a[pv][i]; a[pv][i] = t; }
+        }
+        if (k > 0) {
+            for (int jj = 0; jj < k; ++jj) temp[jj] = a[jj][jj] * a[k][jj];
+            double s = a[k][0] * temp[0];
+            for (int jj = 1; jj < k; ++jj) s += a[k][jj] * temp[jj];
+            a[k][k] -= s;
+            for (int i = k + 1; i < 4; ++i) {
+                double t = a[i][0] * temp[0];
+                for (int jj = 1; jj < k; ++jj) t += a[i][jj] * temp[jj];
+                a[i][k] -= t;
+            }
+        }
+        const double akk = a[k][k];
+        const bool valid = fabs(akk) > 0.0;
+        if (k == 0 && !valid) return true;
+        if (valid)
+            for (int i = k + 1; i < 4; ++i) a[i][k] /= akk;
+        if (sign == 1) { if (akk < 0) sign = 3; }
+        else if (sign == 2) { if (akk > 0) sign = 3; }
+        else if (sign == 0) { if (akk > 0) sign = 1; else if (akk < 0) sign = 2; }
+    }
+    return sign == 1 || sign == 0;
+}
+
+// Closed-form 4x4 inverse by cofactors (what Eigen's fixed-size Matrix4d::inverse() computes);
+// m and r are [row][col].
+__device__ inline void inverse4(const double m[4][4], double r[4][4]) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+            const int i1 = (i + 1) & 3, i2 = (i + 2) & 3, i3 = (i + 3) & 3;
+            const int j1 = (jj + 1) & 3, j2 = (jj + 2) & 3, j3 = (jj + 3) & 3;
+            const double cf = m[i1][j1] * (m[i2][j2] * m[i3][j3] - m[i2][j3] * m[i3][j2]) +
+                              m[i2][j1] * (m[i3][j2] * m[i1][j3] - m[i3][j3] * m[i1][j2]) +
+                              m[i3][j1] * (m[i1][j2] * m[i2][j3] - m[i1][j3] * m[i2][j2]);
+            r[jj][i] = ((i + jj) & 1) ? -cf : cf;
+        }
+    double det = m[0][0] * r[0][0];
+#pragma unroll
+    for (int i = 1; i < 4; ++i) det += m[i][0] * r[0][i];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) r[i][jj] /= det;
+}
+
+// value-function update shared by the WB and RB steps (MHPC_CompoundTypes.h:128-144).
+// In: Quu/Qu in scratch, this lane's Qux column qux[4], Qx value qx, symmetrised Qxx row in Hn[].
+// Out: Hn[] = H row, returns G entry; K column / du / dV written through the pointers.
+template <int NX>
+__device__ __forceinline__ bool value_update(bool on, int l, double* scr, const double qux[4], double qx, double Hn[14],
+                                             double quu_shift, double kcol[4], double du[4], double& Gout, double& dVstep) {
+    double Quu[4][4], Qu[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        Qu[c] = scr[S_QU + c];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) Quu[r][c] = scr[S_QUU + r + 4 * c];
+    }
+    double tst[4][4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) tst[r][c] = Quu[r][c] - (r == c ? 1.0 * quu_shift : 0.0);
+    const bool pd = ldlt4_is_positive(tst);
+    if (!pd) return false;
+    double inv[4][4], Qi[4][4];
+    inverse4(Quu, inv);
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) Qi[r][c] = (inv[r][c] + inv[c][r]) / 2;
+    double T[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        double s = (-Qi[c][0]) * qux[0], t = qux[0] * Qi[0][c], e = (-Qi[c][0]) * Qu[0];
+#pragma unroll
+        for (int cc = 1; cc < 4; ++cc) { s += (-Qi[c][cc]) * qux[cc]; t += qux[cc] * Qi[cc][c]; e += (-Qi[c][cc]) * Qu[cc]; }
+        kcol[c] = s; T[c] = t; du[c] = e;
+    }
+    double g = T[0] * Qu[0];
+#pragma unroll
+    for (int c = 1; c < 4; ++c) g += T[c] * Qu[c];
+    Gout = qx - g;
+    if (on && l < NX) {
+#pragma unroll
+        for (int jc = 0; jc < NX; ++jc) {
+            double s = T[0] * scr[S_QUX + jc];
+#pragma unroll
+            for (int c = 1; c < 4; ++c) s += T[c] * scr[S_QUX + c * 14 + jc];
+            Hn[jc] = Hn[jc] - s;
+        }
+    }
+    double tv[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        double s = (-Qu[0]) * inv[0][c];
+#pragma unroll
+        for (int cc = 1; cc < 4; ++cc) s += (-Qu[cc]) * inv[cc][c];
+        tv[c] = s;
+    }
+    double dv = tv[0] * Qu[0];
+#pragma unroll
+    for (int c = 1; c < 4; ++c) dv += tv[c] * Qu[c];
+    dVstep = dv;
+    return true;
+}
+
+__global__ void __launch_bounds__(BWS_THREADS, 1) k_bws(Dev d, Consts c, Opt opt, int mask_mode, int single_attempt) {
+    extern __shared__ __align__(16) double smem[];
+    double* buf0 = smem;
+    double* scr_all = smem + 2 * REC * 32;
+    const int tid = threadIdx.x;
+    const int hw = tid >> 4, l = tid & 15;          // half-warp = instance slot in the block, lane within
+    const int blk = blockIdx.x;
+    const int i = blk * 32 + hw;
+    const int j = hw;                                 // i & 31
+    double* scr = scr_all + (size_t)hw * SCR;
+    const size_t es = d.npad;
+    const bool valid = i < d.n;
+    bool enabled = valid && inst_enabled(d, i, mask_mode);
+    const int np = valid ? d.n_phases[i] : 0, nwb = valid ? d.n_wb[i] : 0, nk = valid ? d.n_knots[i] : 0;
+    const double dtw = valid ? d.dt_wb[i] : 0.0, dtf = valid ? d.dt_fb[i] : 0.0;
+    double reg = enabled ? d.sd[(size_t)SD_REG * es + i] : 0.0;
+    int n_bws = 1;
+    bool done = !enabled;
+    // knots to walk for this block
+    int ktb = 0;
+    {
+        __shared__ int s_ktb;
+        if (tid == 0) s_ktb = 0;
+        __syncthreads();
+        if (l == 0 && enabled) atomicMax(&s_ktb, nk);
+        __syncthreads();
+        ktb = s_ktb;
+    }
+    const int* rec_len = d.rec_len + (size_t)blk * d.KT;
+    const double* lin_blk = d.lin + (size_t)blk * d.KT * REC * 32;
+
+    while (true) {
+        // ---- one attempt -----------------------------------------------------------------
+        double Hn[14];
+#pragma unroll
+        for (int q = 0; q < 14; ++q) Hn[q] = 0.0;
+        if (l < 16) scr[S_G + l] = 0.0;
+        double dV = 0.0;
+        bool failed = false;
+        int p = np - 1;
+        int off = (enabled && np > 0) ? d.ph_off[ph_idx(d, p, i)] : 0;
+        int Nn = (enabled && np > 0) ? d.ph_N[ph_idx(d, p, i)] : 0;
+        int mode = (enabled && np > 0) ? d.ph_mode[ph_idx(d, p, i)] : 1;
+        __syncwarp();
+
+        if (ktb > 0) {  // prologue load
+            const int len = rec_len[ktb - 1] * 16;
+            const double* src = lin_blk + (size_t)(ktb - 1) * REC * 32;
+            for (int q = tid; q < len; q += BWS_THREADS) __pipeline_memcpy_async(buf0 + 2 * q, src + 2 * q, 16);
+            __pipeline_commit();
+        }
+        for (int it = 0; it < ktb; ++it) {
+            const int kk = ktb - 1 - it;
+            double* buf = buf0 + (size_t)(it & 1) * REC * 32;
+            double* nbuf = buf0 + (size_t)((it & 1) ^ 1) * REC * 32;
+            __pipeline_wait_prior(0);
+            const int alive = (!done && !failed) ? 1 : 0;
+            if (!__syncthreads_or(alive)) break;
+            if (kk > 0) {
+                const int len = rec_len[kk - 1] * 16;
+                const double* src = lin_blk + (size_t)(kk - 1) * REC * 32;
+                for (int q = tid; q < len; q += BWS_THREADS) __pipeline_memcpy_async(nbuf + 2 * q, src + 2 * q, 16);
+            }
+            __pipeline_commit();
+
+            // ---- which kind of knot is this for my instance? ----
+            int ty = 0;  // 0 idle, 1 WB step, 2 RB step, 3 WB terminal, 4 RB terminal
+            if (alive && kk < nk) {
+                while (kk < off) {
+                    --p;
+                    off = d.ph_off[ph_idx(d, p, i)]; Nn = d.ph_N[ph_idx(d, p, i)]; mode = d.ph_mode[ph_idx(d, p, i)];
+                }
+                const bool wb = p < nwb, term = (kk - off == Nn - 1);
+                ty = wb ? (term ? 3 : 1) : (term ? 4 : 2);
+            }
+            const int ty_o = __shfl_xor_sync(0xffffffffu, ty, 16);
+#define RBUF(e) buf[(size_t)(e) * 32 + ((j + (e)) & 31)]
+
+            // ============ terminal knots: value reset across the phase boundary ============
+            if (ty == 3 || ty_o == 3 || ty == 4 || ty_o == 4) {
+                const bool on = (ty == 3 || ty == 4);
+                const bool last = on && (p == np - 1);
+                const bool wbp = (ty == 3);
+                const bool next_rb = on && !last && (p + 1 >= nwb);
+                // (a) WB <- RB: embed the 6-dim value into 14 dims through P^T (.) P  (MultiPhaseDDP.cpp:330-331)
+                const bool embed = wbp && next_rb;
+                double g_old = 0.0;
+                if (embed) {
+                    if (l < 6) {
+#pragma unroll
+                        for (int q = 0; q < 6; ++q) scr[S_MQ + l * MQ_LD + q] = Hn[q];
+                    }
+                    const int pl = (l < 3) ? l : (l >= 7 && l < 10) ? l - 4 : -1;
+                    g_old = (pl >= 0) ? scr[S_G + pl] : 0.0;
+                }
+                __syncwarp();
+                if (embed) {
+                    const int pl = (l < 3) ? l : (l >= 7 && l < 10) ? l - 4 : -1;
+#pragma unroll
+                    for (int q = 0; q < 14; ++q) {
+                        const int pq = (q < 3) ? q : (q >= 7 && q < 10) ? q - 4 : -1;
+                        Hn[q] = (pl >= 0 && pq >= 0) ? scr[S_MQ + pl * MQ_LD + pq] : 0.0;
+                    }
+                }
+                __syncwarp();
+                if (embed && l < 14) scr[S_G + l] = g_old;
+                __syncwarp();
+                // (b) WB phase end: G = Px^T G', H = Px^T H' Px  (MultiPhaseDDP.cpp:320-326), Px = [I7 0; 0 Pb]
+                const bool px = wbp && !last;
+                if (px && l < 14) {
+#pragma unroll
+                    for (int jc = 0; jc < 14; ++jc) {
+                        double acc = (jc < 7) ? Hn[jc] : 0.0;
+                        if (jc >= 2) {
+#pragma unroll
+                            for (int s = 0; s < 7; ++s) acc += Hn[7 + s] * RBUF(R_AB(s, jc - 2));
+                        }
+                        scr[S_MQ + l * MQ_LD + jc] = acc;
+                    }
+                }
+                __syncwarp();
+                double g_new = 0.0;
+                if (px && l < 14) {
+                    double pb[7];
+#pragma unroll
+                    for (int s = 0; s < 7; ++s) pb[s] = (l >= 2) ? RBUF(R_AB(s, l - 2)) : 0.0;
+#pragma unroll
+                    for (int jc = 0; jc < 14; ++jc) {
+                        double acc = (l < 7) ? scr[S_MQ + l * MQ_LD + jc] : 0.0;
+                        if (l >= 2) {
+#pragma unroll
+                            for (int s = 0; s < 7; ++s) acc += pb[s] * scr[S_MQ + (7 + s) * MQ_LD + jc];
+                        }
+                        Hn[jc] = acc;
+                    }
+                    g_new = (l < 7) ? scr[S_G + l] : 0.0;
+                    if (l >= 2) {
+#pragma unroll
+                        for (int s = 0; s < 7; ++s) g_new += pb[s] * scr[S_G + 7 + s];
+                    }
+                }
+                __syncwarp();
+                if (px && l < 14) scr[S_G + l] = g_new;
+                __syncwarp();
+                // (c) terminal cost: G = Phix + Gnext, H = Phixx + Hnext  (SinglePhase.cpp:190-191)
+                if (on) {
+                    if (last) {
+#pragma unroll
+                        for (int q = 0; q < 14; ++q) Hn[q] = 0.0;
+                    }
+                    const int nx = wbp ? 14 : 6;
+                    if (l < nx) {
+                        double gv = last ? 0.0 : scr[S_G + l];
+                        if (wbp) {
+#pragma unroll
+                            for (int jc = 0; jc < 14; ++jc) {
+                                double ph = (jc == l) ? RBUF(R_PHIXXD + l) : 0.0;
+                                if (l >= 1 && l <= 6 && jc >= 1 && jc <= 6) ph = ph + RBUF(R_PHIXXB + (l - 1) + 6 * (jc - 1));
+                                Hn[jc] = ph + Hn[jc];
+                            }
+                            gv = RBUF(R_PHIX + l) + gv;
+                        } else {
+#pragma unroll
+                            for (int jc = 0; jc < 6; ++jc) Hn[jc] = ((jc == l) ? c.rbQf[l] : 0.0) + Hn[jc];
+                            gv = RBUF(R_RPHIX + l) + gv;
+                        }
+                        scr[S_G + l] = gv;
+                        d.Gv[((size_t)kk * 14 + l) * es + i] = gv;
+                    }
+                }
+                __syncwarp();
+            }
+
+            // ============ whole-body step ============
+            if (ty == 1 || ty_o == 1) {
+                const bool on = (ty == 1);
+                const double dt = dtw;
+                const int r0 = (mode == 1) ? 2 : 0;
+                if (on && l < 14) {
+#pragma unroll
+                    for (int jc = 0; jc < 14; ++jc) {   // M = H A
+                        double acc;
+                        if (jc < 2) acc = Hn[jc];
+                        else {
+                            acc = (jc < 7) ? Hn[jc] : Hn[jc - 7] * dt;
+#pragma unroll
+                            for (int s = 0; s < 7; ++s) acc += Hn[7 + s] * RBUF(R_AB(s, jc - 2));
+                        }
+                        scr[S_MQ + l * MQ_LD + jc] = acc;
+                    }
+                    if (l >= 7) {
+#pragma unroll
+                        for (int cc = 0; cc < 4; ++cc) {   // N = H B (rows 7..13 are all B^T N needs)
+                            double acc = Hn[7] * RBUF(R_BB(0, cc));
+#pragma unroll
+                            for (int s = 1; s < 7; ++s) acc += Hn[7 + s] * RBUF(R_BB(s, cc));
+                            scr[S_N + (l - 7) * 4 + cc] = acc;
+                        }
+                    }
+                }
+                __syncwarp();
+                double qux[4] = {0, 0, 0, 0}, qx = 0.0;
+                if (on) {
+                    const double L00 = RBUF(R_LYY), L01 = RBUF(R_LYY + 1), L11 = RBUF(R_LYY + 2);
+                    const double ly0 = RBUF(R_LY), ly1 = RBUF(R_LY + 1);
+                    if (l < 14) {
+                        double ab[7];
+#pragma unroll
+                        for (int s = 0; s < 7; ++s) ab[s] = (l >= 2) ? RBUF(R_AB(s, l - 2)) : 0.0;
+                        const double c0 = (l >= 2) ? RBUF(R_CB(0, l - 2)) : 0.0, c1 = (l >= 2) ? RBUF(R_CB(1, l - 2)) : 0.0;
+                        const double w0 = c0 * L00 + c1 * L01, w1 = c0 * L01 + c1 * L11;   // row l of C^T lyy
+                        const double lxxd = (l >= 3 && l < 7) ? RBUF(R_LXXQ + (l - 3)) : (2 * dt) * c.wbQ[l];
+#pragma unroll
+                        for (int jc = 0; jc < 14; ++jc) {   // Qxx row l = (lxx + C^T lyy C) + A^T M
+                            double q;
+                            if (l < 2) q = scr[S_MQ + l * MQ_LD + jc];
+                            else {
+                                q = (l < 7) ? scr[S_MQ + l * MQ_LD + jc] : scr[S_MQ + (l - 7) * MQ_LD + jc] * dt;
+#pragma unroll
+                                for (int s = 0; s < 7; ++s) q += ab[s] * scr[S_MQ + (7 + s) * MQ_LD + jc];
+                            }
+                            double lc = (jc == l) ? lxxd : 0.0;
+                            if (l >= 2 && jc >= 2) lc = lc + (w0 * RBUF(R_CB(0, jc - 2)) + w1 * RBUF(R_CB(1, jc - 2)));
+                            Hn[jc] = lc + q;
+                            if (jc == l) Hn[jc] += 1.0 * reg;
+                        }
+                        // Qx = (lx + A^T G) + C^T ly
+                        double ag;
+                        if (l < 2) ag = scr[S_G + l];
+                        else {
+                            ag = (l < 7) ? scr[S_G + l] : scr[S_G + l - 7] * dt;
+#pragma unroll
+                            for (int s = 0; s < 7; ++s) ag += ab[s] * scr[S_G + 7 + s];
+                        }
+                        qx = (RBUF(R_LX + l) + ag) + (c0 * ly0 + c1 * ly1);
+                        // Qux column l = (0 + D^T lyy C) + B^T M
+#pragma unroll
+                        for (int cc = 0; cc < 4; ++cc) {
+                            double acc = RBUF(R_BB(0, cc)) * scr[S_MQ + 7 * MQ_LD + l];
+#pragma unroll
+                            for (int s = 1; s < 7; ++s) acc += RBUF(R_BB(s, cc)) * scr[S_MQ + (7 + s) * MQ_LD + l];
+                            const double d0 = RBUF(R_DB(0, cc)), d1 = RBUF(R_DB(1, cc));
+                            const double v0 = d0 * L00 + d1 * L01, v1 = d0 * L01 + d1 * L11;
+                            qux[cc] = (0.0 + (v0 * c0 + v1 * c1)) + acc;
+                        }
+                    }
+                    {   // Quu entry (row l&3, col l>>2) = (luu + D^T lyy D) + B^T N
+                        const int rr = l & 3, cc = l >> 2;
+                        double acc = RBUF(R_BB(0, rr)) * scr[S_N + 0 * 4 + cc];
+#pragma unroll
+                        for (int s = 1; s < 7; ++s) acc += RBUF(R_BB(s, rr)) * scr[S_N + s * 4 + cc];
+                        const double d0 = RBUF(R_DB(0, rr)), d1 = RBUF(R_DB(1, rr));
+                        const double v0 = d0 * L00 + d1 * L01, v1 = d0 * L01 + d1 * L11;
+                        double q = ((rr == cc ? RBUF(R_LUU + rr) : 0.0) + (v0 * RBUF(R_DB(0, cc)) + v1 * RBUF(R_DB(1, cc)))) + acc;
+                        if (rr == cc) q += 1.0 * reg;
+                        scr[S_QUU + rr + 4 * cc] = q;
+                    }
+                    if (l < 4) {   // Qu = (lu + B^T G) + D^T ly
+                        double acc = RBUF(R_BB(0, l)) * scr[S_G + 7];
+#pragma unroll
+                        for (int s = 1; s < 7; ++s) acc += RBUF(R_BB(s, l)) * scr[S_G + 7 + s];
+                        scr[S_QU + l] = (RBUF(R_LU + l) + acc) + (RBUF(R_DB(0, l)) * ly0 + RBUF(R_DB(1, l)) * ly1);
+                    }
+                    (void)r0;
+                }
+                __syncwarp();   // everyone is done reading M
+                if (on && l < 14) {
+#pragma unroll
+                    for (int jc = 0; jc < 14; ++jc) scr[S_MQ + l * MQ_LD + jc] = Hn[jc];
+#pragma unroll
+                    for (int cc = 0; cc < 4; ++cc) scr[S_QUX + cc * 14 + l] = qux[cc];
+                }
+                __syncwarp();
+                if (on && l < 14) {
+#pragma unroll
+                    for (int jc = 0; jc < 14; ++jc) Hn[jc] = (Hn[jc] + scr[S_MQ + jc * MQ_LD + l]) / 2;   // Qxx = (Qxx + Qxx^T)/2
+                }
+                double kcol[4], du[4], gout = 0.0, dvs = 0.0;
+                bool ok = true;
+                if (on) ok = value_update<14>(on, l, scr, qux, qx, Hn, opt.quu_shift, kcol, du, gout, dvs);
+                __syncwarp();
+                if (on) {
+                    if (!ok) failed = true;
+                    else {
+                        dV += dvs;
+                        if (l < 14) {
+                            scr[S_G + l] = gout;
+                            d.Gv[((size_t)kk * 14 + l) * es + i] = gout;
+#pragma unroll
+                            for (int cc = 0; cc < 4; ++cc) d.Kfb[((size_t)kk * KDIM + cc + 4 * l) * es + i] = kcol[cc];
+                        }
+                        if (l < 4) d.dufb[((size_t)kk * 4 + l) * es + i] = du[l];
+                    }
+                }
+                __syncwarp();
+            }
+
+            // ============ rigid-body step (dense 6x6) ============
+            if (ty == 2 || ty_o == 2) {
+                const bool on = (ty == 2);
+                const double dt = dtf;
+                if (on) {   // build dense A (6x6, column-major) and B (6x4) from the record
+                    for (int q = l; q < 36; q += 16) {
+                        const int r = q % 6, cc = q / 6;
+                        double v = (r == cc) ? 1.0 : 0.0;
+                        if (cc == r + 3 && r < 3) v = 1.0 * dt;       // Ac(0,3)=Ac(1,4)=Ac(2,5)=1
+                        if (r == 5 && cc < 2) v = RBUF(R_RA + cc);
+                        scr[S_RA + q] = v;
+                    }
+                    for (int q = l; q < 24; q += 16) scr[S_RB + q] = 0.0;
+                }
+                __syncwarp();
+                if (on && l < 8) {
+                    const int rows[8] = {3, 5, 4, 5, 3, 5, 4, 5}, cols[8] = {0, 0, 1, 1, 2, 2, 3, 3};
+                    scr[S_RB + rows[l] + 6 * cols[l]] = RBUF(R_RB + l);
+                }
+                __syncwarp();
+                if (on && l < 6) {
+#pragma unroll
+                    for (int jc = 0; jc < 6; ++jc) {
+                        double acc = Hn[0] * scr[S_RA + 0 + 6 * jc];
+#pragma unroll
+                        for (int k2 = 1; k2 < 6; ++k2) acc += Hn[k2] * scr[S_RA + k2 + 6 * jc];
+                        scr[S_MQ + l * MQ_LD + jc] = acc;
+                    }
+#pragma unroll
+                    for (int cc = 0; cc < 4; ++cc) {
+                        double acc = Hn[0] * scr[S_RB + 0 + 6 * cc];
+#pragma unroll
+                        for (int k2 = 1; k2 < 6; ++k2) acc += Hn[k2] * scr[S_RB + k2 + 6 * cc];
+                        scr[S_N + l * 4 + cc] = acc;
+                    }
+                }
+                __syncwarp();
+                double qux[4] = {0, 0, 0, 0}, qx = 0.0;
+                if (on) {
+                    if (l < 6) {
+#pragma unroll
+                        for (int jc = 0; jc < 6; ++jc) {
+                            double q = scr[S_RA + 0 + 6 * l] * scr[S_MQ + 0 * MQ_LD + jc];
+#pragma unroll
+                            for (int k2 = 1; k2 < 6; ++k2) q += scr[S_RA + k2 + 6 * l] * scr[S_MQ + k2 * MQ_LD + jc];
+                            Hn[jc] = ((jc == l) ? (2 * dt) * c.rbQ[l] : 0.0) + q;
+                            if (jc == l) Hn[jc] += 1.0 * reg;
+                        }
+                        double ag = scr[S_RA + 0 + 6 * l] * scr[S_G + 0];
+#pragma unroll
+                        for (int k2 = 1; k2 < 6; ++k2) ag += scr[S_RA + k2 + 6 * l] * scr[S_G + k2];
+                        qx = RBUF(R_RLX + l) + ag;
+#pragma unroll
+                        for (int cc = 0; cc < 4; ++cc) {
+                            double acc = scr[S_RB + 0 + 6 * cc] * scr[S_MQ + 0 * MQ_LD + l];
+#pragma unroll
+                            for (int k2 = 1; k2 < 6; ++k2) acc += scr[S_RB + k2 + 6 * cc] * scr[S_MQ + k2 * MQ_LD + l];
+                            qux[cc] = acc;
+                        }
+                    }
+                    {
+                        const int rr = l & 3, cc = l >> 2;
+                        double acc = scr[S_RB + 0 + 6 * rr] * scr[S_N + 0 * 4 + cc];
+#pragma unroll
+                        for (int k2 = 1; k2 < 6; ++k2) acc += scr[S_RB + k2 + 6 * rr] * scr[S_N + k2 * 4 + cc];
+                        double q = ((rr == cc) ? (2 * dt) * c.rbR[mode - 1][rr] : 0.0) + acc;
+                        if (rr == cc) q += 1.0 * reg;
+                        scr[S_QUU + rr + 4 * cc] = q;
+                    }
+                    if (l < 4) {
+                        double acc = scr[S_RB + 0 + 6 * l] * scr[S_G + 0];
+#pragma unroll
+                        for (int k2 = 1; k2 < 6; ++k2) acc += scr[S_RB + k2 + 6 * l] * scr[S_G + k2];
+                        scr[S_QU + l] = RBUF(R_RLU + l) + acc;
+                    }
+                }
+                __syncwarp();
+                if (on && l < 6) {
+#pragma unroll
+                    for (int jc = 0; jc < 6; ++jc) scr[S_MQ + l * MQ_LD + jc] = Hn[jc];
+#pragma unroll
+                    for (int cc = 0; cc < 4; ++cc) scr[S_QUX + cc * 14 + l] = qux[cc];
+                }
+                __syncwarp();
+                if (on && l < 6) {
+#pragma unroll
+                    for (int jc = 0; jc < 6; ++jc) Hn[jc] = (Hn[jc] + scr[S_MQ + jc * MQ_LD + l]) / 2;
+                }
+                double kcol[4], du[4], gout = 0.0, dvs = 0.0;
+                bool ok = true;
+                if (on) ok = value_update<6>(on, l, scr, qux, qx, Hn, opt.quu_shift, kcol, du, gout, dvs);
+                __syncwarp();
+                if (on) {
+                    if (!ok) failed = true;
+                    else {
+                        dV += dvs;
+                        if (l < 6) {
+                            scr[S_G + l] = gout;
+                            d.Gv[((size_t)kk * 14 + l) * es + i] = gout;
+#pragma unroll
+                            for (int cc = 0; cc < 4; ++cc) d.Kfb[((size_t)kk * KDIM + cc + 4 * l) * es + i] = kcol[cc];
+                        }
+                        if (l < 4) d.dufb[((size_t)kk * 4 + l) * es + i] = du[l];
+                    }
+                }
+                __syncwarp();
+            }
+#undef RBUF
+        }
+        __pipeline_wait_prior(0);
+        __syncthreads();
+
+        // ---- outcome of the attempt (MultiPhaseDDP.cpp:209-241) ----
+        int retry = 0;
+        if (!done) {
+            if (single_attempt) {
+                if (l == 0) { d.si[(size_t)SI_BWS_OK * es + i] = failed ? 0 : 1; if (!failed) d.sd[(size_t)SD_DV * es + i] = dV; }
+                done = true;
+            } else if (failed) {
+                reg = fmax(reg * opt.update_regularization, 1e-03);
+                ++n_bws;
+                if (reg > 1000) {
+                    if (l == 0) { d.si[(size_t)SI_STATUS * es + i] = STATUS_REG_ABORT; d.si[(size_t)SI_DDP_ACTIVE * es + i] = 0; d.si[(size_t)SI_N_BWS * es + i] = n_bws; }
+                    done = true;
+                } else retry = 1;
+            } else {
+                if (l == 0) {
+                    d.sd[(size_t)SD_DV * es + i] = dV;
+                    d.sd[(size_t)SD_REG_USED * es + i] = reg;
+                    double r2 = reg / 20;
+                    if (r2 < 1e-06) r2 = 0;
+                    d.sd[(size_t)SD_REG * es + i] = r2;
+                    d.si[(size_t)SI_N_BWS * es + i] = n_bws;
+                    d.si[(size_t)SI_BWS_OK * es + i] = 1;
+                }
+                done = true;
+            }
+        }
+        if (!__syncthreads_or(retry)) break;
+    }
+}
+
+void launch_bws(const Dev& d, const Consts& c, const Opt& opt, int mask_mode, int single_attempt, cudaStream_t s) {
+    cudaFuncSetAttribute(k_bws, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BWS_SMEM);
+    k_bws<<<d.nblk, BWS_THREADS, BWS_SMEM, s>>>(d, c, opt, mask_mode, single_attempt);
+}
+
+}  // namespace mhpc

@@ -1,0 +1,287 @@
+// Linearisation ("forward_sweep_partials_only", SinglePhase.cpp:147-180, and the derivative half of
+// forward_sweep, :82-111): one thread per (knot, instance), lanes = 32 consecutive instances.
+// Compiled once per knot class (-DLIN_CLS=...) so the large generated Jacobian bodies build in
+// parallel and each gets its own register allocation:
+//   CLS_BS / CLS_FS / CLS_FL   whole-body step knots: Dyn_{BS,FS,FL}_par + Euler A,B (PlanarQuadruped.cpp:30-53)
+//                              + running-cost derivatives (CostBase.cpp:19-34) + barrier derivatives (SinglePhase.cpp:239-246)
+//   CLS_IMPF / CLS_IMPB        whole-body terminal knots of flight phases: terminal cost derivatives (CostBase.cpp:50-60),
+//                              touchdown constraint + AL terms (MHPCConstraints.cpp:91-107, SinglePhase.cpp:257-275),
+//                              impact Jacobian Px (PlanarQuadruped.cpp:82-100, used by MultiPhaseDDP.cpp:320)
+//   CLS_LIGHT                  stance-phase terminal knots (Px = I), rigid-body step and terminal knots
+// Every thread writes one knot record of the AoSoA `lin` array (common.cuh).
+#include "kernels.h"
+#include "model.cuh"
+
+#ifndef LIN_CLS
+#error "compile with -DLIN_CLS=<knot class>"
+#endif
+
+namespace mhpc {
+namespace {
+
+#define REC_AT(e) rec[(size_t)(e) * 32 + ((j + (e)) & 31)]
+
+template <int K, int ROW, int COL>
+__device__ __forceinline__ void wb_par_out(double* __restrict__ rec, int j, double dt, double v) {
+    if (K == 0) {
+        if (ROW >= 7) REC_AT(R_AB(ROW - 7, COL - 2)) = (ROW == COL ? 1.0 : 0.0) + v * dt;   // A = I + Ac*dt
+    } else if (K == 1) {
+        REC_AT(R_BB(ROW - 7, COL)) = v * dt;                                                // B = Bc*dt
+    } else if (K == 2) {
+        REC_AT(R_CB(ROW & 1, COL - 2)) = v;
+    } else {
+        REC_AT(R_DB(ROW & 1, COL)) = v;
+    }
+}
+template <int ROW, int COL>
+__device__ __forceinline__ void imp_par_out(double* __restrict__ rec, int j, double v) {
+    if (ROW >= 7) REC_AT(R_AB(ROW - 7, COL - 2)) = v;
+}
+
+#define SX_IN(i, j_) ((i) == 0 ? x[j_] : u[j_])
+#define SX_OUT(k, nz, row, col, v) wb_par_out<k, row, col>(rec, j, dt, v)
+#if LIN_CLS == 0
+__device__ __forceinline__ void dyn_par(const double* x, const double* u, double* __restrict__ rec, int j, double dt) {
+#include "gen/Dyn_BS_par.inc"
+}
+#elif LIN_CLS == 1
+__device__ __forceinline__ void dyn_par(const double* x, const double* u, double* __restrict__ rec, int j, double dt) {
+#include "gen/Dyn_FS_par.inc"
+}
+#elif LIN_CLS == 2
+__device__ __forceinline__ void dyn_par(const double* x, const double* u, double* __restrict__ rec, int j, double dt) {
+#include "gen/Dyn_FL_par.inc"
+}
+#endif
+#undef SX_OUT
+#undef SX_IN
+#define SX_IN(i, j_) (x[j_])
+#define SX_OUT(k, nz, row, col, v) imp_par_out<row, col>(rec, j, v)
+#if LIN_CLS == 3
+__device__ __forceinline__ void imp_par(const double* x, double* __restrict__ rec, int j) {
+#include "gen/Imp_F_par.inc"
+}
+#elif LIN_CLS == 4
+__device__ __forceinline__ void imp_par(const double* x, double* __restrict__ rec, int j) {
+#include "gen/Imp_B_par.inc"
+}
+#endif
+#undef SX_OUT
+#undef SX_IN
+
+// running-cost derivatives of a WB step knot, with barrier terms when `reb` (SinglePhase.cpp:219-249)
+__device__ inline void wb_cost_partials(const Consts& c, int mode, double dt, const double* x, const double* u, const double* y,
+                                        double pos, double vel, double height, bool reb, const double* par,
+                                        double* __restrict__ rec, int j) {
+    const double two_dt = 2 * dt;
+    double lx[14], lu[4], lxxq[4], luu[4];
+#pragma unroll
+    for (int i = 0; i < 14; ++i) lx[i] = (two_dt * c.wbQ[i]) * (x[i] - wb_xref(c, i, pos, vel, height));
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { lu[i] = (two_dt * c.wbR[mode - 1][i]) * (u[i] - 0.0); luu[i] = two_dt * c.wbR[mode - 1][i]; lxxq[i] = two_dt * c.wbQ[3 + i]; }
+    const int r0 = (mode == 1) ? 2 : 0;  // stance rows of y (mode 3: rows 0,1); flight: unused
+    double ly2[2] = {0.0, 0.0}, lyy[3] = {0.0, 0.0, 0.0};
+    if (mode == 1 || mode == 3) {
+        ly2[0] = (two_dt * c.wbS[mode - 1][r0]) * (y[r0] - grf_ref(c, r0));
+        ly2[1] = (two_dt * c.wbS[mode - 1][r0 + 1]) * (y[r0 + 1] - grf_ref(c, r0 + 1));
+        lyy[0] = two_dt * c.wbS[mode - 1][r0];
+        lyy[2] = two_dt * c.wbS[mode - 1][r0 + 1];
+    }
+    if (reb) {
+        double b, bz, bzz;
+        const double dT = par[0], dJ = par[1], dG = par[2], eT = par[3], eJ = par[4], eG = par[5];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {  // torque rows: g = -/+u + 33, gu = -/+1
+            const double sgn = (i < 4) ? -1.0 : 1.0;
+            const int a = i & 3;
+            reb_eval(sgn * u[a] + c.btorque, dT, b, bz, bzz);
+            lu[a] += ((eT * bz) * sgn) * dt;
+            luu[a] += (eT * ((sgn * bzz) * sgn + bz * 0.0)) * dt;
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {  // joint rows: g = -/+q + b, gx = -/+1 on q[3:7]
+            const double sgn = (i < 4) ? -1.0 : 1.0;
+            const int a = i & 3;
+            reb_eval(sgn * x[3 + a] + c.bjoint[i], dJ, b, bz, bzz);
+            lx[3 + a] += ((eJ * bz) * sgn) * dt;
+            lxxq[a] += (eJ * ((sgn * bzz) * sgn + bz * 0.0)) * dt;
+        }
+        if (mode == 1 || mode == 3) {  // GRF rows on the stance foot: Fz >= 0, -/+Fx + mu Fz >= 0
+            const double fx = y[r0], fz = y[r0 + 1];
+            const double gy[3][2] = {{0.0, 1.0}, {-1.0, c.mu}, {1.0, c.mu}};
+            const double g3[3] = {fz, -fx + c.mu * fz, fx + c.mu * fz};
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                reb_eval(g3[i], dG, b, bz, bzz);
+                ly2[0] += ((eG * bz) * gy[i][0]) * dt;
+                ly2[1] += ((eG * bz) * gy[i][1]) * dt;
+                lyy[0] += (eG * ((gy[i][0] * bzz) * gy[i][0] + bz * 0.0)) * dt;
+                lyy[1] += (eG * ((gy[i][0] * bzz) * gy[i][1] + bz * 0.0)) * dt;
+                lyy[2] += (eG * ((gy[i][1] * bzz) * gy[i][1] + bz * 0.0)) * dt;
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 14; ++i) REC_AT(R_LX + i) = lx[i];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { REC_AT(R_LU + i) = lu[i]; REC_AT(R_LXXQ + i) = lxxq[i]; REC_AT(R_LUU + i) = luu[i]; }
+    REC_AT(R_LY) = ly2[0]; REC_AT(R_LY + 1) = ly2[1];
+    REC_AT(R_LYY) = lyy[0]; REC_AT(R_LYY + 1) = lyy[1]; REC_AT(R_LYY + 2) = lyy[2];
+}
+
+__global__ void __launch_bounds__(128) k_lin(Dev d, Consts c, Opt opt, int mask_mode, const int* __restrict__ knots) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= d.n) return;
+    if (!inst_enabled(d, i, mask_mode)) return;
+    const int kk = knots[blockIdx.y];
+    int p, k;
+    if (!knot_to_phase(d, i, kk, p, k)) return;
+    const int mode = d.ph_mode[ph_idx(d, p, i)], N = d.ph_N[ph_idx(d, p, i)];
+    const bool wb = p < d.n_wb[i];
+    const bool term = (k == N - 1);
+    // classify
+    int cls;
+    if (wb && !term) cls = (mode == 1) ? CLS_BS : (mode == 3) ? CLS_FS : CLS_FL;
+    else if (wb && term && mode == 2) cls = CLS_IMPF;
+    else if (wb && term && mode == 4) cls = CLS_IMPB;
+    else cls = CLS_LIGHT;
+    if (cls != LIN_CLS) return;
+
+    const int j = i & 31;
+    double* __restrict__ rec = d.lin + lin_base(d, i, kk);
+    const int slot = d.si[(size_t)SI_ACC_SLOT * d.npad + i];
+    const double* st = d.st_act + act_idx(d, slot, kk, 0, i);
+    const size_t es = d.npad;
+    const double vel = d.vel[i], height = d.height[i];
+    const double pos = d.pos_ref[(size_t)kk * es + i];
+    const int lin_mode = d.si[(size_t)SI_AL_PARTIALS * d.npad + i];  // 2: derivatives of a full forward sweep (AL terms enter Phix/Phixx)
+
+#if LIN_CLS <= 2
+    {
+        const double dt = d.dt_wb[i];
+        double x[14], u[4], y[4];
+#pragma unroll
+        for (int e = 0; e < 14; ++e) x[e] = st[e * es];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { u[e] = st[(14 + e) * es]; y[e] = st[(18 + e) * es]; }
+        dyn_par(x, u, rec, j, dt);
+#if LIN_CLS == 2
+#pragma unroll
+        for (int e = R_CB(0, 0); e < R_LX; ++e) REC_AT(e) = 0.0;   // C = D = 0 in flight
+#endif
+        const bool reb = d.si[(size_t)SI_REB_ON * d.npad + i] != 0;
+        double par[6];
+#pragma unroll
+        for (int q = 0; q < 6; ++q) par[q] = d.par[par_idx(d, p, PAR_DELTA_T + q, i)];
+        wb_cost_partials(c, mode, dt, x, u, y, pos, vel, height, reb, par, rec, j);
+    }
+#elif LIN_CLS <= 4
+    {
+        double x[14];
+#pragma unroll
+        for (int e = 0; e < 14; ++e) x[e] = st[e * es];
+        imp_par(x, rec, j);
+        // terminal cost derivatives: Phix = Qf dx, Phixx = Qf  (CostBase.cpp:58-59)
+#pragma unroll
+        for (int e = 0; e < 14; ++e) {
+            REC_AT(R_PHIX + e) = c.wbQf[mode - 1][e] * (x[e] - wb_xref_term(c, mode, e, pos, vel));
+            REC_AT(R_PHIXXD + e) = c.wbQf[mode - 1][e];
+        }
+        double blk[36];
+#pragma unroll
+        for (int q = 0; q < 36; ++q) blk[q] = 0.0;
+        if (lin_mode == 2 && opt.AL_active) {   // only the full forward sweep adds the AL terms
+            double h, hx[14], hxx[196];
+#pragma unroll
+            for (int q = 0; q < 14; ++q) hx[q] = 0.0;
+#pragma unroll
+            for (int q = 0; q < 196; ++q) hxx[q] = 0.0;
+#if LIN_CLS == 3
+            tconstr_fl1(x, &h, hx, hxx);
+#else
+            tconstr_fl2(x, &h, hx, hxx);
+#endif
+            const double sigma = d.par[par_idx(d, p, PAR_SIGMA, i)], lam = d.par[par_idx(d, p, PAR_LAMBDA, i)];
+            const double s2 = sigma * sigma / 2;
+#pragma unroll
+            for (int a = 1; a <= 6; ++a) {
+                const double add = 50 * (s2 * hx[a] * h + lam * hx[a]);
+                REC_AT(R_PHIX + a) = c.wbQf[mode - 1][a] * (x[a] - wb_xref_term(c, mode, a, pos, vel)) + add;
+            }
+#pragma unroll
+            for (int b = 1; b <= 6; ++b)
+#pragma unroll
+                for (int a = 1; a <= 6; ++a)
+                    blk[(a - 1) + 6 * (b - 1)] = 50 * (s2 * (hx[a] * hx[b] + h * hxx[a + 14 * b]) + lam * hxx[a + 14 * b]);
+        }
+#pragma unroll
+        for (int q = 0; q < 36; ++q) REC_AT(R_PHIXXB + q) = blk[q];
+    }
+#else
+    if (wb) {  // stance-phase terminal knot: Px = I, no terminal constraint
+        double x[14];
+#pragma unroll
+        for (int e = 0; e < 14; ++e) x[e] = st[e * es];
+#pragma unroll
+        for (int cc = 0; cc < 12; ++cc)
+#pragma unroll
+            for (int s = 0; s < 7; ++s) REC_AT(R_AB(s, cc)) = (cc == s + 5) ? 1.0 : 0.0;
+#pragma unroll
+        for (int e = 0; e < 14; ++e) {
+            REC_AT(R_PHIX + e) = c.wbQf[mode - 1][e] * (x[e] - wb_xref_term(c, mode, e, pos, vel));
+            REC_AT(R_PHIXXD + e) = c.wbQf[mode - 1][e];
+        }
+#pragma unroll
+        for (int q = 0; q < 36; ++q) REC_AT(R_PHIXXB + q) = 0.0;
+    } else if (!term) {
+        const double dt = d.dt_fb[i];
+        const int off = d.ph_off[ph_idx(d, p, i)];
+        double x[6], u[4], x0p[3], fh[4], ct[2], a2[2], b8[8];
+#pragma unroll
+        for (int e = 0; e < 6; ++e) x[e] = st[e * es];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) u[e] = st[(14 + e) * es];
+        const double* st0 = d.st_act + act_idx(d, slot, off, 0, i);   // phase-initial state (SinglePhase.cpp:150-153)
+#pragma unroll
+        for (int e = 0; e < 3; ++e) x0p[e] = st0[e * es];
+        rb_foothold(c, mode, x0p, dt * (double)N, fh);
+        rb_contact(mode, ct);
+        fb_dyn_par(x, u, fh, ct, a2, b8);
+        REC_AT(R_RA) = a2[0] * dt; REC_AT(R_RA + 1) = a2[1] * dt;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) REC_AT(R_RB + q) = b8[q] * dt;
+        const double two_dt = 2 * dt;
+#pragma unroll
+        for (int e = 0; e < 6; ++e) REC_AT(R_RLX + e) = (two_dt * c.rbQ[e]) * (x[e] - rb_xref(e, pos, vel, height));
+#pragma unroll
+        for (int e = 0; e < 4; ++e) REC_AT(R_RLU + e) = (two_dt * c.rbR[mode - 1][e]) * (u[e] - grf_ref(c, e));
+    } else {
+#pragma unroll
+        for (int e = 0; e < 6; ++e) REC_AT(R_RPHIX + e) = c.rbQf[e] * (st[e * es] - rb_xref(e, pos, vel, height));
+    }
+#endif
+}
+
+}  // anonymous namespace
+
+#if LIN_CLS == 0
+#define LIN_LAUNCH launch_lin_BS
+#elif LIN_CLS == 1
+#define LIN_LAUNCH launch_lin_FS
+#elif LIN_CLS == 2
+#define LIN_LAUNCH launch_lin_FL
+#elif LIN_CLS == 3
+#define LIN_LAUNCH launch_lin_IMPF
+#elif LIN_CLS == 4
+#define LIN_LAUNCH launch_lin_IMPB
+#else
+#define LIN_LAUNCH launch_lin_LIGHT
+#endif
+
+void LIN_LAUNCH(const Dev& d, const Consts& c, const Opt& opt, int mask_mode, const int* knots, int n_knots, cudaStream_t s) {
+    if (n_knots <= 0) return;
+    dim3 grid((d.n + 127) / 128, n_knots);
+    k_lin<<<grid, 128, 0, s>>>(d, c, opt, mask_mode, knots);
+}
+
+}  // namespace mhpc

