@@ -79,7 +79,7 @@ __global__ void __launch_bounds__(128) k_warmstart(Dev d, Consts c) {
     const int nwb = d.n_wb[i];
     const double dt = d.dt_wb[i];
     const size_t es = d.npad;
-    double* act = d.st_act + act_idx(d, 0, 0, 0, i);
+    double* act = d.st_act;
     double x[14];
 #pragma unroll
     for (int e = 0; e < 14; ++e) x[e] = d.x0[(size_t)e * es + i];

@@ -17,7 +17,7 @@ __global__ void __launch_bounds__(128) k_rollout(Dev d, Consts c, Opt opt, int m
     const bool reb = d.si[(size_t)SI_REB_ON * d.npad + i] != 0;
     const double vel = d.vel[i], height = d.height[i];
     const int np = d.n_phases[i], nwb = d.n_wb[i];
-    double* act = d.st_act + act_idx(d, w, 0, 0, i);
+    double* act = d.st_act + act_idx(d, w, 0, 0, 0);
     const size_t es = d.npad;  // element stride
 
     double x[14];
