@@ -1,0 +1,302 @@
+#!/usr/bin/env python
+"""bench.py - batched MHPC solves/sec on B200 (BASELINE.json metric), one JSON line on stdout.
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--instances 4096]
+
+Workload (config.workload): 4096 independent MHPC instances per GPU, default gait and 4 WB + 4 RB phase split,
+seeded perturbed initial states (SURVEY.md 8(d) config-2 generator, seed 20260101), a FIXED HSDDP budget of
+max_AL_iter x max_DDP_iter = 2 x 3 inner iterations (DDP_thresh = AL_thresh = -1: never converge early).
+A "step" = MHPCLocomotion::initialization() + solve_mhpc() of the whole batch.  All arithmetic FP64.
+
+value : solves/s with the problems resident in HBM (device-timed, CUDA events, max over ranks)
+e2e   : solves/s through the host-facing call mhpc_batch_solve_host: problems from pinned host memory (H2D), solve,
+        results + the first `exec_knots` knots of the execution bag back to the host (D2H), all inside the timed region
+roofline     : the linearisation launch group (dominant FP64 kernel family) against a DFMA peak measured live
+cpu_baseline : the oracle (CPU restatement around the reference's generated C) on one host core, bounded sample
+--impl reference : the same oracle on all host cores (multiprocessing), bounded sample per step
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+METRIC = "batched MHPC solves/sec (4096 inst, fixed HSDDP iters)"
+UNIT = "solves/s"
+# algorithmic flops of one default-horizon linearisation (158 stance + 198 flight WB knots, 356 RB, 2 impacts)
+LIN_FLOP_PER_INSTANCE = 6896848.0
+# bytes the backward sweep must move per instance (records in + K,du,G out), default horizon: 356 WB step records (175 dbl),
+# 4 WB terminal (148), 352 RB step (20), 4 RB terminal (6) read; 712 x (56+4+14) written
+BWS_BYTES_PER_INSTANCE = 8.0 * (356 * 175 + 4 * 148 + 352 * 20 + 4 * 6 + 712 * 74)
+OPT_KW = dict(DDP_thresh=-1.0, AL_thresh=-1.0)
+
+
+def workload_name(n):
+    return (f"{n} instances/GPU, default bounding gait, 4 WB + 4 RB phases (720 knots), perturbed x0 (seed 20260101), "
+            "fixed 2x3 HSDDP iterations; step = initialization + solve")
+
+
+class ClockSampler(threading.Thread):
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], False
+
+    def run(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = sorted(float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit())
+        mx = [float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for k, n in enumerate(names) if any(len(r) > 2 + k and r[2 + k].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(self.rows)}
+
+
+def _oracle_solve_chunk(args):
+    specs_idx, variant = args
+    from helpers import to_orc_problem
+    from oracle.oracle_py import OracleSolver
+    t = time.perf_counter()
+    for i in specs_idx:
+        spec = _spec_of(i)
+        s = OracleSolver(to_orc_problem(spec, **OPT_KW), variant=variant)
+        s.initialization()
+        s.solve()
+    return time.perf_counter() - t
+
+
+def _spec_of(i):
+    from helpers import perturbed_x0
+    return dict(n_wbphase=4, n_fbphase=4, dt_wb=0.001, dt_fb=0.001, cmode=1, vel=1.5, height=0.0,
+                gait_mode=[1, 2, 3, 4], gait_timing=[0.08, 0.1, 0.08, 0.1], x0=perturbed_x0(i))
+
+
+def cpu_baseline_single(sample):
+    """oracle, one core, first `sample` instances of the workload."""
+    t = _oracle_solve_chunk((list(range(sample)), "fast"))
+    return sample / t
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU algorithm (oracle port) on all host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    import multiprocessing as mp
+    from oracle.oracle_py import build
+    build("fast")
+    cores = os.cpu_count() or 1
+    per_core = max(1, args.ref_sample // cores)
+    sample = per_core * cores
+    chunks = [(list(range(c * per_core, (c + 1) * per_core)), "fast") for c in range(cores)]
+    times = []
+    with mp.get_context("fork").Pool(cores) as pool:
+        for it in range(args.warmup + args.steps):
+            t0 = time.perf_counter()
+            pool.map(_oracle_solve_chunk, chunks)
+            dt = time.perf_counter() - t0
+            if it >= args.warmup:
+                times.append(dt)
+    ms = 1e3 * sum(times) / len(times)
+    value = sample / (ms * 1e-3)
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload_name(args.instances) + f" [CPU arm: {sample} of these instances per step]"},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": f"{sample} instances per step ({per_core} per core), oracle -O3 -mavx2 -mfma build"},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours")
+    ap.add_argument("--instances", type=int, default=4096, help="instances per GPU")
+    ap.add_argument("--exec-knots", type=int, default=10, help="knots of the execution bag returned by the e2e call")
+    ap.add_argument("--cpu-sample", type=int, default=256)
+    ap.add_argument("--ref-sample", type=int, default=256)
+    ap.add_argument("--ls-width", type=int, default=8)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    args.warmup = max(args.warmup, 3)
+
+    import numpy as np
+    import torch
+    import mhpc_minimal_env_b200 as m
+    from helpers import make_specs, to_gpu_problem
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback for the product path)")
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    n = args.instances
+    # shard the job by instance: rank r owns global instances [r*n, (r+1)*n)  (no collective inside the solve)
+    specs = [_spec_of(rank * n + i) for i in range(n)]
+    problems = [to_gpu_problem(s) for s in specs]
+    opt = m.default_option(**OPT_KW)
+    batch = m.BatchedMHPC(problems, opt, device=local, ls_width=args.ls_width)
+    stream = torch.cuda.Stream()          # a real (non-NULL) stream shared by the library and the CUDA events below
+    torch.cuda.set_stream(stream)
+    batch.set_stream(stream.cuda_stream)
+
+    def step():
+        batch.initialization()
+        batch.solve()
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        step()
+    e1.record(stream)
+    barrier()
+    ms_total = e0.elapsed_time(e1)
+    t = torch.tensor([ms_total], device="cuda", dtype=torch.float64)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_per_step = float(t.item()) / args.steps
+    value = n * world / (ms_per_step * 1e-3)
+
+    # final result gather (the only communication of the job): per-rank result table -> every rank, over NCCL
+    res_arr = batch.results_array()
+    npad = (n + 31) // 32 * 32
+    table = torch.zeros(6 * npad, device="cuda", dtype=torch.float64)
+    batch.results_to_device(table.data_ptr(), table.numel())
+    torch.cuda.synchronize()
+    if dist is not None:
+        gathered = [torch.zeros_like(table) for _ in range(world)]
+        dist.all_gather(gathered, table)
+        n_ok = int(sum((g.view(6, npad)[3, :n] == 2).sum().item() for g in gathered))
+    else:
+        n_ok = int((table.view(6, npad)[3, :n] == 2).sum().item())
+
+    # ---- end-to-end through the host-facing call, host buffers, copies inside the timed region ----
+    import ctypes as C
+    from mhpc_minimal_env_b200.capi import Problem, Result
+    ek = args.exec_knots
+    pin_p = torch.empty(n * C.sizeof(Problem), dtype=torch.uint8).pin_memory()
+    C.memmove(pin_p.data_ptr(), C.addressof(batch._problems), n * C.sizeof(Problem))
+    pin_r = torch.empty(n * C.sizeof(Result), dtype=torch.uint8).pin_memory()
+    pin_s = torch.empty(n * ek * 22, dtype=torch.float64).pin_memory()
+    pin_g = torch.empty(n * ek * 60, dtype=torch.float64).pin_memory()
+    L = m.load()
+    dp = C.POINTER(C.c_double)
+
+    def e2e_step():
+        rc = L.mhpc_batch_solve_host(batch.h, C.cast(pin_p.data_ptr(), C.POINTER(Problem)), C.cast(pin_r.data_ptr(), C.POINTER(Result)),
+                                     2, C.cast(pin_s.data_ptr(), dp), C.cast(pin_g.data_ptr(), dp), ek)
+        if rc < 0:
+            raise RuntimeError(L.mhpc_last_error().decode())
+
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    e2e_steps = max(2, min(args.steps, 5))
+    for _ in range(e2e_steps):
+        e2e_step()
+    torch.cuda.synchronize()
+    t_e2e = torch.tensor([(time.perf_counter() - t0) / e2e_steps], device="cuda", dtype=torch.float64)
+    if dist is not None:
+        dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+    e2e_value = n * world / float(t_e2e.item())
+    h2d = n * C.sizeof(Problem)
+    d2h = n * C.sizeof(Result) + n * ek * (22 + 60) * 8
+
+    line = None
+    if rank == 0:
+        # ---- per-kernel-family timing and rooflines (rank 0 only, outside the timed region) ----
+        batch.enable_timing(True)
+        step()
+        batch.synchronize()
+        tm = batch.timing()
+        batch.enable_timing(False)
+        lin_ms = batch.time_kernel(0, 5)
+        bws_ms = batch.time_kernel(1, 3)
+        fp64_peak = m.measure_fp64_peak(local)
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        lin_tflops = LIN_FLOP_PER_INSTANCE * n / (lin_ms * 1e-3) / 1e12
+        bws_gbs = BWS_BYTES_PER_INSTANCE * n / (bws_ms * 1e-3) / 1e9
+        roofline = {"kernel": "k_lin (linearisation launch group: Dyn_{BS,FS,FL}_par, Imp_{F,B}_par, light knots)",
+                    "bound": "fp64", "achieved": lin_tflops, "peak": fp64_peak, "unit": "TFLOP/s", "frac": lin_tflops / fp64_peak,
+                    "traffic": None, "ms_per_launch": lin_ms,
+                    "peak_source": "FP64 FMA probe measured live on this GPU (MEASURED_PEAKS.json has no FP64 entry)",
+                    "us_per_horizon_linearize": 1e3 * lin_ms / n}
+        roofline_bws = {"kernel": "k_bws (impact-aware Riccati sweep, one attempt)", "bound": "hbm", "achieved": bws_gbs, "peak": hbm_peak,
+                        "unit": "GB/s", "frac": bws_gbs / hbm_peak, "traffic": None, "ms_per_launch": bws_ms,
+                        "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s"}
+        cpu_v = cpu_baseline_single(args.cpu_sample)
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+                "data": "synthetic",
+                "config": {"workload": workload_name(n), "instances_per_gpu": n, "hsddp_budget": "2x3 (DDP_thresh=AL_thresh=-1)",
+                           "ls_width": args.ls_width, "l2": "working set (>10 GB/GPU) far exceeds the 126 MB L2; no explicit flush",
+                           "sharding": "by instance, contiguous blocks per rank, one final NCCL all_gather of the result table"},
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                        "note": f"mhpc_batch_solve_host: pinned host problems in, results + first {ek} knots of x,u,y,K,du out"},
+                "gpu_launches": int(tm["n_launches"] + 3) * args.steps,
+                "clocks": sampler.summary(),
+                "roofline": roofline, "roofline_bws": roofline_bws,
+                "stage_ms": {k: tm[k] for k in ("total_ms", "rollout_ms", "linearize_ms", "bws_ms", "linesearch_ms", "other_ms")},
+                "cpu_baseline": {"value": cpu_v, "unit": UNIT, "cores": 1, "kind": "port",
+                                 "sample": f"first {args.cpu_sample} instances of the workload, oracle (-O3 -mavx2 -mfma), one core; "
+                                           f"host has {os.cpu_count()} cores -> x{os.cpu_count()} = {cpu_v * (os.cpu_count() or 1):.1f} solves/s if it scaled perfectly"},
+                "solves_finished": n_ok, "device_bytes": batch.device_bytes()}
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

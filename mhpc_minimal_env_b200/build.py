@@ -26,10 +26,13 @@ NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xptxas", "-v", "--expt-relaxed-constexpr"]
 
+# resident 128-thread blocks per SM the Jacobian kernels are compiled for (register cap = 65536 / (128 * LIN_MINBLOCKS))
+LIN_MINBLOCKS = int(os.environ.get("MHPC_LIN_MINBLOCKS", "4"))
+
 # (source, object name, extra defines)
 UNITS = [("capi.cu", "capi.o", []), ("k_misc.cu", "k_misc.o", []), ("k_rollout.cu", "k_rollout.o", []),
          ("k_bws.cu", "k_bws.o", []), ("k_eval.cu", "k_eval.o", [])] + \
-        [("k_lin.cu", f"k_lin_{c}.o", [f"-DLIN_CLS={c}"] + (["-Xptxas", "-O1"] if c < 5 else [])) for c in range(6)]
+        [("k_lin.cu", f"k_lin_{c}.o", [f"-DLIN_CLS={c}"] + (["-Xptxas", "-O1", f"-DLIN_MINBLOCKS={LIN_MINBLOCKS}"] if c < 5 else [])) for c in range(6)]
 # ptxas -O3 degenerates on the 26k-node Jacobian bodies (32 registers, ~100 KB of spill stores per thread);
 # at -O1 it keeps the generator's instruction order and allocates 255 registers (~24 KB of spill stores).
 
@@ -74,7 +77,7 @@ def build(ref: str = "/root/reference", force: bool = False, verbose: bool = Tru
     srcs += [os.path.join(GEN, f) for f in os.listdir(GEN) if f.endswith(".inc")]
     srcs += [os.path.join(HERE, "..", "include", "mhpc_b200.h"), os.path.abspath(__file__)]
     stamp = os.path.join(OBJ, "stamp.txt")
-    dig = _digest(srcs)
+    dig = _digest(srcs) + f":mb{LIN_MINBLOCKS}"
     if not force and os.path.exists(LIB) and os.path.exists(stamp) and open(stamp).read() == dig:
         if verbose:
             print(f"[build] up to date: {LIB}")

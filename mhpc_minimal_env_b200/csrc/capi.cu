@@ -51,6 +51,8 @@ struct mhpc_batch {
     std::vector<Ev> evs;
     mhpc_timing last{};
     int launches = 0;
+    void* stage = nullptr;
+    size_t stage_bytes = 0;
 };
 
 static void fill_opt(Opt& o, const mhpc_hsddp_option& s) {
@@ -179,6 +181,7 @@ void mhpc_batch_destroy(mhpc_batch* b) {
     cudaSetDevice(b->device);
     cudaStreamSynchronize(b->stream);
     free_all(b);
+    if (b->stage) cudaFree(b->stage);
     for (auto& e : b->evs) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
     if (b->own_stream && b->stream) cudaStreamDestroy(b->stream);
     delete b;
@@ -214,6 +217,7 @@ int mhpc_batch_set_problems(mhpc_batch* b, const mhpc_problem* pr) {
         if (np > MAXP) return fail("set_problems: too many phases");
         P = std::max(P, np);
     }
+    const std::vector<int> old_nph = b->h_nph, old_nwb = b->h_nwb, old_mode = b->h_mode, old_N = b->h_N;
     b->h_nph.assign(npad, 0); b->h_nwb.assign(npad, 0); b->h_nk.assign(npad, 0);
     b->h_mode.assign((size_t)P * npad, 1); b->h_N.assign((size_t)P * npad, 0); b->h_off.assign((size_t)P * npad, 0);
     std::vector<double> dtw(npad, 0), dtf(npad, 0), vel(npad, 0), hgt(npad, 0), x0((size_t)14 * npad, 0);
@@ -237,6 +241,19 @@ int mhpc_batch_set_problems(mhpc_batch* b, const mhpc_problem* pr) {
         KT = std::max(KT, off);
         for (int e = 0; e < 14; ++e) x0[(size_t)e * npad + i] = q.x0[e];
     }
+    // same schedule as the previous batch (the common MPC case): only the per-instance scalars change
+    const bool same_schedule = b->have_problems && b->d.npad == npad && b->d.P == P && old_nph == b->h_nph && old_nwb == b->h_nwb &&
+                               old_mode == b->h_mode && old_N == b->h_N;
+    auto upload_scalars = [&]() -> int {
+        Dev& d = b->d;
+        auto up = [&](void* dst, const void* src, size_t bytes) { return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, b->stream); };
+        CK(up(d.dt_wb, dtw.data(), npad * sizeof(double))); CK(up(d.dt_fb, dtf.data(), npad * sizeof(double)));
+        CK(up(d.vel, vel.data(), npad * sizeof(double))); CK(up(d.height, hgt.data(), npad * sizeof(double)));
+        CK(up(d.x0, x0.data(), (size_t)14 * npad * sizeof(double)));
+        CK(cudaStreamSynchronize(b->stream));   // host vectors go out of scope
+        return 0;
+    };
+    if (same_schedule) return upload_scalars();
     // (re)allocate when the shape grows
     if (!b->have_problems || KT > b->alloc_KT || P > b->alloc_P || b->d.npad != npad) {
         CK(cudaStreamSynchronize(b->stream));
@@ -307,10 +324,7 @@ int mhpc_batch_set_problems(mhpc_batch* b, const mhpc_problem* pr) {
         CK(up(d.ph_N + (size_t)p * npad, b->h_N.data() + (size_t)p * npad, npad * sizeof(int)));
         CK(up(d.ph_off + (size_t)p * npad, b->h_off.data() + (size_t)p * npad, npad * sizeof(int)));
     }
-    CK(up(d.dt_wb, dtw.data(), npad * sizeof(double))); CK(up(d.dt_fb, dtf.data(), npad * sizeof(double)));
-    CK(up(d.vel, vel.data(), npad * sizeof(double))); CK(up(d.height, hgt.data(), npad * sizeof(double)));
-    CK(up(d.x0, x0.data(), (size_t)14 * npad * sizeof(double)));
-    CK(cudaStreamSynchronize(b->stream));   // host vectors go out of scope
+    if (upload_scalars()) return -1;
     b->have_problems = true;
     return 0;
 }
@@ -713,6 +727,25 @@ int mhpc_batch_get_field(mhpc_batch* b, int inst, int phase, int field, double* 
     return dim;
 }
 
+// execution bag (MHPCLocomotion.cpp:178-194): nominal x,u,y and K,du of the leading knots, instance-major
+__global__ void k_gather_exec(Dev d, int kn, double* st_out, double* gain_out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= d.n) return;
+    const int k = blockIdx.y;
+    if (st_out) for (int e = 0; e < ST; ++e) st_out[((size_t)i * kn + k) * ST + e] = d.st_nom[((size_t)k * ST + e) * d.npad + i];
+    if (gain_out) {
+        for (int e = 0; e < KDIM; ++e) gain_out[((size_t)i * kn + k) * 60 + e] = d.Kfb[((size_t)k * KDIM + e) * d.npad + i];
+        for (int e = 0; e < 4; ++e) gain_out[((size_t)i * kn + k) * 60 + 56 + e] = d.dufb[((size_t)k * 4 + e) * d.npad + i];
+    }
+}
+__global__ void k_results_pack(Dev d, mhpc_result* out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= d.n) return;
+    mhpc_result r;
+    r.cost = d.sd[(size_t)SD_COST * d.npad + i]; r.exp_cost_change = d.sd[(size_t)SD_DV * d.npad + i]; r.viol = d.sd[(size_t)SD_VIOL * d.npad + i];
+    r.status = d.si[(size_t)SI_STATUS * d.npad + i]; r.iter_AL = d.si[(size_t)SI_ITER_AL * d.npad + i]; r.n_records = d.si[(size_t)SI_N_REC * d.npad + i]; r.pad = 0;
+    out[i] = r;
+}
 __global__ void k_results_table(Dev d, double* out) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= d.npad) return;
@@ -738,27 +771,27 @@ int mhpc_batch_solve_host(mhpc_batch* b, const mhpc_problem* problems, mhpc_resu
     if (mhpc_batch_set_problems(b, problems)) return -1;
     if (mhpc_batch_initialization(b)) return -1;
     if (mhpc_batch_solve(b, 0)) return -1;
-    if (results && mhpc_batch_get_results(b, results)) return -1;
-    if (exec_phases > 0 && exec_knots > 0 && (exec_state || exec_gain)) {
-        // execution bag (MHPCLocomotion.cpp:178-194): nominal x,u,y and K,du of the leading knots, instance-major on the host
-        const Dev& d = b->d;
-        const int kn = std::min(exec_knots, d.KT);
-        std::vector<double> st((size_t)kn * ST * d.npad), kf((size_t)kn * KDIM * d.npad), du((size_t)kn * 4 * d.npad);
-        if (exec_state) CK(cudaMemcpyAsync(st.data(), d.st_nom, st.size() * sizeof(double), cudaMemcpyDeviceToHost, b->stream));
-        if (exec_gain) {
-            CK(cudaMemcpyAsync(kf.data(), d.Kfb, kf.size() * sizeof(double), cudaMemcpyDeviceToHost, b->stream));
-            CK(cudaMemcpyAsync(du.data(), d.dufb, du.size() * sizeof(double), cudaMemcpyDeviceToHost, b->stream));
-        }
-        CK(cudaStreamSynchronize(b->stream));
-        for (int i = 0; i < b->n; ++i)
-            for (int k = 0; k < kn; ++k) {
-                if (exec_state) for (int e = 0; e < ST; ++e) exec_state[((size_t)i * exec_knots + k) * ST + e] = st[((size_t)k * ST + e) * d.npad + i];
-                if (exec_gain) {
-                    for (int e = 0; e < KDIM; ++e) exec_gain[((size_t)i * exec_knots + k) * 60 + e] = kf[((size_t)k * KDIM + e) * d.npad + i];
-                    for (int e = 0; e < 4; ++e) exec_gain[((size_t)i * exec_knots + k) * 60 + 56 + e] = du[((size_t)k * 4 + e) * d.npad + i];
-                }
-            }
+    const Dev& d = b->d;
+    const int kn = (exec_phases > 0 && exec_knots > 0) ? std::min(exec_knots, d.KT) : 0;
+    // staging buffers (device): packed results + instance-major execution bag, one contiguous D2H each
+    const size_t need_res = (size_t)b->n * sizeof(mhpc_result);
+    const size_t need_st = exec_state ? (size_t)b->n * kn * ST * sizeof(double) : 0, need_gn = exec_gain ? (size_t)b->n * kn * 60 * sizeof(double) : 0;
+    if (b->stage_bytes < need_res + need_st + need_gn) {
+        if (b->stage) cudaFree(b->stage);
+        CK(cudaMalloc(&b->stage, need_res + need_st + need_gn));
+        b->stage_bytes = need_res + need_st + need_gn;
     }
+    char* base = (char*)b->stage;
+    mhpc_result* dres = (mhpc_result*)base;
+    double* dst = exec_state && kn ? (double*)(base + need_res) : nullptr;
+    double* dgn = exec_gain && kn ? (double*)(base + need_res + need_st) : nullptr;
+    if (results) k_results_pack<<<(b->n + 127) / 128, 128, 0, b->stream>>>(d, dres);
+    if (kn && (dst || dgn)) { dim3 g((b->n + 127) / 128, kn); k_gather_exec<<<g, 128, 0, b->stream>>>(d, kn, dst, dgn); }
+    if (results) CK(cudaMemcpyAsync(results, dres, need_res, cudaMemcpyDeviceToHost, b->stream));
+    if (dst) CK(cudaMemcpyAsync(exec_state, dst, need_st, cudaMemcpyDeviceToHost, b->stream));
+    if (dgn) CK(cudaMemcpyAsync(exec_gain, dgn, need_gn, cudaMemcpyDeviceToHost, b->stream));
+    CK(cudaStreamSynchronize(b->stream));
+    CK(cudaGetLastError());
     return 0;
 }
 

@@ -9,6 +9,8 @@
 //                              impact Jacobian Px (PlanarQuadruped.cpp:82-100, used by MultiPhaseDDP.cpp:320)
 //   CLS_LIGHT                  stance-phase terminal knots (Px = I), rigid-body step and terminal knots
 // Every thread writes one knot record of the AoSoA `lin` array (common.cuh).
+#include <stdlib.h>
+
 #include "kernels.h"
 #include "model.cuh"
 
@@ -129,7 +131,10 @@ __device__ inline void wb_cost_partials(const Consts& c, int mode, double dt, co
     REC_AT(R_LYY) = lyy[0]; REC_AT(R_LYY + 1) = lyy[1]; REC_AT(R_LYY + 2) = lyy[2];
 }
 
-__global__ void __launch_bounds__(128) k_lin(Dev d, Consts c, Opt opt, int mask_mode, const int* __restrict__ knots) {
+#ifndef LIN_MINBLOCKS
+#define LIN_MINBLOCKS 1
+#endif
+__global__ void __launch_bounds__(128, LIN_MINBLOCKS) k_lin(Dev d, Consts c, Opt opt, int mask_mode, const int* __restrict__ knots) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= d.n) return;
     if (!inst_enabled(d, i, mask_mode)) return;
@@ -280,8 +285,18 @@ __global__ void __launch_bounds__(128) k_lin(Dev d, Consts c, Opt opt, int mask_
 
 void LIN_LAUNCH(const Dev& d, const Consts& c, const Opt& opt, int mask_mode, const int* knots, int n_knots, cudaStream_t s) {
     if (n_knots <= 0) return;
-    dim3 grid((d.n + 127) / 128, n_knots);
-    k_lin<<<grid, 128, 0, s>>>(d, c, opt, mask_mode, knots);
+    // Residency throttle for the spill-heavy Jacobian bodies: the per-thread local-memory frame is several KB, so the
+    // number of resident threads decides whether spills stay in L1/L2 or go to HBM.  (block size, dynamic smem padding)
+    static int threads = 0, pad = 0;
+    if (!threads) {
+        const char* t = getenv("MHPC_LIN_THREADS");
+        const char* q = getenv("MHPC_LIN_SMEM");
+        threads = t ? atoi(t) : 128;
+        pad = q ? atoi(q) : 0;
+        if (pad > 48 * 1024) cudaFuncSetAttribute(k_lin, cudaFuncAttributeMaxDynamicSharedMemorySize, pad);
+    }
+    dim3 grid((d.n + threads - 1) / threads, n_knots);
+    k_lin<<<grid, threads, pad, s>>>(d, c, opt, mask_mode, knots);
 }
 
 }  // namespace mhpc

@@ -1,0 +1,11 @@
+"""dev: time the linearisation / sweep / rollout launches for a given residency setting (env MHPC_LIN_THREADS/SMEM)."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+import mhpc_minimal_env_b200 as m
+from helpers import make_specs, to_gpu_problem
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
+b = m.BatchedMHPC([to_gpu_problem(s) for s in make_specs(n, 2)], m.default_option(DDP_thresh=-1.0, AL_thresh=-1.0))
+b.initialization(); b.solve(); b.synchronize()
+print("threads", os.environ.get("MHPC_LIN_THREADS"), "smem", os.environ.get("MHPC_LIN_SMEM"),
+      "lin ms", round(b.time_kernel(0, 3), 3), "bws ms", round(b.time_kernel(1, 2), 3), "rollout8 ms", round(b.time_kernel(2, 2), 3), flush=True)
