@@ -266,7 +266,6 @@ int mhpc_batch_set_problems(mhpc_batch* b, const mhpc_problem* pr) {
         int rc = 0;
         rc |= dalloc(b, &d.n_phases, npad); rc |= dalloc(b, &d.n_wb, npad); rc |= dalloc(b, &d.n_knots, npad);
         rc |= dalloc(b, &d.ph_mode, (size_t)P * npad); rc |= dalloc(b, &d.ph_N, (size_t)P * npad); rc |= dalloc(b, &d.ph_off, (size_t)P * npad);
-        rc |= dalloc(b, &d.rec_len, (size_t)nblk * KT);
         rc |= dalloc(b, &d.dt_wb, npad); rc |= dalloc(b, &d.dt_fb, npad); rc |= dalloc(b, &d.vel, npad); rc |= dalloc(b, &d.height, npad);
         rc |= dalloc(b, &d.x0, (size_t)14 * npad);
         rc |= dalloc(b, &d.pos_ref, (size_t)KT * npad);
@@ -275,7 +274,7 @@ int mhpc_batch_set_problems(mhpc_batch* b, const mhpc_problem* pr) {
         rc |= dalloc(b, &d.Kfb, (size_t)KT * KDIM * npad);
         rc |= dalloc(b, &d.dufb, (size_t)KT * 4 * npad);
         rc |= dalloc(b, &d.Gv, (size_t)KT * 14 * npad);
-        rc |= dalloc(b, &d.lin, (size_t)nblk * KT * REC * 32);
+        rc |= dalloc(b, &d.lin, (size_t)npad * KT * REC);
         rc |= dalloc(b, &d.par, (size_t)P * NPAR * npad);
         rc |= dalloc(b, &d.tr_cost, (size_t)d.W * npad); rc |= dalloc(b, &d.tr_viol2, (size_t)d.W * npad);
         rc |= dalloc(b, &d.tr_h, (size_t)d.W * P * npad);
@@ -288,7 +287,6 @@ int mhpc_batch_set_problems(mhpc_batch* b, const mhpc_problem* pr) {
     }
     Dev& d = b->d;
     // record lengths per (block, knot) and knot lists per class
-    std::vector<int> rec_len((size_t)nblk * d.KT, 0);
     std::set<int> cls_knots[CLS_N];
     for (int i = 0; i < n; ++i) {
         const int np = b->h_nph[i], nwb = b->h_nwb[i];
@@ -297,18 +295,14 @@ int mhpc_batch_set_problems(mhpc_batch* b, const mhpc_problem* pr) {
             const bool wb = p < nwb;
             for (int k = 0; k < N; ++k) {
                 const bool term = (k == N - 1);
-                int len, cls;
-                if (wb && !term) { len = WB_STEP_LEN; cls = mode == 1 ? CLS_BS : mode == 3 ? CLS_FS : CLS_FL; }
-                else if (wb) { len = WB_TERM_LEN; cls = mode == 2 ? CLS_IMPF : mode == 4 ? CLS_IMPB : CLS_LIGHT; }
-                else if (!term) { len = RB_STEP_LEN; cls = CLS_LIGHT; }
-                else { len = RB_TERM_LEN; cls = CLS_LIGHT; }
-                int& r = rec_len[(size_t)(i >> 5) * d.KT + off + k];
-                r = std::max(r, len);
+                int cls;
+                if (wb && !term) cls = mode == 1 ? CLS_BS : mode == 3 ? CLS_FS : CLS_FL;
+                else if (wb) cls = mode == 2 ? CLS_IMPF : mode == 4 ? CLS_IMPB : CLS_LIGHT;
+                else cls = CLS_LIGHT;
                 cls_knots[cls].insert(off + k);
             }
         }
     }
-    CK(cudaMemcpyAsync(d.rec_len, rec_len.data(), rec_len.size() * sizeof(int), cudaMemcpyHostToDevice, b->stream));
     for (int c = 0; c < CLS_N; ++c) {
         std::vector<int> v(cls_knots[c].begin(), cls_knots[c].end());
         b->knot_cnt[c] = (int)v.size();
@@ -358,7 +352,7 @@ int mhpc_batch_initialization(mhpc_batch* b) {
     CK(cudaMemsetAsync(d.Kfb, 0, (size_t)d.KT * KDIM * d.npad * sizeof(double), b->stream));
     CK(cudaMemsetAsync(d.dufb, 0, (size_t)d.KT * 4 * d.npad * sizeof(double), b->stream));
     CK(cudaMemsetAsync(d.Gv, 0, (size_t)d.KT * 14 * d.npad * sizeof(double), b->stream));
-    CK(cudaMemsetAsync(d.lin, 0, (size_t)d.nblk * d.KT * REC * 32 * sizeof(double), b->stream));
+    CK(cudaMemsetAsync(d.lin, 0, (size_t)d.npad * d.KT * REC * sizeof(double), b->stream));
     launch_setup(d, b->c, b->stream);                 // build_problem: references + AL/ReB parameters
     launch_warmstart(d, b->c, b->stream);             // warmstart()
     launch_copy_nominal(d, MASK_ALL, b->stream);      // update_nominal_trajectory()
@@ -651,11 +645,8 @@ int mhpc_batch_get_field(mhpc_batch* b, int inst, int phase, int field, double* 
     // fields decoded from the AoSoA knot records
     std::vector<double> recs((size_t)N * REC);
     {
-        const double* base = d.lin + lin_base(d, inst, off);
-        std::vector<double> blk((size_t)N * REC * 32);
-        CK(cudaMemcpyAsync(blk.data(), base, blk.size() * sizeof(double), cudaMemcpyDeviceToHost, b->stream));
+        CK(cudaMemcpyAsync(recs.data(), d.lin + lin_base(d, inst, off), recs.size() * sizeof(double), cudaMemcpyDeviceToHost, b->stream));
         CK(cudaStreamSynchronize(b->stream));
-        for (int k = 0; k < N; ++k) for (int e = 0; e < REC; ++e) recs[(size_t)k * REC + e] = blk[((size_t)k * REC + e) * 32 + ((inst + e) & 31)];
     }
     auto R = [&](int k, int e) { return recs[(size_t)k * REC + e]; };
     const int r0 = (mode == 1) ? 2 : 0;

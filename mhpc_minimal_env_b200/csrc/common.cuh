@@ -3,12 +3,10 @@
 // Trajectory-type data is structure-of-arrays over instances so that the
 // thread-per-instance kernels (rollout, linearise, line-search select) coalesce:
 //     st[(knot * ST + e) * npad + inst]          e: 0..13 x | 14..17 u | 18..21 y
-// Per-knot linearisation records are AoSoA in blocks of 32 instances so that the writer
-// (lane = instance) stores full 256 B rows and the backward sweep (one CTA = the same 32
-// instances) pulls one contiguous chunk per knot into shared memory:
-//     lin[((blk * KT + knot) * REC + e) * 32 + ((j + e) & 31)]      j = inst & 31
-// (the (j + e) rotation makes both the per-instance gather and the broadcast reads of the
-// sweep conflict-free in shared memory).
+// Per-knot linearisation records are array-of-structures, one contiguous 1408 B record per
+// (instance, knot), so that the backward sweep (a half-warp per instance) streams its instance's
+// records with 16-byte cp.async into warp-private shared memory, one knot ahead of the math:
+//     lin[(inst * KT + knot) * REC + e]
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -78,7 +76,6 @@ struct Dev {
     // schedule
     int *n_phases, *n_wb, *n_knots;     // [npad]
     int *ph_mode, *ph_N, *ph_off;       // [P][npad]
-    int *rec_len;                       // [nblk][KT] doubles to pull per knot in the sweep
     double *dt_wb, *dt_fb, *vel, *height;  // [npad]
     double* x0;                         // [14][npad]
     double* pos_ref;                    // [KT][npad]
@@ -105,10 +102,7 @@ __host__ __device__ inline size_t st_idx(const Dev& d, int kk, int e, int i) { r
 __host__ __device__ inline size_t act_idx(const Dev& d, int w, int kk, int e, int i) {
     return (((size_t)w * d.KT + kk) * ST + e) * d.npad + i;
 }
-__host__ __device__ inline size_t lin_base(const Dev& d, int i, int kk) { return ((size_t)(i >> 5) * d.KT + kk) * REC * 32; }
-__host__ __device__ inline size_t lin_idx(const Dev& d, int i, int kk, int e) {
-    return lin_base(d, i, kk) + (size_t)e * 32 + ((i + e) & 31);
-}
+__host__ __device__ inline size_t lin_base(const Dev& d, int i, int kk) { return ((size_t)i * d.KT + kk) * REC; }
 __host__ __device__ inline size_t par_idx(const Dev& d, int p, int q, int i) { return ((size_t)p * NPAR + q) * d.npad + i; }
 __host__ __device__ inline size_t ph_idx(const Dev& d, int p, int i) { return (size_t)p * d.npad + i; }
 

@@ -2,10 +2,10 @@
 // MHPC_CompoundTypes.h:116-144) with the regularisation retry loop of MultiPhaseDDP::solve
 // (MultiPhaseDDP.cpp:209-227) folded in.
 //
-// One CTA = one AoSoA block of 32 instances = 16 warps; a half-warp owns one instance, lane r owns
-// row r of the value Hessian H (registers).  Time is sequential; every knot the CTA pulls one
-// contiguous record chunk (<= 45 KB) into shared memory with cp.async (double buffered, one
-// __syncthreads per knot) and each half-warp consumes its instance's elements from there.
+// A half-warp owns one instance, lane r owns row r of the value Hessian H (registers).  Time is
+// sequential; every warp streams the knot records of its two instances into warp-private shared
+// memory with 16-byte cp.async, one knot ahead of the math (double buffered, synchronised with
+// __syncwarp only: warps never wait for each other, there is no CTA barrier in the sweep).
 // The structure of the reference's matrices is used instead of dense 14x14 products:
 //   A = [I7  dt*I7 ; 0(7x2) Ab(7x12)],  B = [0 ; Bb],  C/D = two stance rows,  lxx/luu diagonal,
 // which removes only exact-zero / exact-one terms of the dense sums.
@@ -16,7 +16,8 @@
 
 namespace mhpc {
 
-constexpr int BWS_THREADS = 512;
+constexpr int BWS_THREADS = 128;             // 4 warps = 8 instances per CTA
+constexpr int BWS_INST = BWS_THREADS / 16;
 constexpr int MQ_LD = 15;
 // per-instance scratch (doubles)
 constexpr int S_G = 0;        // 16
@@ -28,7 +29,7 @@ constexpr int S_QU = 326;     // 4
 constexpr int S_RA = 330;     // 36 dense RB A
 constexpr int S_RB = 366;     // 24 dense RB B
 constexpr int SCR = 391;
-constexpr size_t BWS_SMEM = (size_t)(2 * REC * 32 + SCR * 32) * sizeof(double);
+constexpr size_t BWS_SMEM = (size_t)(2 * REC + SCR + 1) * BWS_INST * sizeof(double);
 
 // Eigen::LDLT<>::isPositive() restated (diagonal pivoting on the largest |a_ii|, sign of D tracked;
 // Eigen/src/Cholesky/LDLT.h); call site SinglePhase.cpp:202-205.
@@ -156,83 +157,84 @@ __device__ __forceinline__ bool value_update(bool on, int l, double* scr, const 
     return true;
 }
 
-__global__ void __launch_bounds__(BWS_THREADS, 1) k_bws(Dev d, Consts c, Opt opt, int mask_mode, int single_attempt) {
+__device__ __forceinline__ int knot_rec_len(bool wb, bool term) {
+    return wb ? (term ? WB_TERM_LEN : WB_STEP_LEN) : (term ? RB_TERM_LEN : RB_STEP_LEN);
+}
+
+__global__ void __launch_bounds__(BWS_THREADS, 4) k_bws(Dev d, Consts c, Opt opt, int mask_mode, int single_attempt) {
     extern __shared__ __align__(16) double smem[];
-    double* buf0 = smem;
-    double* scr_all = smem + 2 * REC * 32;
     const int tid = threadIdx.x;
-    const int hw = tid >> 4, l = tid & 15;          // half-warp = instance slot in the block, lane within
-    const int blk = blockIdx.x;
-    const int i = blk * 32 + hw;
-    const int j = hw;                                 // i & 31
-    double* scr = scr_all + (size_t)hw * SCR;
+    const int hw = tid >> 4, l = tid & 15;          // half-warp = instance slot in the CTA, lane within
+    const int i = blockIdx.x * BWS_INST + hw;
+    double* bufs = smem + (size_t)hw * 2 * REC;                        // [2 stages][REC] of my instance
+    double* scr = smem + (size_t)BWS_INST * 2 * REC + (size_t)hw * SCR;
     const size_t es = d.npad;
     const bool valid = i < d.n;
-    bool enabled = valid && inst_enabled(d, i, mask_mode);
-    const int np = valid ? d.n_phases[i] : 0, nwb = valid ? d.n_wb[i] : 0, nk = valid ? d.n_knots[i] : 0;
+    const bool enabled = valid && inst_enabled(d, i, mask_mode);
+    const int np = valid ? d.n_phases[i] : 0, nwb = valid ? d.n_wb[i] : 0, nk = enabled ? d.n_knots[i] : 0;
     const double dtw = valid ? d.dt_wb[i] : 0.0, dtf = valid ? d.dt_fb[i] : 0.0;
     double reg = enabled ? d.sd[(size_t)SD_REG * es + i] : 0.0;
     int n_bws = 1;
     bool done = !enabled;
-    // knots to walk for this block
-    int ktb = 0;
-    {
-        __shared__ int s_ktb;
-        if (tid == 0) s_ktb = 0;
-        __syncthreads();
-        if (l == 0 && enabled) atomicMax(&s_ktb, nk);
-        __syncthreads();
-        ktb = s_ktb;
-    }
-    const int* rec_len = d.rec_len + (size_t)blk * d.KT;
-    const double* lin_blk = d.lin + (size_t)blk * d.KT * REC * 32;
+    const int ktb = max(nk, __shfl_xor_sync(0xffffffffu, nk, 16));     // knots this warp walks
+    const double* lin_i = d.lin + (size_t)(valid ? i : 0) * d.KT * REC;
+
+    // per-instance schedule walker used both by the prefetcher (one knot ahead) and by the math
+    struct Walk { int p, off, N, mode; };
+    auto walk_init = [&](Walk& w) {
+        w.p = np - 1;
+        w.off = (enabled && np > 0) ? d.ph_off[ph_idx(d, w.p, i)] : 0;
+        w.N = (enabled && np > 0) ? d.ph_N[ph_idx(d, w.p, i)] : 0;
+        w.mode = (enabled && np > 0) ? d.ph_mode[ph_idx(d, w.p, i)] : 1;
+    };
+    auto walk_to = [&](Walk& w, int kk) {
+        while (kk < w.off) {
+            --w.p;
+            w.off = d.ph_off[ph_idx(d, w.p, i)]; w.N = d.ph_N[ph_idx(d, w.p, i)]; w.mode = d.ph_mode[ph_idx(d, w.p, i)];
+        }
+    };
+    auto prefetch = [&](Walk& w, int kk, double* dst) {
+        if (enabled && kk < nk) {
+            walk_to(w, kk);
+            const int len = knot_rec_len(w.p < nwb, kk - w.off == w.N - 1);
+            const double* src = lin_i + (size_t)kk * REC;
+            for (int q = l; 2 * q < len; q += 16) __pipeline_memcpy_async(dst + 2 * q, src + 2 * q, 16);
+        }
+        __pipeline_commit();
+    };
 
     while (true) {
         // ---- one attempt -----------------------------------------------------------------
         double Hn[14];
 #pragma unroll
         for (int q = 0; q < 14; ++q) Hn[q] = 0.0;
-        if (l < 16) scr[S_G + l] = 0.0;
+        scr[S_G + l] = 0.0;
         double dV = 0.0;
         bool failed = false;
-        int p = np - 1;
-        int off = (enabled && np > 0) ? d.ph_off[ph_idx(d, p, i)] : 0;
-        int Nn = (enabled && np > 0) ? d.ph_N[ph_idx(d, p, i)] : 0;
-        int mode = (enabled && np > 0) ? d.ph_mode[ph_idx(d, p, i)] : 1;
+        Walk wk, wp;
+        walk_init(wk); walk_init(wp);
+        int& p = wk.p; int& off = wk.off; int& Nn = wk.N; int& mode = wk.mode;
         __syncwarp();
-
-        if (ktb > 0) {  // prologue load
-            const int len = rec_len[ktb - 1] * 16;
-            const double* src = lin_blk + (size_t)(ktb - 1) * REC * 32;
-            for (int q = tid; q < len; q += BWS_THREADS) __pipeline_memcpy_async(buf0 + 2 * q, src + 2 * q, 16);
-            __pipeline_commit();
-        }
+        if (ktb > 0) prefetch(wp, ktb - 1, bufs);
         for (int it = 0; it < ktb; ++it) {
             const int kk = ktb - 1 - it;
-            double* buf = buf0 + (size_t)(it & 1) * REC * 32;
-            double* nbuf = buf0 + (size_t)((it & 1) ^ 1) * REC * 32;
+            double* buf = bufs + (size_t)(it & 1) * REC;
+            double* nbuf = bufs + (size_t)((it & 1) ^ 1) * REC;
             __pipeline_wait_prior(0);
+            __syncwarp();
             const int alive = (!done && !failed) ? 1 : 0;
-            if (!__syncthreads_or(alive)) break;
-            if (kk > 0) {
-                const int len = rec_len[kk - 1] * 16;
-                const double* src = lin_blk + (size_t)(kk - 1) * REC * 32;
-                for (int q = tid; q < len; q += BWS_THREADS) __pipeline_memcpy_async(nbuf + 2 * q, src + 2 * q, 16);
-            }
-            __pipeline_commit();
+            if (!__any_sync(0xffffffffu, alive)) break;
+            if (kk > 0) prefetch(wp, kk - 1, nbuf); else __pipeline_commit();
 
             // ---- which kind of knot is this for my instance? ----
             int ty = 0;  // 0 idle, 1 WB step, 2 RB step, 3 WB terminal, 4 RB terminal
             if (alive && kk < nk) {
-                while (kk < off) {
-                    --p;
-                    off = d.ph_off[ph_idx(d, p, i)]; Nn = d.ph_N[ph_idx(d, p, i)]; mode = d.ph_mode[ph_idx(d, p, i)];
-                }
+                walk_to(wk, kk);
                 const bool wb = p < nwb, term = (kk - off == Nn - 1);
                 ty = wb ? (term ? 3 : 1) : (term ? 4 : 2);
             }
             const int ty_o = __shfl_xor_sync(0xffffffffu, ty, 16);
-#define RBUF(e) buf[(size_t)(e) * 32 + ((j + (e)) & 31)]
+#define RBUF(e) buf[(e)]
 
             // ============ terminal knots: value reset across the phase boundary ============
             if (ty == 3 || ty_o == 3 || ty == 4 || ty_o == 4) {
@@ -468,9 +470,9 @@ __global__ void __launch_bounds__(BWS_THREADS, 1) k_bws(Dev d, Consts c, Opt opt
                     for (int q = l; q < 24; q += 16) scr[S_RB + q] = 0.0;
                 }
                 __syncwarp();
-                if (on && l < 8) {
-                    const int rows[8] = {3, 5, 4, 5, 3, 5, 4, 5}, cols[8] = {0, 0, 1, 1, 2, 2, 3, 3};
-                    scr[S_RB + rows[l] + 6 * cols[l]] = RBUF(R_RB + l);
+                if (on && l < 8) {   // CCS order (3,0)(5,0)(4,1)(5,1)(3,2)(5,2)(4,3)(5,3)
+                    const int col = l >> 1, row = (l & 1) ? 5 : 3 + (col & 1);
+                    scr[S_RB + row + 6 * col] = RBUF(R_RB + l);
                 }
                 __syncwarp();
                 if (on && l < 6) {
@@ -563,7 +565,7 @@ __global__ void __launch_bounds__(BWS_THREADS, 1) k_bws(Dev d, Consts c, Opt opt
 #undef RBUF
         }
         __pipeline_wait_prior(0);
-        __syncthreads();
+        __syncwarp();
 
         // ---- outcome of the attempt (MultiPhaseDDP.cpp:209-241) ----
         int retry = 0;
@@ -591,13 +593,13 @@ __global__ void __launch_bounds__(BWS_THREADS, 1) k_bws(Dev d, Consts c, Opt opt
                 done = true;
             }
         }
-        if (!__syncthreads_or(retry)) break;
+        if (!__any_sync(0xffffffffu, retry)) break;
     }
 }
 
 void launch_bws(const Dev& d, const Consts& c, const Opt& opt, int mask_mode, int single_attempt, cudaStream_t s) {
     cudaFuncSetAttribute(k_bws, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BWS_SMEM);
-    k_bws<<<d.nblk, BWS_THREADS, BWS_SMEM, s>>>(d, c, opt, mask_mode, single_attempt);
+    k_bws<<<(d.n + BWS_INST - 1) / BWS_INST, BWS_THREADS, BWS_SMEM, s>>>(d, c, opt, mask_mode, single_attempt);
 }
 
 }  // namespace mhpc

@@ -8,7 +8,7 @@
 //                              touchdown constraint + AL terms (MHPCConstraints.cpp:91-107, SinglePhase.cpp:257-275),
 //                              impact Jacobian Px (PlanarQuadruped.cpp:82-100, used by MultiPhaseDDP.cpp:320)
 //   CLS_LIGHT                  stance-phase terminal knots (Px = I), rigid-body step and terminal knots
-// Every thread writes one knot record of the AoSoA `lin` array (common.cuh).
+// Every thread writes one knot record of the `lin` array (common.cuh).
 #include <stdlib.h>
 
 #include "kernels.h"
@@ -21,7 +21,7 @@
 namespace mhpc {
 namespace {
 
-#define REC_AT(e) rec[(size_t)(e) * 32 + ((j + (e)) & 31)]
+#define REC_AT(e) rec[(e)]
 
 template <int K, int ROW, int COL>
 __device__ __forceinline__ void wb_par_out(double* __restrict__ rec, int j, double dt, double v) {
