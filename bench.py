@@ -163,9 +163,13 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
+    from mhpc_minimal_env_b200.sharding import gather_result_table, shard_range
     n = args.instances
-    # shard the job by instance: rank r owns global instances [r*n, (r+1)*n)  (no collective inside the solve)
-    specs = [_spec_of(rank * n + i) for i in range(n)]
+    # weak scaling: n instances per rank; the job of n*world instances is sharded by instance into contiguous blocks
+    # (no collective inside the solve)
+    g_begin, g_end = shard_range(n * world, rank, world)
+    assert g_end - g_begin == n
+    specs = [_spec_of(i) for i in range(g_begin, g_end)]
     problems = [to_gpu_problem(s) for s in specs]
     opt = m.default_option(**OPT_KW)
     batch = m.BatchedMHPC(problems, opt, device=local, ls_width=args.ls_width)
@@ -206,12 +210,8 @@ def main():
     table = torch.zeros(6 * npad, device="cuda", dtype=torch.float64)
     batch.results_to_device(table.data_ptr(), table.numel())
     torch.cuda.synchronize()
-    if dist is not None:
-        gathered = [torch.zeros_like(table) for _ in range(world)]
-        dist.all_gather(gathered, table)
-        n_ok = int(sum((g.view(6, npad)[3, :n] == 2).sum().item() for g in gathered))
-    else:
-        n_ok = int((table.view(6, npad)[3, :n] == 2).sum().item())
+    full = gather_result_table(table.view(6, npad)[:, :n].contiguous(), n * world, world, dist)
+    n_ok = int((full[3] == 2).sum().item())
 
     # ---- end-to-end through the host-facing call, host buffers, copies inside the timed region ----
     import ctypes as C
