@@ -4,6 +4,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <set>
 #include <string>
@@ -53,6 +54,7 @@ struct mhpc_batch {
     int launches = 0;
     void* stage = nullptr;
     size_t stage_bytes = 0;
+    bool keep_dead_partials = false;
 };
 
 static void fill_opt(Opt& o, const mhpc_hsddp_option& s) {
@@ -173,6 +175,7 @@ int mhpc_batch_create(int n, const mhpc_hsddp_option* opt, int device, int ls_wi
     fill_opt(b->opt, *opt);
     fill_eps(b->eps, b->opt.alpha);
     fill_consts(b->c);
+    { const char* e = getenv("MHPC_KEEP_DEAD_PARTIALS"); b->keep_dead_partials = e && e[0] == '1'; }
     *out = b;
     return 0;
 }
@@ -477,7 +480,11 @@ int mhpc_batch_solve(mhpc_batch* b, int sync_early_exit) {
             { Stage st(b, TB_OTHER);
               launch_copy_nominal(d, MASK_DDP, s);
               launch_ddp_end(d, b->opt, it, s); b->launches += 2; }
-            if (linearize(b, MASK_LIN)) return -1;                   // forward_sweep_partials_only
+            // forward_sweep_partials_only (MultiPhaseDDP.cpp:262).  After the LAST inner iteration the reference still
+            // linearises, but every derivative it writes is overwritten by the next outer iteration's forward_sweep(0)
+            // (same trajectory: K (x - x_nom) = 0 exactly) or never read (end of solve): the launch is dead work and is
+            // skipped; no result, record or trajectory depends on it.  MHPC_KEEP_DEAD_PARTIALS=1 restores it.
+            if (it < maxDDP || b->keep_dead_partials) { if (linearize(b, MASK_LIN)) return -1; }
         }
         { Stage st(b, TB_OTHER); launch_al_end(d, b->opt, b->c, MASK_RUNNING, 1, s); b->launches++; }
         if (sync_early_exit && al < maxAL) {

@@ -28,14 +28,24 @@ constexpr int S_QUU = 310;    // 16
 constexpr int S_QU = 326;     // 4
 constexpr int S_RA = 330;     // 36 dense RB A
 constexpr int S_RB = 366;     // 24 dense RB B
-constexpr int SCR = 391;
+constexpr int S_ADJ = 390;    // 16 adjugate of Quu
+constexpr int S_INV = 406;    // 16 Quu^-1
+constexpr int S_QI = 422;     // 16 symmetrised Quu^-1
+constexpr int SCR = 439;
 constexpr size_t BWS_SMEM = (size_t)(2 * REC + SCR + 1) * BWS_INST * sizeof(double);
 
 // Eigen::LDLT<>::isPositive() restated (diagonal pivoting on the largest |a_ii|, sign of D tracked;
 // Eigen/src/Cholesky/LDLT.h); call site SinglePhase.cpp:202-205.
-__device__ inline bool ldlt4_is_positive(double a[4][4]) {
+__device__ __forceinline__ bool ldlt4_is_positive(const double q[4][4]) {
+    // work on a full symmetric copy of the LOWER triangle (the only part Eigen reads) so that the symmetric pivot
+    // swaps are plain row + column swaps with compile-time indices (everything stays in registers)
+    double a[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) a[i][jj] = (i >= jj) ? q[i][jj] : q[jj][i];
     int sign = 0;  // 0 zero, 1 pos, 2 neg, 3 indefinite
-    double temp[4];
+    bool result_known = false, result = true;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         int pv = k;
@@ -43,116 +53,120 @@ __device__ inline bool ldlt4_is_positive(double a[4][4]) {
 #pragma unroll
         for (int i = k + 1; i < 4; ++i)
             if (fabs(a[i][i]) > big) { big = fabs(a[i][i]); pv = i; }
-        if (pv != k) {
-            for (int jj = 0; jj < k; ++jj) { double t = a[k][jj]; a[k][jj] = a[pv][jj]; a[pv][jj] = t; }
-            for (int i = pv + 1; i < 4; ++i) { double t = a[i][k]; a[i][k] = a[i][pv]; a[i][pv] = t; }
-            { double t = a[k][k]; a[k][k] = a[pv][pv]; a[pv][pv] = t; }
-            for (int i = k + 1; i < pv; ++i) { double t = a[i][k]; a[i][k] = a[pv][i]; a[pv][i] = t; }
+#pragma unroll
+        for (int pp = k + 1; pp < 4; ++pp) {
+            if (pv == pp) {
+#pragma unroll
+                for (int c = 0; c < 4; ++c) { const double t = a[k][c]; a[k][c] = a[pp][c]; a[pp][c] = t; }
+#pragma unroll
+                for (int r = 0; r < 4; ++r) { const double t = a[r][k]; a[r][k] = a[r][pp]; a[r][pp] = t; }
+            }
         }
         if (k > 0) {
+            double temp[3];
+#pragma unroll
             for (int jj = 0; jj < k; ++jj) temp[jj] = a[jj][jj] * a[k][jj];
-            double s = a[k][0] * temp[0];
-            for (int jj = 1; jj < k; ++jj) s += a[k][jj] * temp[jj];
-            a[k][k] -= s;
+            double sacc = a[k][0] * temp[0];
+#pragma unroll
+            for (int jj = 1; jj < k; ++jj) sacc += a[k][jj] * temp[jj];
+            a[k][k] -= sacc;
+#pragma unroll
             for (int i = k + 1; i < 4; ++i) {
                 double t = a[i][0] * temp[0];
+#pragma unroll
                 for (int jj = 1; jj < k; ++jj) t += a[i][jj] * temp[jj];
                 a[i][k] -= t;
             }
         }
         const double akk = a[k][k];
         const bool valid = fabs(akk) > 0.0;
-        if (k == 0 && !valid) return true;
-        if (valid)
+        if (k == 0 && !valid && !result_known) { result_known = true; result = true; }
+        if (valid) {
+#pragma unroll
             for (int i = k + 1; i < 4; ++i) a[i][k] /= akk;
+        }
         if (sign == 1) { if (akk < 0) sign = 3; }
         else if (sign == 2) { if (akk > 0) sign = 3; }
         else if (sign == 0) { if (akk > 0) sign = 1; else if (akk < 0) sign = 2; }
     }
-    return sign == 1 || sign == 0;
+    return result_known ? result : (sign == 1 || sign == 0);
 }
 
-// Closed-form 4x4 inverse by cofactors (what Eigen's fixed-size Matrix4d::inverse() computes);
-// m and r are [row][col].
-__device__ inline void inverse4(const double m[4][4], double r[4][4]) {
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int jj = 0; jj < 4; ++jj) {
-            const int i1 = (i + 1) & 3, i2 = (i + 2) & 3, i3 = (i + 3) & 3;
-            const int j1 = (jj + 1) & 3, j2 = (jj + 2) & 3, j3 = (jj + 3) & 3;
-            const double cf = m[i1][j1] * (m[i2][j2] * m[i3][j3] - m[i2][j3] * m[i3][j2]) +
-                              m[i2][j1] * (m[i3][j2] * m[i1][j3] - m[i3][j3] * m[i1][j2]) +
-                              m[i3][j1] * (m[i1][j2] * m[i2][j3] - m[i1][j3] * m[i2][j2]);
-            r[jj][i] = ((i + jj) & 1) ? -cf : cf;
-        }
-    double det = m[0][0] * r[0][0];
-#pragma unroll
-    for (int i = 1; i < 4; ++i) det += m[i][0] * r[0][i];
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int jj = 0; jj < 4; ++jj) r[i][jj] /= det;
-}
-
-// value-function update shared by the WB and RB steps (MHPC_CompoundTypes.h:128-144).
-// In: Quu/Qu in scratch, this lane's Qux column qux[4], Qx value qx, symmetrised Qxx row in Hn[].
-// Out: Hn[] = H row, returns G entry; K column / du / dV written through the pointers.
+// value-function update shared by the WB and RB steps (MHPC_CompoundTypes.h:128-144).  Called by ALL lanes of the warp
+// (`on` = this half-warp takes part).  Quu^-1 is the closed-form cofactor inverse (what a fixed-size Matrix4d::inverse()
+// computes): lane l forms ONE adjugate entry and does ONE division, the 16 entries are shared through scratch.
+// In: Quu/Qu/Qux in scratch, this lane's Qux column qux[4], Qx value qx, symmetrised Qxx row in Hn[].
+// Out: Hn[] = H row, G entry, K column, du, dV of the step.
 template <int NX>
 __device__ __forceinline__ bool value_update(bool on, int l, double* scr, const double qux[4], double qx, double Hn[14],
                                              double quu_shift, double kcol[4], double du[4], double& Gout, double& dVstep) {
-    double Quu[4][4], Qu[4];
+    bool pd = true;
+    if (on) {
+        double tst[4][4];
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
-        Qu[c] = scr[S_QU + c];
+        for (int r = 0; r < 4; ++r)
 #pragma unroll
-        for (int r = 0; r < 4; ++r) Quu[r][c] = scr[S_QUU + r + 4 * c];
+            for (int c = 0; c < 4; ++c) tst[r][c] = scr[S_QUU + r + 4 * c] - (r == c ? 1.0 * quu_shift : 0.0);
+        pd = ldlt4_is_positive(tst);
+        // adjugate entry r[jj][i] from the cofactor of (i, jj)
+        const int i = l & 3, jj = l >> 2;
+        const int i1 = (i + 1) & 3, i2 = (i + 2) & 3, i3 = (i + 3) & 3, j1 = (jj + 1) & 3, j2 = (jj + 2) & 3, j3 = (jj + 3) & 3;
+#define QM(r, c) scr[S_QUU + (r) + 4 * (c)]
+        const double cf = QM(i1, j1) * (QM(i2, j2) * QM(i3, j3) - QM(i2, j3) * QM(i3, j2)) +
+                          QM(i2, j1) * (QM(i3, j2) * QM(i1, j3) - QM(i3, j3) * QM(i1, j2)) +
+                          QM(i3, j1) * (QM(i1, j2) * QM(i2, j3) - QM(i1, j3) * QM(i2, j2));
+        scr[S_ADJ + jj + 4 * i] = ((i + jj) & 1) ? -cf : cf;
     }
-    double tst[4][4];
+    __syncwarp();
+    if (on) {
+        double det = QM(0, 0) * scr[S_ADJ + 0 + 4 * 0];
 #pragma unroll
-    for (int r = 0; r < 4; ++r)
+        for (int i = 1; i < 4; ++i) det += QM(i, 0) * scr[S_ADJ + 0 + 4 * i];
+        scr[S_INV + l] = scr[S_ADJ + l] / det;
+#undef QM
+    }
+    __syncwarp();
+    if (on) {
+        const int r = l & 3, c = l >> 2;
+        scr[S_QI + l] = (scr[S_INV + r + 4 * c] + scr[S_INV + c + 4 * r]) / 2;
+    }
+    __syncwarp();
+    if (!on || !pd) return !on ? true : false;
+    double Qu[4], T[4];
 #pragma unroll
-        for (int c = 0; c < 4; ++c) tst[r][c] = Quu[r][c] - (r == c ? 1.0 * quu_shift : 0.0);
-    const bool pd = ldlt4_is_positive(tst);
-    if (!pd) return false;
-    double inv[4][4], Qi[4][4];
-    inverse4(Quu, inv);
+    for (int c = 0; c < 4; ++c) Qu[c] = scr[S_QU + c];
 #pragma unroll
-    for (int r = 0; r < 4; ++r)
+    for (int c = 0; c < 4; ++c) {   // Qi(r, c) at S_QI + r + 4c
+        double sacc = (-scr[S_QI + c + 4 * 0]) * qux[0], t = qux[0] * scr[S_QI + 0 + 4 * c], e = (-scr[S_QI + c + 4 * 0]) * Qu[0];
 #pragma unroll
-        for (int c = 0; c < 4; ++c) Qi[r][c] = (inv[r][c] + inv[c][r]) / 2;
-    double T[4];
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {
-        double s = (-Qi[c][0]) * qux[0], t = qux[0] * Qi[0][c], e = (-Qi[c][0]) * Qu[0];
-#pragma unroll
-        for (int cc = 1; cc < 4; ++cc) { s += (-Qi[c][cc]) * qux[cc]; t += qux[cc] * Qi[cc][c]; e += (-Qi[c][cc]) * Qu[cc]; }
-        kcol[c] = s; T[c] = t; du[c] = e;
+        for (int cc = 1; cc < 4; ++cc) {
+            sacc += (-scr[S_QI + c + 4 * cc]) * qux[cc];
+            t += qux[cc] * scr[S_QI + cc + 4 * c];
+            e += (-scr[S_QI + c + 4 * cc]) * Qu[cc];
+        }
+        kcol[c] = sacc; T[c] = t; du[c] = e;
     }
     double g = T[0] * Qu[0];
 #pragma unroll
     for (int c = 1; c < 4; ++c) g += T[c] * Qu[c];
     Gout = qx - g;
-    if (on && l < NX) {
+    if (l < NX) {
 #pragma unroll
         for (int jc = 0; jc < NX; ++jc) {
-            double s = T[0] * scr[S_QUX + jc];
+            double sacc = T[0] * scr[S_QUX + jc];
 #pragma unroll
-            for (int c = 1; c < 4; ++c) s += T[c] * scr[S_QUX + c * 14 + jc];
-            Hn[jc] = Hn[jc] - s;
+            for (int c = 1; c < 4; ++c) sacc += T[c] * scr[S_QUX + c * 14 + jc];
+            Hn[jc] = Hn[jc] - sacc;
         }
     }
-    double tv[4];
+    double dv = 0.0;
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
-        double s = (-Qu[0]) * inv[0][c];
+    for (int c = 0; c < 4; ++c) {   // dV = ((-Qu^T) Quu^-1) Qu with the un-symmetrised inverse
+        double sacc = (-Qu[0]) * scr[S_INV + 0 + 4 * c];
 #pragma unroll
-        for (int cc = 1; cc < 4; ++cc) s += (-Qu[cc]) * inv[cc][c];
-        tv[c] = s;
+        for (int cc = 1; cc < 4; ++cc) sacc += (-Qu[cc]) * scr[S_INV + cc + 4 * c];
+        dv = (c == 0) ? sacc * Qu[0] : dv + sacc * Qu[c];
     }
-    double dv = tv[0] * Qu[0];
-#pragma unroll
-    for (int c = 1; c < 4; ++c) dv += tv[c] * Qu[c];
     dVstep = dv;
     return true;
 }
@@ -437,7 +451,7 @@ __global__ void __launch_bounds__(BWS_THREADS, 4) k_bws(Dev d, Consts c, Opt opt
                 }
                 double kcol[4], du[4], gout = 0.0, dvs = 0.0;
                 bool ok = true;
-                if (on) ok = value_update<14>(on, l, scr, qux, qx, Hn, opt.quu_shift, kcol, du, gout, dvs);
+                ok = value_update<14>(on, l, scr, qux, qx, Hn, opt.quu_shift, kcol, du, gout, dvs);
                 __syncwarp();
                 if (on) {
                     if (!ok) failed = true;
@@ -455,81 +469,60 @@ __global__ void __launch_bounds__(BWS_THREADS, 4) k_bws(Dev d, Consts c, Opt opt
                 __syncwarp();
             }
 
-            // ============ rigid-body step (dense 6x6) ============
+            // ============ rigid-body step ============
+            // A = I + dt*[0 I3; 0 0] + e5 (a0, a1, 0, 0, 0, 0), B has two non-zeros per column (rows 3 + (c&1) and 5):
+            // only exact-zero terms of the reference's dense 6x6 products are dropped, the remaining terms keep the
+            // ascending inner-index order.
             if (ty == 2 || ty_o == 2) {
                 const bool on = (ty == 2);
                 const double dt = dtf;
-                if (on) {   // build dense A (6x6, column-major) and B (6x4) from the record
-                    for (int q = l; q < 36; q += 16) {
-                        const int r = q % 6, cc = q / 6;
-                        double v = (r == cc) ? 1.0 : 0.0;
-                        if (cc == r + 3 && r < 3) v = 1.0 * dt;       // Ac(0,3)=Ac(1,4)=Ac(2,5)=1
-                        if (r == 5 && cc < 2) v = RBUF(R_RA + cc);
-                        scr[S_RA + q] = v;
-                    }
-                    for (int q = l; q < 24; q += 16) scr[S_RB + q] = 0.0;
-                }
-                __syncwarp();
-                if (on && l < 8) {   // CCS order (3,0)(5,0)(4,1)(5,1)(3,2)(5,2)(4,3)(5,3)
-                    const int col = l >> 1, row = (l & 1) ? 5 : 3 + (col & 1);
-                    scr[S_RB + row + 6 * col] = RBUF(R_RB + l);
-                }
-                __syncwarp();
+                const double a0 = on ? RBUF(R_RA) : 0.0, a1 = on ? RBUF(R_RA + 1) : 0.0;
+                double bt[4], b5[4];   // B(3 + (c&1), c), B(5, c)
+#pragma unroll
+                for (int cc = 0; cc < 4; ++cc) { bt[cc] = on ? RBUF(R_RB + 2 * cc) : 0.0; b5[cc] = on ? RBUF(R_RB + 2 * cc + 1) : 0.0; }
                 if (on && l < 6) {
+                    // M = H A (row l)
+                    scr[S_MQ + l * MQ_LD + 0] = Hn[0] + Hn[5] * a0;
+                    scr[S_MQ + l * MQ_LD + 1] = Hn[1] + Hn[5] * a1;
+                    scr[S_MQ + l * MQ_LD + 2] = Hn[2];
+                    scr[S_MQ + l * MQ_LD + 3] = Hn[0] * dt + Hn[3];
+                    scr[S_MQ + l * MQ_LD + 4] = Hn[1] * dt + Hn[4];
+                    scr[S_MQ + l * MQ_LD + 5] = Hn[2] * dt + Hn[5];
+                    // N = H B (row l)
 #pragma unroll
-                    for (int jc = 0; jc < 6; ++jc) {
-                        double acc = Hn[0] * scr[S_RA + 0 + 6 * jc];
-#pragma unroll
-                        for (int k2 = 1; k2 < 6; ++k2) acc += Hn[k2] * scr[S_RA + k2 + 6 * jc];
-                        scr[S_MQ + l * MQ_LD + jc] = acc;
-                    }
-#pragma unroll
-                    for (int cc = 0; cc < 4; ++cc) {
-                        double acc = Hn[0] * scr[S_RB + 0 + 6 * cc];
-#pragma unroll
-                        for (int k2 = 1; k2 < 6; ++k2) acc += Hn[k2] * scr[S_RB + k2 + 6 * cc];
-                        scr[S_N + l * 4 + cc] = acc;
-                    }
+                    for (int cc = 0; cc < 4; ++cc) scr[S_N + l * 4 + cc] = Hn[3 + (cc & 1)] * bt[cc] + Hn[5] * b5[cc];
                 }
                 __syncwarp();
                 double qux[4] = {0, 0, 0, 0}, qx = 0.0;
                 if (on) {
                     if (l < 6) {
+                        const double acol = (l == 0) ? a0 : a1;
 #pragma unroll
-                        for (int jc = 0; jc < 6; ++jc) {
-                            double q = scr[S_RA + 0 + 6 * l] * scr[S_MQ + 0 * MQ_LD + jc];
-#pragma unroll
-                            for (int k2 = 1; k2 < 6; ++k2) q += scr[S_RA + k2 + 6 * l] * scr[S_MQ + k2 * MQ_LD + jc];
+                        for (int jc = 0; jc < 6; ++jc) {   // Qxx row l = lxx + A^T M
+                            double q;
+                            if (l < 2) q = scr[S_MQ + l * MQ_LD + jc] + acol * scr[S_MQ + 5 * MQ_LD + jc];
+                            else if (l == 2) q = scr[S_MQ + 2 * MQ_LD + jc];
+                            else q = dt * scr[S_MQ + (l - 3) * MQ_LD + jc] + scr[S_MQ + l * MQ_LD + jc];
                             Hn[jc] = ((jc == l) ? (2 * dt) * c.rbQ[l] : 0.0) + q;
                             if (jc == l) Hn[jc] += 1.0 * reg;
                         }
-                        double ag = scr[S_RA + 0 + 6 * l] * scr[S_G + 0];
-#pragma unroll
-                        for (int k2 = 1; k2 < 6; ++k2) ag += scr[S_RA + k2 + 6 * l] * scr[S_G + k2];
+                        double ag;
+                        if (l < 2) ag = scr[S_G + l] + acol * scr[S_G + 5];
+                        else if (l == 2) ag = scr[S_G + 2];
+                        else ag = dt * scr[S_G + l - 3] + scr[S_G + l];
                         qx = RBUF(R_RLX + l) + ag;
 #pragma unroll
-                        for (int cc = 0; cc < 4; ++cc) {
-                            double acc = scr[S_RB + 0 + 6 * cc] * scr[S_MQ + 0 * MQ_LD + l];
-#pragma unroll
-                            for (int k2 = 1; k2 < 6; ++k2) acc += scr[S_RB + k2 + 6 * cc] * scr[S_MQ + k2 * MQ_LD + l];
-                            qux[cc] = acc;
-                        }
+                        for (int cc = 0; cc < 4; ++cc)   // Qux column l = B^T M
+                            qux[cc] = bt[cc] * scr[S_MQ + (3 + (cc & 1)) * MQ_LD + l] + b5[cc] * scr[S_MQ + 5 * MQ_LD + l];
                     }
                     {
                         const int rr = l & 3, cc = l >> 2;
-                        double acc = scr[S_RB + 0 + 6 * rr] * scr[S_N + 0 * 4 + cc];
-#pragma unroll
-                        for (int k2 = 1; k2 < 6; ++k2) acc += scr[S_RB + k2 + 6 * rr] * scr[S_N + k2 * 4 + cc];
+                        const double acc = bt[rr] * scr[S_N + (3 + (rr & 1)) * 4 + cc] + b5[rr] * scr[S_N + 5 * 4 + cc];
                         double q = ((rr == cc) ? (2 * dt) * c.rbR[mode - 1][rr] : 0.0) + acc;
                         if (rr == cc) q += 1.0 * reg;
                         scr[S_QUU + rr + 4 * cc] = q;
                     }
-                    if (l < 4) {
-                        double acc = scr[S_RB + 0 + 6 * l] * scr[S_G + 0];
-#pragma unroll
-                        for (int k2 = 1; k2 < 6; ++k2) acc += scr[S_RB + k2 + 6 * l] * scr[S_G + k2];
-                        scr[S_QU + l] = RBUF(R_RLU + l) + acc;
-                    }
+                    if (l < 4) scr[S_QU + l] = RBUF(R_RLU + l) + (bt[l] * scr[S_G + 3 + (l & 1)] + b5[l] * scr[S_G + 5]);
                 }
                 __syncwarp();
                 if (on && l < 6) {
@@ -544,9 +537,7 @@ __global__ void __launch_bounds__(BWS_THREADS, 4) k_bws(Dev d, Consts c, Opt opt
                     for (int jc = 0; jc < 6; ++jc) Hn[jc] = (Hn[jc] + scr[S_MQ + jc * MQ_LD + l]) / 2;
                 }
                 double kcol[4], du[4], gout = 0.0, dvs = 0.0;
-                bool ok = true;
-                if (on) ok = value_update<6>(on, l, scr, qux, qx, Hn, opt.quu_shift, kcol, du, gout, dvs);
-                __syncwarp();
+                bool ok = value_update<6>(on, l, scr, qux, qx, Hn, opt.quu_shift, kcol, du, gout, dvs);
                 if (on) {
                     if (!ok) failed = true;
                     else {
