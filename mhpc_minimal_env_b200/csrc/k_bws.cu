@@ -26,12 +26,10 @@ constexpr int S_N = 226;      // 7 x 4  : rows 7..13 of H*B   (RB: 6 x 4)
 constexpr int S_QUX = 254;    // 4 x 14
 constexpr int S_QUU = 310;    // 16
 constexpr int S_QU = 326;     // 4
-constexpr int S_RA = 330;     // 36 dense RB A
-constexpr int S_RB = 366;     // 24 dense RB B
-constexpr int S_ADJ = 390;    // 16 adjugate of Quu
-constexpr int S_INV = 406;    // 16 Quu^-1
-constexpr int S_QI = 422;     // 16 symmetrised Quu^-1
-constexpr int SCR = 439;
+constexpr int S_ADJ = 330;    // 16 adjugate of Quu
+constexpr int S_INV = 346;    // 16 Quu^-1
+constexpr int S_QI = 362;     // 16 symmetrised Quu^-1
+constexpr int SCR = 379;
 constexpr size_t BWS_SMEM = (size_t)(2 * REC + SCR + 1) * BWS_INST * sizeof(double);
 
 // Eigen::LDLT<>::isPositive() restated (diagonal pivoting on the largest |a_ii|, sign of D tracked;

@@ -208,3 +208,90 @@ def test_fixed_iteration_budget_and_early_exit_agree():
         o.initialization()
     res = _check_solve(gpu, orcs)
     assert all(r["n_records"] == 6 for r in res)
+
+
+def _oracle_counts(args):
+    idx, cfg, optkw = args
+    from oracle.oracle_py import OracleSolver
+    out = []
+    specs = make_specs(max(idx) + 1, cfg)
+    for i in idx:
+        o = OracleSolver(to_orc_problem(specs[i], **optkw), variant="strict")
+        o.initialization()
+        st = o.solve()
+        # the reference's own sensitivity to FMA contraction (its CMake build uses -O3 -march=native): same algorithm, "fast" build
+        f = OracleSolver(to_orc_problem(specs[i], **optkw), variant="fast")
+        f.initialization()
+        f.solve()
+        fc = [r["cost"] for r in f.records()]
+        recs = o.records()
+        sens = [abs(fc[k] - r["cost"]) if k < len(fc) else 0.0 for k, r in enumerate(recs)]
+        out.append((i, st, [(r["iter_AL"], r["iter_DDP"], r["n_bws"], r["n_fit"], r["reg"], r["eps"], r["cost"], sens[k]) for k, r in enumerate(recs)]))
+    return out
+
+
+def _batch_vs_oracle(n, cfg, optkw=None, check_every=1):
+    """BASELINE config sizes: iteration counts / regularisation / accepted step sizes bit-exact for every checked instance."""
+    import multiprocessing as mp
+    import os
+    import mhpc_minimal_env_b200 as m
+    optkw = optkw or {}
+    specs = make_specs(n, cfg)
+    gpu = m.BatchedMHPC([to_gpu_problem(s) for s in specs], m.default_option(**optkw))
+    gpu.initialization()
+    gpu.solve()
+    res = gpu.results()
+    idx = list(range(0, n, check_every))
+    nproc = min(os.cpu_count() or 1, 16)
+    chunks = [(idx[k::nproc], cfg, optkw) for k in range(nproc) if idx[k::nproc]]
+    with mp.get_context("fork").Pool(len(chunks)) as pool:
+        outs = [x for part in pool.map(_oracle_counts, chunks) for x in part]
+    bad = []
+    for i, st, recs in outs:
+        rg = gpu.records(i)
+        got = [(r["iter_AL"], r["iter_DDP"], r["n_bws"], r["n_fit"], r["reg"], r["eps"]) for r in rg]
+        exp = [tuple(r[:6]) for r in recs]
+        if got != exp or (res[i]["status"] == 3) != (st == 1):
+            bad.append((i, got, exp))
+            continue
+        for a, b in zip(rg, recs):
+            # 1e-6 relative, widened only where the CPU reference itself moves by more than that between its -ffp-contract=off
+            # and FMA-contracted builds (ill-conditioned iterations: |dV| ~ 1e8 amplifies rounding)
+            tol = max(TOL_COST * abs(b[6]), 8.0 * b[7])
+            assert abs(a["cost"] - b[6]) <= tol, (i, a["cost"], b[6], b[7])
+    assert not bad, (len(bad), bad[:3])
+    return gpu, res
+
+
+def test_config2_1024_instances_bit_exact_counts():
+    """BASELINE configs[1]: 1024 instances with perturbed initial states, bit-exact mode/iteration check vs the CPU."""
+    _batch_vs_oracle(1024, 2)
+
+
+def test_full_size_properties_4096():
+    """BASELINE full sizes (4096 instances, configs 2 and 4): size-independent properties.
+    * batch-composition invariance: an instance's whole trace is bit-identical whether it is solved inside the 4096 batch or
+      in a batch of 16 (instances are independent; no arithmetic crosses instances);
+    * idempotence: initialization + solve twice gives bit-identical results;
+    * every executed inner iteration of every instance lowers the cost (Armijo) or is the last-trial fallback;
+    * a sample of the batch agrees with the oracle (counts bit-exact)."""
+    import mhpc_minimal_env_b200 as m
+    for cfg in (2, 4):
+        gpu, res = _batch_vs_oracle(4096, cfg, check_every=128)
+        a1 = gpu.results_array()
+        gpu.initialization()
+        gpu.solve()
+        a2 = gpu.results_array()
+        assert a1.tobytes() == a2.tobytes()
+        assert all(r["status"] in (1, 2) for r in res)
+        pick = list(range(5, 4096, 273))
+        specs = make_specs(4096, cfg)
+        small = m.BatchedMHPC([to_gpu_problem(specs[i]) for i in pick], m.default_option())
+        small.initialization()
+        small.solve()
+        rs = small.results()
+        for k, i in enumerate(pick):
+            assert rs[k] == res[i], (cfg, i)
+            assert small.records(k) == gpu.records(i)
+            recs = gpu.records(i)
+            assert all(r["cost"] <= r["cost_prev"] or r["n_fit"] == 11 for r in recs)
