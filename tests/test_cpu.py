@@ -220,3 +220,22 @@ def test_two_rank_sharding_and_gather_gloo():
         s.initialization()
         s.forward_sweep(0.0)
         assert table[0, i] == s.scalars()["cost"]
+
+
+def _build_cpp_example(tmp_path):
+    exe = str(tmp_path / "test_main_batched")
+    subprocess.check_call(["g++", "-std=c++14", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "examples", "test_main_batched.cpp"), _lib_path(),
+                           "-Wl,-rpath," + os.path.dirname(_lib_path()), "-o", exe])
+    return exe
+
+
+@pytest.mark.skipif(not os.path.exists(_lib_path()), reason="libmhpc_b200.so not built")
+def test_cpp_host_mirror_compiles_against_the_c_abi(tmp_path):
+    """include/mhpc_b200.hpp (HSDDP_OPTION, MHPCUserParameters, USRCMD, Gait, BatchedMHPCLocomotion) + the batched
+    test_main build with a plain C++14 compiler and link against the C ABI only."""
+    exe = _build_cpp_example(tmp_path)
+    import torch
+    if not torch.cuda.is_available():
+        r = subprocess.run([exe, "2"], capture_output=True, text=True)
+        assert r.returncode != 0 and "no CUDA device" in (r.stderr + r.stdout)   # fails loudly, no CPU fallback

@@ -295,3 +295,28 @@ def test_full_size_properties_4096():
             assert small.records(k) == gpu.records(i)
             recs = gpu.records(i)
             assert all(r["cost"] <= r["cost_prev"] or r["n_fit"] == 11 for r in recs)
+
+
+def test_cpp_batched_test_main_reproduces_default_run(tmp_path):
+    """examples/test_main_batched.cpp (the reference's test_main.cpp with a batch dimension, through include/mhpc_b200.hpp):
+    instance 0 = the reference's default ./mhpc_ctrl run."""
+    import json
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    lib = os.path.join(root, "mhpc_minimal_env_b200", "libmhpc_b200.so")
+    exe = str(tmp_path / "test_main_batched")
+    subprocess.check_call(["g++", "-std=c++14", "-I", os.path.join(root, "include"), os.path.join(root, "examples", "test_main_batched.cpp"),
+                           lib, "-Wl,-rpath," + os.path.dirname(lib), "-o", exe])
+    out = subprocess.run([exe, "3"], capture_output=True, text=True, cwd=str(tmp_path), check=True).stdout
+    gold = json.load(open(os.path.join(root, "tests", "golden", "solve_traces.json")))["cases"]["config1_default"]
+    line0 = [ln for ln in out.splitlines() if ln.startswith("instance 0:")][0]
+    cost = float(line0.split("cost")[1].split()[0])
+    assert abs(cost - gold["scalars"]["cost"]) <= TOL_COST * gold["scalars"]["cost"]
+    recs = [ln.split() for ln in out.split("instance 1:")[0].splitlines() if ln.strip().startswith("AL")]
+    assert [(int(r[1]), int(r[3]), int(r[5]), int(r[8])) for r in recs] == \
+           [(r["iter_AL"], r["iter_DDP"], r["n_bws"], r["n_fit"]) for r in gold["records"]]
+    lines = open(os.path.join(str(tmp_path), "state.txt")).read().splitlines()   # print_debugInfo: one knot per line
+    assert len(lines) == 720 and len(lines[0].split()) == 14 and len(lines[-1].split()) == 6
+    assert abs(float(lines[0].split()[0]) - 0.0927) < 1e-15
+    assert abs(float(lines[0].split()[13]) - gold["final"]["x_first"][13]) < 1e-12
