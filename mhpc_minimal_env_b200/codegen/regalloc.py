@@ -1,0 +1,289 @@
+"""Generator-side register allocation for the large Jacobian bodies.
+
+The CasADi Jacobian DAGs keep ~900 FP64 values live at once; a thread has ~120 FP64 registers.  Left to ptxas, the
+emitted straight-line code spills ~2x more than necessary (measured: 106 KB of spill loads per Dyn_BS_par evaluation at
+128 registers against a Belady optimum of 57 KB for the same instruction order).  This emitter does the allocation itself:
+
+* a fixed file of `cap` mutable FP64 variables (r0..r{cap-1}) that ptxas keeps in registers,
+* an explicit per-thread spill array (`SX_SPILL(slot)`, a volatile local-memory array in the kernel) with slot reuse,
+* Belady (furthest-next-use) eviction over the emitted instruction order,
+* software prefetch: the operands of instruction s+lookahead are made resident at step s, so the reload latency
+  (L1/L2) overlaps with `lookahead` independent instructions instead of stalling the consumer.
+
+The arithmetic (operation set, operand order, evaluation order) is exactly that of the SSA form; only the storage of
+intermediate values changes, so results are bit-identical to `emit_inc` (checked on the CPU by emitting the same
+allocation as plain C: tests/test_cpu.py::test_codegen_bit_exact_against_reference_objects).
+
+Macros expected from the includer:  SX_IN(i, j), SX_OUT(k, nz, row, col, v), SX_SINCOS(a, s, c).  The body declares its own
+register variables r0..r{cap-1} and the volatile local spill array `sx_spill`.
+"""
+from __future__ import annotations
+
+import bisect
+from typing import Dict, List, Tuple
+
+from .sxdag import ADD, CONST, COS, DIV, IN, MUL, NEG, SIN, SQ, SQRT, SUB, SXFunction
+
+_BIN = {ADD: "+", SUB: "-", MUL: "*", DIV: "/"}
+INF = 1 << 60
+
+
+def ilp_schedule(instrs, operands_of, window: int = 48, lat_fp: int = 6, lat_slow: int = 20, slow=None):
+    """Window-limited list scheduling: re-order the straight-line program so that dependent instructions are at least
+    `lat` issue slots apart when independent work is available among the next `window` instructions of the original
+    order (bounded look-ahead keeps the live ranges, hence the spill traffic, close to the original order's)."""
+    T = len(instrs)
+    if window <= 1:
+        return list(range(T))
+    def_of = {}
+    for t, ins in enumerate(instrs):
+        for v in ins:
+            def_of[v] = t
+    preds = []
+    for t, ins in enumerate(instrs):
+        preds.append([def_of[p] for p in operands_of(ins) if p in def_of])
+    done_at = [None] * T          # issue slot at which the result becomes available
+    scheduled = [False] * T
+    order = []
+    head = 0                      # first unscheduled instruction in the original order
+    clock = 0
+    while head < T:
+        best, best_ready = -1, None
+        seen = 0
+        t = head
+        while t < T and seen < window:
+            if not scheduled[t]:
+                seen += 1
+                ok = True
+                ready = 0
+                for q in preds[t]:
+                    if not scheduled[q]:
+                        ok = False
+                        break
+                    if done_at[q] > ready:
+                        ready = done_at[q]
+                if ok:
+                    if ready <= clock:
+                        best, best_ready = t, ready
+                        break               # oldest ready instruction wins
+                    if best < 0 or ready < best_ready:
+                        best, best_ready = t, ready
+            t += 1
+        if best_ready > clock:
+            clock = best_ready
+        scheduled[best] = True
+        order.append(best)
+        done_at[best] = clock + (lat_slow if (slow and slow(instrs[best])) else lat_fp)
+        clock += 1
+        while head < T and scheduled[head]:
+            head += 1
+    return order
+
+
+def allocate(fn: SXFunction, cap: int = 104, lookahead: int = 48, window: int = 0) -> Tuple[List[str], Dict[str, int]]:
+    nodes = fn.nodes
+    n = len(nodes)
+    is_const = [nd.op == CONST for nd in nodes]
+
+    # sin/cos pairs on the same argument -> one sincos producing two values
+    partner: Dict[int, int] = {}
+    by_arg: Dict[int, Dict[str, int]] = {}
+    for i, nd in enumerate(nodes):
+        if nd.op in (SIN, COS):
+            by_arg.setdefault(nd.a, {})[nd.op] = i
+    for d in by_arg.values():
+        if SIN in d and COS in d:
+            partner[d[SIN]] = d[COS]
+            partner[d[COS]] = d[SIN]
+
+    # instruction list: every non-constant node in emitted order; a sincos pair is one instruction at the first member
+    instrs: List[Tuple[int, ...]] = []      # (primary node, [secondary node])
+    skip = set()
+    for i in range(n):
+        if is_const[i] or i in skip:
+            continue
+        if i in partner:
+            instrs.append((i, partner[i]))
+            skip.add(partner[i])
+        else:
+            instrs.append((i,))
+    T = len(instrs)
+
+    def operands(ins) -> List[int]:
+        nd = nodes[ins[0]]
+        ops = []
+        for p in (nd.a, nd.b):
+            if p >= 0 and not is_const[p] and p not in ops:
+                ops.append(p)
+        return ops
+
+    if window > 1:
+        perm = ilp_schedule(instrs, operands, window, slow=lambda ins: nodes[ins[0]].op in (DIV, SQRT, SIN, COS))
+        instrs = [instrs[k] for k in perm]
+    def_pos: Dict[int, int] = {}
+    for t, ins in enumerate(instrs):
+        for v in ins:
+            def_pos[v] = t
+
+    uses: Dict[int, List[int]] = {}
+    for t, ins in enumerate(instrs):
+        for p in operands(ins):
+            uses.setdefault(p, []).append(t)
+    stores_of: Dict[int, list] = {}
+    for st in fn.stores:
+        stores_of.setdefault(st.node, []).append(st)
+
+    def next_use(v: int, t: int) -> int:
+        u = uses.get(v)
+        if not u:
+            return INF
+        k = bisect.bisect_right(u, t)
+        return u[k] if k < len(u) else INF
+
+    out: List[str] = []
+    # constant outputs
+    for st in fn.stores:
+        if is_const[st.node]:
+            out.append(f"SX_OUT({st.out}, {st.nz}, {st.row}, {st.col}, {nodes[st.node].lit});")
+
+    reg_of: Dict[int, int] = {}          # value -> register
+    free_regs = list(range(cap - 1, -1, -1))
+    slot_of: Dict[int, int] = {}         # value -> spill slot (valid while the value is live)
+    free_slots: List[int] = []
+    n_slots = 0
+    pins: Dict[int, int] = {}            # value -> last instruction index that pinned it
+    stats = {"loads": 0, "stores": 0, "instrs": T}
+
+    def opnd(v: int) -> str:
+        return nodes[v].lit if is_const[v] else f"r{reg_of[v]}"
+
+    def evict(t: int, protect, before: bool = False) -> int:
+        # `before`: called ahead of executing instruction t (prefetch stage), so a use AT t still counts
+        best, best_nu = -1, -1
+        for v in reg_of:
+            if v in protect or pins.get(v, -1) >= t:
+                continue
+            nu = next_use(v, t - 1 if before else t)
+            if nu > best_nu:
+                best, best_nu = v, nu
+        if best < 0:
+            raise RuntimeError("register file too small for the pinned working set; raise cap or lower lookahead")
+        r = reg_of.pop(best)
+        if best_nu < INF and best not in slot_of:
+            nonlocal n_slots
+            if free_slots:
+                s = free_slots.pop()
+            else:
+                s = n_slots
+                n_slots += 1
+            slot_of[best] = s
+            out.append(f"sx_spill[{s}] = r{r};")
+            stats["stores"] += 1
+        return r
+
+    def get_reg(t: int, protect, before: bool = False) -> int:
+        if free_regs:
+            return free_regs.pop()
+        return evict(t, protect, before)
+
+    def release(v: int) -> None:
+        if v in reg_of:
+            free_regs.append(reg_of.pop(v))
+        if v in slot_of:
+            free_slots.append(slot_of.pop(v))
+
+    def make_resident(q: int, t: int) -> None:
+        """operands of instruction q become resident and pinned (issued at step t <= q)"""
+        ops = operands(instrs[q])
+        for p in ops:
+            if p not in reg_of and p not in slot_of:
+                continue   # not computed yet: it is produced (and pinned) before q
+            if p not in reg_of:
+                r = get_reg(t, set(ops), before=True)
+                reg_of[p] = r
+                out.append(f"r{r} = sx_spill[{slot_of[p]}];")
+                stats["loads"] += 1
+            pins[p] = max(pins.get(p, -1), q)
+
+    for q in range(min(lookahead, T)):
+        make_resident(q, 0)
+    for t, ins in enumerate(instrs):
+        if t + lookahead < T:
+            make_resident(t + lookahead, t)
+        v = ins[0]
+        nd = nodes[v]
+        ops = operands(ins)
+        for p in ops:   # safety net: an operand defined inside the lookahead window may have been evicted since
+            if p not in reg_of:
+                r = get_reg(t, set(ops), before=True)
+                reg_of[p] = r
+                out.append(f"r{r} = sx_spill[{slot_of[p]}];")
+                stats["loads"] += 1
+                stats["late_loads"] = stats.get("late_loads", 0) + 1
+        a = opnd(nd.a) if nd.a >= 0 else None
+        b = opnd(nd.b) if nd.b >= 0 else None
+        # operands that die here free their registers before the destination is chosen
+        for p in ops:
+            if next_use(p, t) == INF and pins.get(p, -1) <= t:
+                release(p)
+        protect = set(p for p in ops if p in reg_of)
+        dests = []
+        for w in ins:
+            r = get_reg(t, protect | set(x for x, _ in dests))
+            reg_of[w] = r
+            dests.append((w, r))
+            nu = next_use(w, t)
+            if nu - t <= lookahead:   # its first consumer has already had its prefetch step: pin until then
+                pins[w] = max(pins.get(w, -1), nu)
+        if len(ins) == 2:
+            s_id, c_id = (ins[0], ins[1]) if nodes[ins[0]].op == SIN else (ins[1], ins[0])
+            out.append(f"SX_SINCOS({a}, r{reg_of[s_id]}, r{reg_of[c_id]});")
+        elif nd.op == IN:
+            out.append(f"r{dests[0][1]} = SX_IN({nd.arg}, {nd.idx});")
+        elif nd.op in _BIN:
+            out.append(f"r{dests[0][1]} = {a} {_BIN[nd.op]} {b};")
+        elif nd.op == NEG:
+            out.append(f"r{dests[0][1]} = -{a};")
+        elif nd.op == SQ:
+            out.append(f"r{dests[0][1]} = {a} * {a};")
+        elif nd.op == SQRT:
+            out.append(f"r{dests[0][1]} = sqrt({a});")
+        elif nd.op == SIN:
+            out.append(f"r{dests[0][1]} = sin({a});")
+        elif nd.op == COS:
+            out.append(f"r{dests[0][1]} = cos({a});")
+        else:
+            raise AssertionError(nd.op)
+        for w, r in dests:
+            for st in stores_of.get(w, []):
+                out.append(f"SX_OUT({st.out}, {st.nz}, {st.row}, {st.col}, r{r});")
+            if not uses.get(w):
+                release(w)
+    stats["slots"] = n_slots
+    stats["cap"] = cap
+    decl = ["double " + ", ".join(f"r{k}" for k in range(cap)) + ";", f"volatile double sx_spill[{max(n_slots, 1)}];"]
+    return decl + out, stats
+
+
+def emit_inc_regalloc(fn: SXFunction, cap: int = 104, lookahead: int = 48, window: int = 0) -> Tuple[str, Dict[str, int]]:
+    body, stats = allocate(fn, cap, lookahead, window)
+    hdr = [
+        f"// GENERATED at build time by mhpc_minimal_env_b200/codegen (regalloc) from the CasADi SX function `{fn.name}`.",
+        f"// register file {cap} FP64, lookahead {lookahead}, ILP window {window}: {stats['instrs']} instructions, {stats['loads']} reloads, "
+        f"{stats['stores']} spill stores, {stats['slots']} spill slots. Do not edit.",
+    ]
+    return "\n".join(hdr + body) + "\n", stats
+
+
+def emit_c_regalloc(fn: SXFunction, symbol: str, cap: int = 104, lookahead: int = 48, window: int = 0) -> str:
+    body, stats = allocate(fn, cap, lookahead, window)
+    return "\n".join([
+        "#include <math.h>",
+        f"void {symbol}(const double** arg, double** res) {{",
+        "#define SX_IN(i, j) (arg[i][j])",
+        "#define SX_OUT(k, nz, row, col, v) res[k][nz] = (v)",
+        "#define SX_SINCOS(a, s, c) do { const double t_ = (a); (s) = sin(t_); (c) = cos(t_); } while (0)",
+        *("  " + s for s in body),
+        "#undef SX_IN", "#undef SX_OUT", "#undef SX_SINCOS",
+        "}", "",
+    ])

@@ -40,32 +40,33 @@ __device__ __forceinline__ void imp_par_out(double* __restrict__ rec, int j, dou
     if (ROW >= 7) REC_AT(R_AB(ROW - 7, COL - 2)) = v;
 }
 
-#define SX_IN(i, j_) ((i) == 0 ? x[j_] : u[j_])
+// The Jacobian bodies come in the generator-allocated form (codegen/regalloc.py: a fixed file of FP64 register
+// variables + an explicit volatile local spill array with Belady eviction and software prefetch); inputs are read
+// straight from the SoA trajectory (`st`, element stride `es`), outputs go straight to the knot record.
+#define SX_IN(i, j_) ((i) == 0 ? st[(size_t)(j_) * es] : st[(size_t)(14 + (j_)) * es])
 #define SX_OUT(k, nz, row, col, v) wb_par_out<k, row, col>(rec, j, dt, v)
 #if LIN_CLS == 0
-__device__ __forceinline__ void dyn_par(const double* x, const double* u, double* __restrict__ rec, int j, double dt) {
-#include "gen/Dyn_BS_par.inc"
+__device__ __forceinline__ void dyn_par(const double* __restrict__ st, size_t es, double* __restrict__ rec, int j, double dt) {
+#include "gen/Dyn_BS_par_ra.inc"
 }
 #elif LIN_CLS == 1
-__device__ __forceinline__ void dyn_par(const double* x, const double* u, double* __restrict__ rec, int j, double dt) {
-#include "gen/Dyn_FS_par.inc"
+__device__ __forceinline__ void dyn_par(const double* __restrict__ st, size_t es, double* __restrict__ rec, int j, double dt) {
+#include "gen/Dyn_FS_par_ra.inc"
 }
 #elif LIN_CLS == 2
-__device__ __forceinline__ void dyn_par(const double* x, const double* u, double* __restrict__ rec, int j, double dt) {
-#include "gen/Dyn_FL_par.inc"
+__device__ __forceinline__ void dyn_par(const double* __restrict__ st, size_t es, double* __restrict__ rec, int j, double dt) {
+#include "gen/Dyn_FL_par_ra.inc"
 }
 #endif
 #undef SX_OUT
-#undef SX_IN
-#define SX_IN(i, j_) (x[j_])
 #define SX_OUT(k, nz, row, col, v) imp_par_out<row, col>(rec, j, v)
 #if LIN_CLS == 3
-__device__ __forceinline__ void imp_par(const double* x, double* __restrict__ rec, int j) {
-#include "gen/Imp_F_par.inc"
+__device__ __forceinline__ void imp_par(const double* __restrict__ st, size_t es, double* __restrict__ rec, int j) {
+#include "gen/Imp_F_par_ra.inc"
 }
 #elif LIN_CLS == 4
-__device__ __forceinline__ void imp_par(const double* x, double* __restrict__ rec, int j) {
-#include "gen/Imp_B_par.inc"
+__device__ __forceinline__ void imp_par(const double* __restrict__ st, size_t es, double* __restrict__ rec, int j) {
+#include "gen/Imp_B_par_ra.inc"
 }
 #endif
 #undef SX_OUT
@@ -164,12 +165,12 @@ __global__ void __launch_bounds__(128, LIN_MINBLOCKS) k_lin(Dev d, Consts c, Opt
 #if LIN_CLS <= 2
     {
         const double dt = d.dt_wb[i];
+        dyn_par(st, es, rec, j, dt);
         double x[14], u[4], y[4];
 #pragma unroll
         for (int e = 0; e < 14; ++e) x[e] = st[e * es];
 #pragma unroll
         for (int e = 0; e < 4; ++e) { u[e] = st[(14 + e) * es]; y[e] = st[(18 + e) * es]; }
-        dyn_par(x, u, rec, j, dt);
 #if LIN_CLS == 2
 #pragma unroll
         for (int e = R_CB(0, 0); e < R_LX; ++e) REC_AT(e) = 0.0;   // C = D = 0 in flight
@@ -182,10 +183,10 @@ __global__ void __launch_bounds__(128, LIN_MINBLOCKS) k_lin(Dev d, Consts c, Opt
     }
 #elif LIN_CLS <= 4
     {
+        imp_par(st, es, rec, j);
         double x[14];
 #pragma unroll
         for (int e = 0; e < 14; ++e) x[e] = st[e * es];
-        imp_par(x, rec, j);
         // terminal cost derivatives: Phix = Qf dx, Phixx = Qf  (CostBase.cpp:58-59)
 #pragma unroll
         for (int e = 0; e < 14; ++e) {

@@ -105,11 +105,29 @@ def test_codegen_bit_exact_against_reference_objects(tmp_path):
         argp = (ctypes.POINTER(ctypes.c_double) * len(a))(*[np.ascontiguousarray(v).ctypes.data_as(ctypes.POINTER(ctypes.c_double)) for v in a])
         resp = (ctypes.POINTER(ctypes.c_double) * len(res))(*[v.ctypes.data_as(ctypes.POINTER(ctypes.c_double)) for v in res])
         getattr(L, "gen_" + name)(argp, resp)
-        for k, o in enumerate(m["outputs"]):
-            dense = np.zeros((o["nrow"], o["ncol"]))
-            for nz, (r, c) in enumerate(zip(o["row"], o["col"])):
-                dense[r, c] = res[k][nz]
-            assert np.array_equal(dense, ref[k]), (name, k, np.max(np.abs(dense - ref[k])))
+        def dense_of(vals):
+            outm = []
+            for k, o in enumerate(m["outputs"]):
+                dm = np.zeros((o["nrow"], o["ncol"]))
+                for nz, (r, c) in enumerate(zip(o["row"], o["col"])):
+                    dm[r, c] = vals[k][nz]
+                outm.append(dm)
+            return outm
+        for k, dm in enumerate(dense_of(res)):
+            assert np.array_equal(dm, ref[k]), (name, k, np.max(np.abs(dm - ref[k])))
+        if hasattr(L, "genra_" + name):
+            # generator-side register allocation (codegen/regalloc.py): same operations, explicit spill array -> bit-exact
+            for v in res:
+                v[:] = 0
+            getattr(L, "genra_" + name)(argp, resp)
+            for k, dm in enumerate(dense_of(res)):
+                assert np.array_equal(dm, ref[k]), ("regalloc", name, k)
+            # device form: shared reciprocals (a/d -> a*(1/d), one reciprocal per distinct denominator): <= 1 ulp per quotient
+            for v in res:
+                v[:] = 0
+            getattr(L, "gendev_" + name)(argp, resp)
+            for k, dm in enumerate(dense_of(res)):
+                assert relerr(dm, ref[k]) <= 1e-12, ("shared reciprocals", name, k, relerr(dm, ref[k]))
 
 
 def _lib_path():
