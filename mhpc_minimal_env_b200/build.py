@@ -89,7 +89,7 @@ def build(ref: str = "/root/reference", force: bool = False, verbose: bool = Tru
     srcs += [os.path.join(GEN, f) for f in os.listdir(GEN) if f.endswith(".inc")]
     srcs += [os.path.join(HERE, "..", "include", "mhpc_b200.h"), os.path.abspath(__file__)]
     stamp = os.path.join(OBJ, "stamp.txt")
-    dig = _digest(srcs) + f":mb{LIN_MINBLOCKS}:{FL_OPT}:{FL_MINBLOCKS}:{os.environ.get('MHPC_RA_CAP', '')}:{os.environ.get('MHPC_RA_LOOKAHEAD', '')}:{os.environ.get('MHPC_RA_WINDOW', '')}:{os.environ.get('MHPC_SHARE_RCP', '')}"
+    dig = _digest(srcs) + f":mb{LIN_MINBLOCKS}:{FL_OPT}:{FL_MINBLOCKS}:{os.environ.get('MHPC_RA_CAP', '')}:{os.environ.get('MHPC_RA_LOOKAHEAD', '')}:{os.environ.get('MHPC_RA_WINDOW', '')}:{os.environ.get('MHPC_SHARE_RCP', '')}:{os.environ.get('MHPC_RA_SMEM', '')}"
     if not force and os.path.exists(LIB) and os.path.exists(stamp) and open(stamp).read() == dig:
         if verbose:
             print(f"[build] up to date: {LIB}")

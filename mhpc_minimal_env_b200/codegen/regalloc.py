@@ -80,7 +80,7 @@ def ilp_schedule(instrs, operands_of, window: int = 48, lat_fp: int = 6, lat_slo
     return order
 
 
-def allocate(fn: SXFunction, cap: int = 104, lookahead: int = 48, window: int = 0) -> Tuple[List[str], Dict[str, int]]:
+def allocate(fn: SXFunction, cap: int = 104, lookahead: int = 48, window: int = 0, smem_slots: int = 0) -> Tuple[List[str], Dict[str, int]]:
     nodes = fn.nodes
     n = len(nodes)
     is_const = [nd.op == CONST for nd in nodes]
@@ -152,7 +152,10 @@ def allocate(fn: SXFunction, cap: int = 104, lookahead: int = 48, window: int = 
     free_slots: List[int] = []
     n_slots = 0
     pins: Dict[int, int] = {}            # value -> last instruction index that pinned it
-    stats = {"loads": 0, "stores": 0, "instrs": T}
+    stats = {"loads": 0, "stores": 0, "instrs": T, "smem_loads": 0, "smem_stores": 0, "smem_to_local": 0}
+    # second level: `smem_slots` per-thread shared-memory slots (SX_SMEM(slot)), also managed furthest-next-use
+    sm_of: Dict[int, int] = {}           # value -> shared-memory slot
+    free_sm = list(range(smem_slots - 1, -1, -1))
 
     def opnd(v: int) -> str:
         return nodes[v].lit if is_const[v] else f"r{reg_of[v]}"
@@ -169,17 +172,53 @@ def allocate(fn: SXFunction, cap: int = 104, lookahead: int = 48, window: int = 
         if best < 0:
             raise RuntimeError("register file too small for the pinned working set; raise cap or lower lookahead")
         r = reg_of.pop(best)
-        if best_nu < INF and best not in slot_of:
-            nonlocal n_slots
-            if free_slots:
-                s = free_slots.pop()
-            else:
-                s = n_slots
-                n_slots += 1
-            slot_of[best] = s
-            out.append(f"sx_spill[{s}] = r{r};")
-            stats["stores"] += 1
+        if best_nu < INF and best not in slot_of and best not in sm_of:
+            spill_value(best, best_nu, r, t - 1 if before else t)
         return r
+
+    def local_slot() -> int:
+        nonlocal n_slots
+        if free_slots:
+            return free_slots.pop()
+        n_slots += 1
+        return n_slots - 1
+
+    def spill_value(v: int, v_nu: int, r: int, now: int) -> None:
+        """value v (in register r, next use v_nu) leaves the register file: shared memory if it is needed sooner than
+        something already there (which then moves on to local memory), else local memory."""
+        if smem_slots > 0:
+            if free_sm:
+                sm_of[v] = free_sm.pop()
+                out.append(f"SX_SMEM({sm_of[v]}) = r{r};")
+                stats["smem_stores"] += 1
+                return
+            far, far_nu = -1, -1
+            for w in sm_of:
+                nu = next_use(w, now)
+                if nu > far_nu:
+                    far, far_nu = w, nu
+            if far_nu > v_nu:
+                sl = sm_of.pop(far)
+                if far_nu < INF and far not in slot_of:   # still needed: hand it down to local memory through the scratch register
+                    slot_of[far] = local_slot()
+                    out.append(f"rt = SX_SMEM({sl}); sx_spill[{slot_of[far]}] = rt;")
+                    stats["smem_to_local"] += 1
+                    stats["stores"] += 1
+                sm_of[v] = sl
+                out.append(f"SX_SMEM({sl}) = r{r};")
+                stats["smem_stores"] += 1
+                return
+        slot_of[v] = local_slot()
+        out.append(f"sx_spill[{slot_of[v]}] = r{r};")
+        stats["stores"] += 1
+
+    def reload(p: int, r: int) -> None:
+        if p in sm_of:
+            out.append(f"r{r} = SX_SMEM({sm_of[p]});")
+            stats["smem_loads"] += 1
+        else:
+            out.append(f"r{r} = sx_spill[{slot_of[p]}];")
+            stats["loads"] += 1
 
     def get_reg(t: int, protect, before: bool = False) -> int:
         if free_regs:
@@ -191,18 +230,19 @@ def allocate(fn: SXFunction, cap: int = 104, lookahead: int = 48, window: int = 
             free_regs.append(reg_of.pop(v))
         if v in slot_of:
             free_slots.append(slot_of.pop(v))
+        if v in sm_of:
+            free_sm.append(sm_of.pop(v))
 
     def make_resident(q: int, t: int) -> None:
         """operands of instruction q become resident and pinned (issued at step t <= q)"""
         ops = operands(instrs[q])
         for p in ops:
-            if p not in reg_of and p not in slot_of:
+            if p not in reg_of and p not in slot_of and p not in sm_of:
                 continue   # not computed yet: it is produced (and pinned) before q
             if p not in reg_of:
                 r = get_reg(t, set(ops), before=True)
                 reg_of[p] = r
-                out.append(f"r{r} = sx_spill[{slot_of[p]}];")
-                stats["loads"] += 1
+                reload(p, r)
             pins[p] = max(pins.get(p, -1), q)
 
     for q in range(min(lookahead, T)):
@@ -217,8 +257,7 @@ def allocate(fn: SXFunction, cap: int = 104, lookahead: int = 48, window: int = 
             if p not in reg_of:
                 r = get_reg(t, set(ops), before=True)
                 reg_of[p] = r
-                out.append(f"r{r} = sx_spill[{slot_of[p]}];")
-                stats["loads"] += 1
+                reload(p, r)
                 stats["late_loads"] = stats.get("late_loads", 0) + 1
         a = opnd(nd.a) if nd.a >= 0 else None
         b = opnd(nd.b) if nd.b >= 0 else None
@@ -261,29 +300,31 @@ def allocate(fn: SXFunction, cap: int = 104, lookahead: int = 48, window: int = 
                 release(w)
     stats["slots"] = n_slots
     stats["cap"] = cap
-    decl = ["double " + ", ".join(f"r{k}" for k in range(cap)) + ";", f"volatile double sx_spill[{max(n_slots, 1)}];"]
+    decl = ["double rt, " + ", ".join(f"r{k}" for k in range(cap)) + ";", f"volatile double sx_spill[{max(n_slots, 1)}];"]
     return decl + out, stats
 
 
-def emit_inc_regalloc(fn: SXFunction, cap: int = 104, lookahead: int = 48, window: int = 0) -> Tuple[str, Dict[str, int]]:
-    body, stats = allocate(fn, cap, lookahead, window)
+def emit_inc_regalloc(fn: SXFunction, cap: int = 104, lookahead: int = 48, window: int = 0, smem_slots: int = 0) -> Tuple[str, Dict[str, int]]:
+    body, stats = allocate(fn, cap, lookahead, window, smem_slots)
     hdr = [
         f"// GENERATED at build time by mhpc_minimal_env_b200/codegen (regalloc) from the CasADi SX function `{fn.name}`.",
         f"// register file {cap} FP64, lookahead {lookahead}, ILP window {window}: {stats['instrs']} instructions, {stats['loads']} reloads, "
-        f"{stats['stores']} spill stores, {stats['slots']} spill slots. Do not edit.",
+        f"{stats['stores']} spill stores, {stats['slots']} local slots; shared-memory level: {smem_slots} slots, {stats['smem_loads']} loads, {stats['smem_stores']} stores. Do not edit.",
     ]
     return "\n".join(hdr + body) + "\n", stats
 
 
-def emit_c_regalloc(fn: SXFunction, symbol: str, cap: int = 104, lookahead: int = 48, window: int = 0) -> str:
-    body, stats = allocate(fn, cap, lookahead, window)
+def emit_c_regalloc(fn: SXFunction, symbol: str, cap: int = 104, lookahead: int = 48, window: int = 0, smem_slots: int = 0) -> str:
+    body, stats = allocate(fn, cap, lookahead, window, smem_slots)
     return "\n".join([
         "#include <math.h>",
         f"void {symbol}(const double** arg, double** res) {{",
+        f"  volatile double sx_smem_c[{max(smem_slots, 1)}];",
+        "#define SX_SMEM(s) sx_smem_c[s]",
         "#define SX_IN(i, j) (arg[i][j])",
         "#define SX_OUT(k, nz, row, col, v) res[k][nz] = (v)",
         "#define SX_SINCOS(a, s, c) do { const double t_ = (a); (s) = sin(t_); (c) = cos(t_); } while (0)",
         *("  " + s for s in body),
-        "#undef SX_IN", "#undef SX_OUT", "#undef SX_SINCOS",
+        "#undef SX_IN", "#undef SX_OUT", "#undef SX_SINCOS", "#undef SX_SMEM",
         "}", "",
     ])

@@ -18,8 +18,17 @@
 #error "compile with -DLIN_CLS=<knot class>"
 #endif
 
+#include "gen/gen_meta.h"
+
 namespace mhpc {
 namespace {
+
+constexpr int LIN_THREADS = 128;
+#if LIN_CLS <= 4
+constexpr size_t LIN_SMEM = (size_t)MHPC_RA_SMEM_SLOTS * LIN_THREADS * sizeof(double);
+#else
+constexpr size_t LIN_SMEM = 0;
+#endif
 
 #define REC_AT(e) rec[(e)]
 
@@ -44,33 +53,35 @@ __device__ __forceinline__ void imp_par_out(double* __restrict__ rec, int j, dou
 // variables + an explicit volatile local spill array with Belady eviction and software prefetch); inputs are read
 // straight from the SoA trajectory (`st`, element stride `es`), outputs go straight to the knot record.
 #define SX_IN(i, j_) ((i) == 0 ? st[(size_t)(j_) * es] : st[(size_t)(14 + (j_)) * es])
+#define SX_SMEM(s) sx_sm[(s) * LIN_THREADS]     /* second spill level: per-thread shared-memory slots, conflict-free */
 #define SX_OUT(k, nz, row, col, v) wb_par_out<k, row, col>(rec, j, dt, v)
 #if LIN_CLS == 0
-__device__ __forceinline__ void dyn_par(const double* __restrict__ st, size_t es, double* __restrict__ rec, int j, double dt) {
+__device__ __forceinline__ void dyn_par(const double* __restrict__ st, size_t es, double* __restrict__ rec, int j, double dt, volatile double* sx_sm) {
 #include "gen/Dyn_BS_par_ra.inc"
 }
 #elif LIN_CLS == 1
-__device__ __forceinline__ void dyn_par(const double* __restrict__ st, size_t es, double* __restrict__ rec, int j, double dt) {
+__device__ __forceinline__ void dyn_par(const double* __restrict__ st, size_t es, double* __restrict__ rec, int j, double dt, volatile double* sx_sm) {
 #include "gen/Dyn_FS_par_ra.inc"
 }
 #elif LIN_CLS == 2
-__device__ __forceinline__ void dyn_par(const double* __restrict__ st, size_t es, double* __restrict__ rec, int j, double dt) {
+__device__ __forceinline__ void dyn_par(const double* __restrict__ st, size_t es, double* __restrict__ rec, int j, double dt, volatile double* sx_sm) {
 #include "gen/Dyn_FL_par_ra.inc"
 }
 #endif
 #undef SX_OUT
 #define SX_OUT(k, nz, row, col, v) imp_par_out<row, col>(rec, j, v)
 #if LIN_CLS == 3
-__device__ __forceinline__ void imp_par(const double* __restrict__ st, size_t es, double* __restrict__ rec, int j) {
+__device__ __forceinline__ void imp_par(const double* __restrict__ st, size_t es, double* __restrict__ rec, int j, volatile double* sx_sm) {
 #include "gen/Imp_F_par_ra.inc"
 }
 #elif LIN_CLS == 4
-__device__ __forceinline__ void imp_par(const double* __restrict__ st, size_t es, double* __restrict__ rec, int j) {
+__device__ __forceinline__ void imp_par(const double* __restrict__ st, size_t es, double* __restrict__ rec, int j, volatile double* sx_sm) {
 #include "gen/Imp_B_par_ra.inc"
 }
 #endif
 #undef SX_OUT
 #undef SX_IN
+#undef SX_SMEM
 
 // running-cost derivatives of a WB step knot, with barrier terms when `reb` (SinglePhase.cpp:219-249)
 __device__ inline void wb_cost_partials(const Consts& c, int mode, double dt, const double* x, const double* u, const double* y,
@@ -135,7 +146,10 @@ __device__ inline void wb_cost_partials(const Consts& c, int mode, double dt, co
 #ifndef LIN_MINBLOCKS
 #define LIN_MINBLOCKS 1
 #endif
-__global__ void __launch_bounds__(128, LIN_MINBLOCKS) k_lin(Dev d, Consts c, Opt opt, int mask_mode, const int* __restrict__ knots) {
+__global__ void __launch_bounds__(LIN_THREADS, LIN_MINBLOCKS) k_lin(Dev d, Consts c, Opt opt, int mask_mode, const int* __restrict__ knots) {
+    extern __shared__ __align__(16) double sx_smem_base[];
+    volatile double* sx_sm = sx_smem_base + threadIdx.x;
+    (void)sx_sm;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= d.n) return;
     if (!inst_enabled(d, i, mask_mode)) return;
@@ -165,7 +179,7 @@ __global__ void __launch_bounds__(128, LIN_MINBLOCKS) k_lin(Dev d, Consts c, Opt
 #if LIN_CLS <= 2
     {
         const double dt = d.dt_wb[i];
-        dyn_par(st, es, rec, j, dt);
+        dyn_par(st, es, rec, j, dt, sx_sm);
         double x[14], u[4], y[4];
 #pragma unroll
         for (int e = 0; e < 14; ++e) x[e] = st[e * es];
@@ -183,7 +197,7 @@ __global__ void __launch_bounds__(128, LIN_MINBLOCKS) k_lin(Dev d, Consts c, Opt
     }
 #elif LIN_CLS <= 4
     {
-        imp_par(st, es, rec, j);
+        imp_par(st, es, rec, j, sx_sm);
         double x[14];
 #pragma unroll
         for (int e = 0; e < 14; ++e) x[e] = st[e * es];
@@ -286,18 +300,11 @@ __global__ void __launch_bounds__(128, LIN_MINBLOCKS) k_lin(Dev d, Consts c, Opt
 
 void LIN_LAUNCH(const Dev& d, const Consts& c, const Opt& opt, int mask_mode, const int* knots, int n_knots, cudaStream_t s) {
     if (n_knots <= 0) return;
-    // Residency throttle for the spill-heavy Jacobian bodies: the per-thread local-memory frame is several KB, so the
-    // number of resident threads decides whether spills stay in L1/L2 or go to HBM.  (block size, dynamic smem padding)
-    static int threads = 0, pad = 0;
-    if (!threads) {
-        const char* t = getenv("MHPC_LIN_THREADS");
-        const char* q = getenv("MHPC_LIN_SMEM");
-        threads = t ? atoi(t) : 128;
-        pad = q ? atoi(q) : 0;
-        if (pad > 48 * 1024) cudaFuncSetAttribute(k_lin, cudaFuncAttributeMaxDynamicSharedMemorySize, pad);
-    }
-    dim3 grid((d.n + threads - 1) / threads, n_knots);
-    k_lin<<<grid, threads, pad, s>>>(d, c, opt, mask_mode, knots);
+    // 128-thread blocks; the Jacobian classes carry MHPC_RA_SMEM_SLOTS shared-memory spill slots per thread
+    // (codegen/regalloc.py), sized so that LIN_MINBLOCKS blocks are resident per SM.
+    if (LIN_SMEM > 48 * 1024) cudaFuncSetAttribute(k_lin, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LIN_SMEM);
+    dim3 grid((d.n + LIN_THREADS - 1) / LIN_THREADS, n_knots);
+    k_lin<<<grid, LIN_THREADS, LIN_SMEM, s>>>(d, c, opt, mask_mode, knots);
 }
 
 }  // namespace mhpc
