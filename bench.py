@@ -33,6 +33,7 @@ METRIC = "batched MHPC solves/sec (4096 inst, fixed HSDDP iters)"
 UNIT = "solves/s"
 # algorithmic flops of one default-horizon linearisation (158 stance + 198 flight WB knots, 356 RB, 2 impacts)
 LIN_FLOP_PER_INSTANCE = 6896848.0
+BS_FLOP_PER_KNOT = 27569.0
 # bytes the backward sweep must move per instance (records in + K,du,G out), default horizon: 356 WB step records (175 dbl),
 # 4 WB terminal (148), 352 RB step (20), 4 RB terminal (6) read; 712 x (56+4+14) written
 BWS_BYTES_PER_INSTANCE = 8.0 * (356 * 175 + 4 * 148 + 352 * 20 + 4 * 6 + 712 * 74)
@@ -277,6 +278,8 @@ def main():
         tm = batch.timing()
         batch.enable_timing(False)
         lin_ms = batch.time_kernel(0, 5)
+        lin_bs_ms = batch.time_kernel(10, 5)      # the single dominant kernel: k_lin<BS> (back-stance Jacobian knots)
+        batch.backward_sweep(1.0)                 # large regularisation: every instance completes the sweep
         bws_ms = batch.time_kernel(1, 3)
         fp64_peak = m.measure_fp64_peak(local)
         peaks = {}
@@ -287,11 +290,23 @@ def main():
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
         lin_tflops = LIN_FLOP_PER_INSTANCE * n / (lin_ms * 1e-3) / 1e12
         bws_gbs = BWS_BYTES_PER_INSTANCE * n / (bws_ms * 1e-3) / 1e9
-        roofline = {"kernel": "k_lin (linearisation launch group: Dyn_{BS,FS,FL}_par, Imp_{F,B}_par, light knots)",
-                    "bound": "fp64", "achieved": lin_tflops, "peak": fp64_peak, "unit": "TFLOP/s", "frac": lin_tflops / fp64_peak,
-                    "traffic": None, "ms_per_launch": lin_ms,
-                    "peak_source": "FP64 FMA probe measured live on this GPU (MEASURED_PEAKS.json has no FP64 entry)",
-                    "us_per_horizon_linearize": 1e3 * lin_ms / n}
+        n_bs_knots = 79                                   # back-stance step knots per default horizon (phase 0)
+        bs_flop = BS_FLOP_PER_KNOT * n_bs_knots * n       # 27 569 flop per WB-stance knot
+        bs_tflops = bs_flop / (lin_bs_ms * 1e-3) / 1e12
+        traffic = None
+        try:   # dram bytes of ONE k_lin<BS> launch at this batch size from the committed ncu --set full capture
+            prof = json.load(open(os.path.join(ROOT, "profiles", "r1_lin_bs_ncu_traffic.json")))
+            if prof.get("instances") == n:
+                traffic = prof["dram_bytes_per_launch"]
+        except Exception:
+            pass
+        roofline = {"kernel": "k_lin<BS> (Dyn_BS_par + Euler A,B + cost/barrier partials, 79 back-stance knots x instances)",
+                    "bound": "fp64", "achieved": bs_tflops, "peak": fp64_peak, "unit": "TFLOP/s", "frac": bs_tflops / fp64_peak,
+                    "traffic": traffic, "algorithmic_bytes": 1352.0 * n_bs_knots * n, "ms_per_launch": lin_bs_ms,
+                    "peak_source": "FP64 FMA probe measured live on this GPU (MEASURED_PEAKS.json has no FP64 entry)"}
+        roofline_lin_group = {"kernel": "linearisation launch group (k_lin<BS,FS,FL,IMPF,IMPB,light>)", "bound": "fp64",
+                              "achieved": lin_tflops, "peak": fp64_peak, "unit": "TFLOP/s", "frac": lin_tflops / fp64_peak,
+                              "ms_per_launch": lin_ms, "us_per_horizon_linearize": 1e3 * lin_ms / n}
         roofline_bws = {"kernel": "k_bws (impact-aware Riccati sweep, one attempt)", "bound": "hbm", "achieved": bws_gbs, "peak": hbm_peak,
                         "unit": "GB/s", "frac": bws_gbs / hbm_peak, "traffic": None, "ms_per_launch": bws_ms,
                         "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s"}
@@ -306,7 +321,7 @@ def main():
                         "note": f"mhpc_batch_solve_host: pinned host problems in, results + first {ek} knots of x,u,y,K,du out"},
                 "gpu_launches": int(tm["n_launches"] + 3) * args.steps,
                 "clocks": sampler.summary(),
-                "roofline": roofline, "roofline_bws": roofline_bws,
+                "roofline": roofline, "roofline_lin_group": roofline_lin_group, "roofline_bws": roofline_bws,
                 "stage_ms": {k: tm[k] for k in ("total_ms", "rollout_ms", "linearize_ms", "bws_ms", "linesearch_ms", "other_ms")},
                 "cpu_baseline": {"value": cpu_v, "unit": UNIT, "cores": 1, "kind": _cpu_kind(),
                                  "sample": f"first {args.cpu_sample} instances of the workload, reference sources (-O3 -mavx2 -mfma, Eigen stand-in), one core; "

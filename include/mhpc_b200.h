@@ -150,7 +150,7 @@ typedef struct mhpc_timing { float total_ms, rollout_ms, linearize_ms, bws_ms, l
 int mhpc_batch_enable_timing(mhpc_batch* b, int on);
 int mhpc_batch_get_timing(mhpc_batch* b, mhpc_timing* t);
 /* run `reps` linearisation launches back to back and return the average ms per launch (CUDA events) */
-int mhpc_batch_time_kernel(mhpc_batch* b, int which /*0 linearize, 1 backward sweep, 2 one rollout chunk*/, int reps, float* ms_per_launch);
+int mhpc_batch_time_kernel(mhpc_batch* b, int which /*0 linearize group, 1 backward sweep, 2 one rollout chunk, 10+c linearisation knot class c (0 BS,1 FS,2 FL,3 IMPF,4 IMPB,5 light)*/, int reps, float* ms_per_launch);
 /* FP64 FMA peak probe on this device (TFLOP/s), used as the roofline denominator for the linearisation */
 int mhpc_measure_fp64_peak(int device, double* tflops);
 long long mhpc_batch_device_bytes(mhpc_batch* b);

@@ -39,9 +39,10 @@ FUNCTIONS = [
 # the large Jacobian bodies additionally get a generator-side register allocation (codegen/regalloc.py)
 REGALLOC_FUNCTIONS = ["Dyn_BS_par", "Dyn_FS_par", "Dyn_FL_par", "Imp_F_par", "Imp_B_par"]
 RA_CAP = int(os.environ.get("MHPC_RA_CAP", "104"))
-RA_LOOKAHEAD = int(os.environ.get("MHPC_RA_LOOKAHEAD", "48"))
+RA_LOOKAHEAD = int(os.environ.get("MHPC_RA_LOOKAHEAD", "24"))
 RA_WINDOW = int(os.environ.get("MHPC_RA_WINDOW", "0"))
 SHARE_RCP = os.environ.get("MHPC_SHARE_RCP", "1") == "1"
+RA_FAR = int(os.environ.get("MHPC_RA_FAR", "128"))           # prefetch distance for operands in local memory (0: same as lookahead)
 RA_SMEM = int(os.environ.get("MHPC_RA_SMEM", "108"))      # per-thread shared-memory slots of the second spill level
 
 HERE = os.path.dirname(os.path.abspath(__file__))
@@ -151,15 +152,15 @@ def generate(ref: str = DEFAULT_REF, out: str = DEFAULT_OUT, verbose: bool = Tru
         write(name + ".inc", emit_inc(fn))
     ra_stats = {}
     for name in REGALLOC_FUNCTIONS:
-        text, st = emit_inc_regalloc(dev[name], RA_CAP, RA_LOOKAHEAD, RA_WINDOW, RA_SMEM)
+        text, st = emit_inc_regalloc(dev[name], RA_CAP, RA_LOOKAHEAD, RA_WINDOW, RA_SMEM, RA_FAR)
         write(name + "_ra.inc", text)
         ra_stats[name] = st
     write("gen_check.c", "".join(emit_c(fn, "gen_" + name) for name, fn in fns.items()) +
-          "".join(emit_c_regalloc(fns[name], "genra_" + name, RA_CAP, RA_LOOKAHEAD, RA_WINDOW, RA_SMEM) for name in REGALLOC_FUNCTIONS) +
-          "".join(emit_c_regalloc(dev[name], "gendev_" + name, RA_CAP, RA_LOOKAHEAD, RA_WINDOW, RA_SMEM) for name in REGALLOC_FUNCTIONS))
+          "".join(emit_c_regalloc(fns[name], "genra_" + name, RA_CAP, RA_LOOKAHEAD, RA_WINDOW, RA_SMEM, RA_FAR) for name in REGALLOC_FUNCTIONS) +
+          "".join(emit_c_regalloc(dev[name], "gendev_" + name, RA_CAP, RA_LOOKAHEAD, RA_WINDOW, RA_SMEM, RA_FAR) for name in REGALLOC_FUNCTIONS))
     write("gen_meta.h", emit_meta_h(metas) + f"#define MHPC_RA_SMEM_SLOTS {RA_SMEM}\n")
     metas["_source_sha256"] = h.hexdigest()
-    metas["_regalloc"] = {"cap": RA_CAP, "lookahead": RA_LOOKAHEAD, "window": RA_WINDOW, "share_reciprocals": SHARE_RCP, "smem_slots": RA_SMEM, "stats": ra_stats}
+    metas["_regalloc"] = {"cap": RA_CAP, "lookahead": RA_LOOKAHEAD, "window": RA_WINDOW, "share_reciprocals": SHARE_RCP, "smem_slots": RA_SMEM, "far_lookahead": RA_FAR, "stats": ra_stats}
     write("gen_meta.json", json.dumps(metas, indent=1))
     if verbose:
         for name in FUNCTIONS:

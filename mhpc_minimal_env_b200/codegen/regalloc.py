@@ -80,7 +80,10 @@ def ilp_schedule(instrs, operands_of, window: int = 48, lat_fp: int = 6, lat_slo
     return order
 
 
-def allocate(fn: SXFunction, cap: int = 104, lookahead: int = 48, window: int = 0, smem_slots: int = 0) -> Tuple[List[str], Dict[str, int]]:
+def allocate(fn: SXFunction, cap: int = 104, lookahead: int = 48, window: int = 0, smem_slots: int = 0,
+             far_lookahead: int = 0) -> Tuple[List[str], Dict[str, int]]:
+    """`lookahead`: prefetch distance (instructions) for operands held in shared memory / produced recently;
+    `far_lookahead` (> lookahead, 0 = off): longer distance used for operands that sit in LOCAL memory (HBM latency)."""
     nodes = fn.nodes
     n = len(nodes)
     is_const = [nd.op == CONST for nd in nodes]
@@ -233,21 +236,26 @@ def allocate(fn: SXFunction, cap: int = 104, lookahead: int = 48, window: int = 
         if v in sm_of:
             free_sm.append(sm_of.pop(v))
 
-    def make_resident(q: int, t: int) -> None:
+    def make_resident(q: int, t: int, local_only: bool = False) -> None:
         """operands of instruction q become resident and pinned (issued at step t <= q)"""
         ops = operands(instrs[q])
         for p in ops:
             if p not in reg_of and p not in slot_of and p not in sm_of:
                 continue   # not computed yet: it is produced (and pinned) before q
+            if local_only and (p in reg_of or p in sm_of):
+                continue   # the far pass only starts the long-latency (local memory) reloads early
             if p not in reg_of:
                 r = get_reg(t, set(ops), before=True)
                 reg_of[p] = r
                 reload(p, r)
             pins[p] = max(pins.get(p, -1), q)
 
+    far = far_lookahead if far_lookahead > lookahead else 0
     for q in range(min(lookahead, T)):
         make_resident(q, 0)
     for t, ins in enumerate(instrs):
+        if far and t + far < T:
+            make_resident(t + far, t, local_only=True)
         if t + lookahead < T:
             make_resident(t + lookahead, t)
         v = ins[0]
@@ -304,8 +312,9 @@ def allocate(fn: SXFunction, cap: int = 104, lookahead: int = 48, window: int = 
     return decl + out, stats
 
 
-def emit_inc_regalloc(fn: SXFunction, cap: int = 104, lookahead: int = 48, window: int = 0, smem_slots: int = 0) -> Tuple[str, Dict[str, int]]:
-    body, stats = allocate(fn, cap, lookahead, window, smem_slots)
+def emit_inc_regalloc(fn: SXFunction, cap: int = 104, lookahead: int = 48, window: int = 0, smem_slots: int = 0,
+                      far_lookahead: int = 0) -> Tuple[str, Dict[str, int]]:
+    body, stats = allocate(fn, cap, lookahead, window, smem_slots, far_lookahead)
     hdr = [
         f"// GENERATED at build time by mhpc_minimal_env_b200/codegen (regalloc) from the CasADi SX function `{fn.name}`.",
         f"// register file {cap} FP64, lookahead {lookahead}, ILP window {window}: {stats['instrs']} instructions, {stats['loads']} reloads, "
@@ -314,8 +323,9 @@ def emit_inc_regalloc(fn: SXFunction, cap: int = 104, lookahead: int = 48, windo
     return "\n".join(hdr + body) + "\n", stats
 
 
-def emit_c_regalloc(fn: SXFunction, symbol: str, cap: int = 104, lookahead: int = 48, window: int = 0, smem_slots: int = 0) -> str:
-    body, stats = allocate(fn, cap, lookahead, window, smem_slots)
+def emit_c_regalloc(fn: SXFunction, symbol: str, cap: int = 104, lookahead: int = 48, window: int = 0, smem_slots: int = 0,
+                    far_lookahead: int = 0) -> str:
+    body, stats = allocate(fn, cap, lookahead, window, smem_slots, far_lookahead)
     return "\n".join([
         "#include <math.h>",
         f"void {symbol}(const double** arg, double** res) {{",

@@ -829,8 +829,12 @@ int mhpc_batch_time_kernel(mhpc_batch* b, int which, int reps, float* ms_per_lau
     b->timing = false;
     auto run = [&]() -> int {
         if (which == 0) {
-            std::vector<int> v(b->d.npad, 1);
             return linearize(b, MASK_ALL);
+        } else if (which >= 10 && which < 10 + CLS_N) {   // one knot class of the linearisation only
+            const int cls = which - 10;
+            typedef void (*lin_fn)(const Dev&, const Consts&, const Opt&, int, const int*, int, cudaStream_t);
+            const lin_fn fns[CLS_N] = {launch_lin_BS, launch_lin_FS, launch_lin_FL, launch_lin_IMPF, launch_lin_IMPB, launch_lin_LIGHT};
+            fns[cls](b->d, b->c, b->opt, MASK_ALL, b->knot_list[cls], b->knot_cnt[cls], b->stream);
         } else if (which == 1) {
             launch_bws(b->d, b->c, b->opt, MASK_ALL, 1, b->stream);
         } else {

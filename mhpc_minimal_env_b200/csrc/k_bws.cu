@@ -26,10 +26,14 @@ constexpr int S_N = 226;      // 7 x 4  : rows 7..13 of H*B   (RB: 6 x 4)
 constexpr int S_QUX = 254;    // 4 x 14
 constexpr int S_QUU = 310;    // 16
 constexpr int S_QU = 326;     // 4
-constexpr int S_ADJ = 330;    // 16 adjugate of Quu
-constexpr int S_INV = 346;    // 16 Quu^-1
-constexpr int S_QI = 362;     // 16 symmetrised Quu^-1
-constexpr int SCR = 379;
+// the three 4x4 work matrices of the value update live in the M/Qxx area, which is dead once Qxx has been symmetrised
+constexpr int S_ADJ = S_MQ;         // 16 adjugate of Quu
+constexpr int S_INV = S_MQ + 16;    // 16 Quu^-1
+constexpr int S_QI = S_MQ + 32;     // 16 symmetrised Quu^-1
+constexpr int SCR = 331;
+#ifndef BWS_MINBLOCKS
+#define BWS_MINBLOCKS 4
+#endif
 constexpr size_t BWS_SMEM = (size_t)(2 * REC + SCR + 1) * BWS_INST * sizeof(double);
 
 // Eigen::LDLT<>::isPositive() restated (diagonal pivoting on the largest |a_ii|, sign of D tracked;
@@ -173,7 +177,7 @@ __device__ __forceinline__ int knot_rec_len(bool wb, bool term) {
     return wb ? (term ? WB_TERM_LEN : WB_STEP_LEN) : (term ? RB_TERM_LEN : RB_STEP_LEN);
 }
 
-__global__ void __launch_bounds__(BWS_THREADS, 4) k_bws(Dev d, Consts c, Opt opt, int mask_mode, int single_attempt) {
+__global__ void __launch_bounds__(BWS_THREADS, BWS_MINBLOCKS) k_bws(Dev d, Consts c, Opt opt, int mask_mode, int single_attempt) {
     extern __shared__ __align__(16) double smem[];
     const int tid = threadIdx.x;
     const int hw = tid >> 4, l = tid & 15;          // half-warp = instance slot in the CTA, lane within
@@ -449,6 +453,7 @@ __global__ void __launch_bounds__(BWS_THREADS, 4) k_bws(Dev d, Consts c, Opt opt
                 }
                 double kcol[4], du[4], gout = 0.0, dvs = 0.0;
                 bool ok = true;
+                __syncwarp();
                 ok = value_update<14>(on, l, scr, qux, qx, Hn, opt.quu_shift, kcol, du, gout, dvs);
                 __syncwarp();
                 if (on) {
@@ -535,6 +540,7 @@ __global__ void __launch_bounds__(BWS_THREADS, 4) k_bws(Dev d, Consts c, Opt opt
                     for (int jc = 0; jc < 6; ++jc) Hn[jc] = (Hn[jc] + scr[S_MQ + jc * MQ_LD + l]) / 2;
                 }
                 double kcol[4], du[4], gout = 0.0, dvs = 0.0;
+                __syncwarp();
                 bool ok = value_update<6>(on, l, scr, qux, qx, Hn, opt.quu_shift, kcol, du, gout, dvs);
                 if (on) {
                     if (!ok) failed = true;
