@@ -84,8 +84,10 @@ __device__ __forceinline__ bool ldlt4_is_positive(const double q[4][4]) {
         const bool valid = fabs(akk) > 0.0;
         if (k == 0 && !valid && !result_known) { result_known = true; result = true; }
         if (valid) {
+            // one reciprocal per pivot instead of a division per entry (<= 1 ulp on L; only the SIGNS of the pivots are used)
+            const double rk = 1.0 / akk;
 #pragma unroll
-            for (int i = k + 1; i < 4; ++i) a[i][k] /= akk;
+            for (int i = k + 1; i < 4; ++i) a[i][k] *= rk;
         }
         if (sign == 1) { if (akk < 0) sign = 3; }
         else if (sign == 2) { if (akk > 0) sign = 3; }
@@ -194,6 +196,11 @@ __global__ void __launch_bounds__(BWS_THREADS, BWS_MINBLOCKS) k_bws(Dev d, Const
     bool done = !enabled;
     const int ktb = max(nk, __shfl_xor_sync(0xffffffffu, nk, 16));     // knots this warp walks
     const double* lin_i = d.lin + (size_t)(valid ? i : 0) * d.KT * REC;
+    // lane-constant parts of the output addresses (SoA over instances): only `kk * stride` is added per knot
+    double* const gv_lane = d.Gv + (size_t)l * es + (valid ? i : 0);
+    double* const kf_lane = d.Kfb + (size_t)(4 * l) * es + (valid ? i : 0);
+    double* const du_lane = d.dufb + (size_t)l * es + (valid ? i : 0);
+    const size_t gv_knot = 14 * es, kf_knot = (size_t)KDIM * es, du_knot = 4 * es;
 
     // per-instance schedule walker used both by the prefetcher (one knot ahead) and by the math
     struct Walk { int p, off, N, mode; };
@@ -341,7 +348,7 @@ __global__ void __launch_bounds__(BWS_THREADS, BWS_MINBLOCKS) k_bws(Dev d, Const
                             gv = RBUF(R_RPHIX + l) + gv;
                         }
                         scr[S_G + l] = gv;
-                        d.Gv[((size_t)kk * 14 + l) * es + i] = gv;
+                        gv_lane[(size_t)kk * gv_knot] = gv;
                     }
                 }
                 __syncwarp();
@@ -462,11 +469,11 @@ __global__ void __launch_bounds__(BWS_THREADS, BWS_MINBLOCKS) k_bws(Dev d, Const
                         dV += dvs;
                         if (l < 14) {
                             scr[S_G + l] = gout;
-                            d.Gv[((size_t)kk * 14 + l) * es + i] = gout;
+                            gv_lane[(size_t)kk * gv_knot] = gout;
 #pragma unroll
-                            for (int cc = 0; cc < 4; ++cc) d.Kfb[((size_t)kk * KDIM + cc + 4 * l) * es + i] = kcol[cc];
+                            for (int cc = 0; cc < 4; ++cc) kf_lane[(size_t)kk * kf_knot + (size_t)cc * es] = kcol[cc];
                         }
-                        if (l < 4) d.dufb[((size_t)kk * 4 + l) * es + i] = du[l];
+                        if (l < 4) du_lane[(size_t)kk * du_knot] = du[l];
                     }
                 }
                 __syncwarp();
@@ -548,11 +555,11 @@ __global__ void __launch_bounds__(BWS_THREADS, BWS_MINBLOCKS) k_bws(Dev d, Const
                         dV += dvs;
                         if (l < 6) {
                             scr[S_G + l] = gout;
-                            d.Gv[((size_t)kk * 14 + l) * es + i] = gout;
+                            gv_lane[(size_t)kk * gv_knot] = gout;
 #pragma unroll
-                            for (int cc = 0; cc < 4; ++cc) d.Kfb[((size_t)kk * KDIM + cc + 4 * l) * es + i] = kcol[cc];
+                            for (int cc = 0; cc < 4; ++cc) kf_lane[(size_t)kk * kf_knot + (size_t)cc * es] = kcol[cc];
                         }
-                        if (l < 4) d.dufb[((size_t)kk * 4 + l) * es + i] = du[l];
+                        if (l < 4) du_lane[(size_t)kk * du_knot] = du[l];
                     }
                 }
                 __syncwarp();
