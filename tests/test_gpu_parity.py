@@ -320,3 +320,39 @@ def test_cpp_batched_test_main_reproduces_default_run(tmp_path):
     assert len(lines) == 720 and len(lines[0].split()) == 14 and len(lines[-1].split()) == 6
     assert abs(float(lines[0].split()[0]) - 0.0927) < 1e-15
     assert abs(float(lines[0].split()[13]) - gold["final"]["x_first"][13]) < 1e-12
+
+
+def test_odd_shapes_and_start_modes():
+    """Ragged / extreme problem shapes: a single whole-body phase, 12 phases, start in another gait mode, coarser time steps,
+    maximum knots per phase (N_TIMESTEPS_MAX = 110), different command velocity / height - all in ONE batch."""
+    import mhpc_minimal_env_b200 as m
+    from oracle.oracle_py import OracleSolver
+    base = make_specs(8, 2)
+    variants = [dict(n_wbphase=1, n_fbphase=0), dict(n_wbphase=6, n_fbphase=6), dict(cmode=3), dict(cmode=2, n_wbphase=3, n_fbphase=2),
+                dict(dt_wb=0.00125, dt_fb=0.00125), dict(gait_timing=[0.11, 0.06, 0.11, 0.06]), dict(vel=1.0, height=-0.02),
+                dict(n_wbphase=2, n_fbphase=7, dt_fb=0.002)]
+    specs = []
+    for s, v in zip(base, variants):
+        s = dict(s)
+        s.update(v)
+        specs.append(s)
+    gpu = m.BatchedMHPC([to_gpu_problem(s) for s in specs])
+    gpu.initialization()
+    gpu.solve()
+    res = gpu.results()
+    for i, s in enumerate(specs):
+        o = OracleSolver(to_orc_problem(s))
+        o.initialization()
+        assert gpu.schedule(i) == o.schedule()
+        st = o.solve()
+        ro, rg = o.records(), gpu.records(i)
+        assert [(r["iter_AL"], r["iter_DDP"], r["n_bws"], r["n_fit"], r["reg"], r["eps"]) for r in rg] == \
+               [(r["iter_AL"], r["iter_DDP"], r["n_bws"], r["n_fit"], r["reg"], r["eps"]) for r in ro], (i, variants[i])
+        assert (res[i]["status"] == 3) == (st == 1)
+        for a, b in zip(rg, ro):
+            if np.isnan(b["cost"]):      # a diverged explicit-Euler rollout is NaN in the reference too: same flow, same NaN
+                assert np.isnan(a["cost"])
+                continue
+            assert abs(a["cost"] - b["cost"]) <= 1e-5 * abs(b["cost"]), (i, variants[i], a["cost"], b["cost"])
+        if not np.isnan(o.scalars()["cost"]):
+            _cmp_fields(gpu, o, i, ["X_NOM", "U_NOM"], 1e-4, "odd shapes trajectory")
