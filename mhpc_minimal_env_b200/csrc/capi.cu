@@ -45,6 +45,12 @@ struct mhpc_batch {
     long long bytes = 0;
     int* knot_list[CLS_N] = {nullptr};
     int knot_cnt[CLS_N] = {0};
+    // non-uniform batches (instances with different schedules): per knot class an explicit list of (knot, instance)
+    // pairs, so that every lane of a linearisation warp evaluates the SAME generated function (no class divergence)
+    unsigned* pair_list[CLS_N] = {nullptr};
+    int pair_cnt[CLS_N] = {0};
+    bool uniform = true;
+    size_t pair_cap[CLS_N] = {0};
     int alloc_KT = 0, alloc_P = 0;
     // timing
     bool timing = false;
@@ -121,10 +127,11 @@ static int dalloc(mhpc_batch* b, T** p, size_t count) {
     return 0;
 }
 static void free_all(mhpc_batch* b) {
+    for (int c = 0; c < CLS_N; ++c) { if (b->pair_list[c]) cudaFree(b->pair_list[c]); b->pair_cap[c] = 0; }
     for (void* p : b->allocs) cudaFree(p);
     b->allocs.clear();
     b->bytes = 0;
-    for (int c = 0; c < CLS_N; ++c) { b->knot_list[c] = nullptr; b->knot_cnt[c] = 0; }
+    for (int c = 0; c < CLS_N; ++c) { b->knot_list[c] = nullptr; b->knot_cnt[c] = 0; b->pair_list[c] = nullptr; b->pair_cnt[c] = 0; }
 }
 
 // stage timing helpers
@@ -306,6 +313,50 @@ int mhpc_batch_set_problems(mhpc_batch* b, const mhpc_problem* pr) {
             }
         }
     }
+    // uniform batch <=> every instance has the schedule of instance 0
+    b->uniform = true;
+    for (int i = 1; i < n && b->uniform; ++i) {
+        if (b->h_nph[i] != b->h_nph[0] || b->h_nwb[i] != b->h_nwb[0]) b->uniform = false;
+        for (int p = 0; p < b->h_nph[0] && b->uniform; ++p)
+            if (b->h_mode[(size_t)p * npad + i] != b->h_mode[(size_t)p * npad] || b->h_N[(size_t)p * npad + i] != b->h_N[(size_t)p * npad]) b->uniform = false;
+    }
+    if (!b->uniform) {
+        if (n >= (1 << 20) || d.KT >= (1 << 12)) return fail("set_problems: non-uniform batches support < 2^20 instances and < 4096 knots");
+        std::vector<std::vector<unsigned>> pairs(CLS_N);
+        std::vector<std::vector<int>> cls_at((size_t)d.KT);   // per knot: (instance, class) in instance order
+        for (int c = 0; c < CLS_N; ++c) pairs[c].reserve((size_t)n * 64);
+        std::vector<unsigned char> cls_of((size_t)n * d.KT, 255);
+        for (int i = 0; i < n; ++i) {
+            const int np = b->h_nph[i], nwb = b->h_nwb[i];
+            for (int p = 0; p < np; ++p) {
+                const int mode = b->h_mode[(size_t)p * npad + i], N = b->h_N[(size_t)p * npad + i], off = b->h_off[(size_t)p * npad + i];
+                const bool wb = p < nwb;
+                for (int k = 0; k < N; ++k) {
+                    const bool term = (k == N - 1);
+                    int cls;
+                    if (wb && !term) cls = mode == 1 ? CLS_BS : mode == 3 ? CLS_FS : CLS_FL;
+                    else if (wb) cls = mode == 2 ? CLS_IMPF : mode == 4 ? CLS_IMPB : CLS_LIGHT;
+                    else cls = CLS_LIGHT;
+                    cls_of[(size_t)(off + k) * n + i] = (unsigned char)cls;
+                }
+            }
+        }
+        for (int kk = 0; kk < d.KT; ++kk)       // knot-major, instance-minor: neighbouring lanes read neighbouring instances
+            for (int i = 0; i < n; ++i) {
+                const unsigned char c = cls_of[(size_t)kk * n + i];
+                if (c != 255) pairs[c].push_back(((unsigned)kk << 20) | (unsigned)i);
+            }
+        for (int c = 0; c < CLS_N; ++c) {
+            b->pair_cnt[c] = (int)pairs[c].size();
+            if (pairs[c].empty()) continue;
+            if (!b->pair_list[c] || b->pair_cap[c] < pairs[c].size()) {
+                if (b->pair_list[c]) cudaFree(b->pair_list[c]);
+                CK(cudaMalloc(&b->pair_list[c], pairs[c].size() * sizeof(unsigned)));
+                b->pair_cap[c] = pairs[c].size();
+            }
+            CK(cudaMemcpy(b->pair_list[c], pairs[c].data(), pairs[c].size() * sizeof(unsigned), cudaMemcpyHostToDevice));
+        }
+    }
     for (int c = 0; c < CLS_N; ++c) {
         std::vector<int> v(cls_knots[c].begin(), cls_knots[c].end());
         b->knot_cnt[c] = (int)v.size();
@@ -329,12 +380,12 @@ int mhpc_batch_set_problems(mhpc_batch* b, const mhpc_problem* pr) {
 static int linearize(mhpc_batch* b, int mask_mode) {
     Stage st(b, TB_LIN);
     const Dev& d = b->d;
-    launch_lin_BS(d, b->c, b->opt, mask_mode, b->knot_list[CLS_BS], b->knot_cnt[CLS_BS], b->stream);
-    launch_lin_FS(d, b->c, b->opt, mask_mode, b->knot_list[CLS_FS], b->knot_cnt[CLS_FS], b->stream);
-    launch_lin_FL(d, b->c, b->opt, mask_mode, b->knot_list[CLS_FL], b->knot_cnt[CLS_FL], b->stream);
-    launch_lin_IMPF(d, b->c, b->opt, mask_mode, b->knot_list[CLS_IMPF], b->knot_cnt[CLS_IMPF], b->stream);
-    launch_lin_IMPB(d, b->c, b->opt, mask_mode, b->knot_list[CLS_IMPB], b->knot_cnt[CLS_IMPB], b->stream);
-    launch_lin_LIGHT(d, b->c, b->opt, mask_mode, b->knot_list[CLS_LIGHT], b->knot_cnt[CLS_LIGHT], b->stream);
+    typedef void (*lin_fn)(const Dev&, const Consts&, const Opt&, int, const int*, int, cudaStream_t);
+    const lin_fn fns[CLS_N] = {launch_lin_BS, launch_lin_FS, launch_lin_FL, launch_lin_IMPF, launch_lin_IMPB, launch_lin_LIGHT};
+    for (int c = 0; c < CLS_N; ++c) {
+        if (b->uniform) fns[c](d, b->c, b->opt, mask_mode, b->knot_list[c], b->knot_cnt[c], b->stream);
+        else fns[c](d, b->c, b->opt, mask_mode, (const int*)b->pair_list[c], -b->pair_cnt[c], b->stream);   // negative count = pair list
+    }
     for (int c = 0; c < CLS_N; ++c) b->launches += b->knot_cnt[c] > 0;
     CK(cudaGetLastError());
     return 0;

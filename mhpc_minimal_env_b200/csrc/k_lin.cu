@@ -146,14 +146,23 @@ __device__ inline void wb_cost_partials(const Consts& c, int mode, double dt, co
 #ifndef LIN_MINBLOCKS
 #define LIN_MINBLOCKS 1
 #endif
-__global__ void __launch_bounds__(LIN_THREADS, LIN_MINBLOCKS) k_lin(Dev d, Consts c, Opt opt, int mask_mode, const int* __restrict__ knots) {
+__global__ void __launch_bounds__(LIN_THREADS, LIN_MINBLOCKS) k_lin(Dev d, Consts c, Opt opt, int mask_mode, const int* __restrict__ knots, int n_pairs) {
     extern __shared__ __align__(16) double sx_smem_base[];
     volatile double* sx_sm = sx_smem_base + threadIdx.x;
     (void)sx_sm;
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= d.n) return;
+    int i, kk;
+    if (n_pairs > 0) {   // non-uniform batch: explicit (knot, instance) work list of this knot class
+        const int t = blockIdx.x * blockDim.x + threadIdx.x;
+        if (t >= n_pairs) return;
+        const unsigned pr = ((const unsigned*)knots)[t];
+        kk = (int)(pr >> 20);
+        i = (int)(pr & 0xFFFFFu);
+    } else {
+        i = blockIdx.x * blockDim.x + threadIdx.x;
+        if (i >= d.n) return;
+        kk = knots[blockIdx.y];
+    }
     if (!inst_enabled(d, i, mask_mode)) return;
-    const int kk = knots[blockIdx.y];
     int p, k;
     if (!knot_to_phase(d, i, kk, p, k)) return;
     const int mode = d.ph_mode[ph_idx(d, p, i)], N = d.ph_N[ph_idx(d, p, i)];
@@ -299,12 +308,17 @@ __global__ void __launch_bounds__(LIN_THREADS, LIN_MINBLOCKS) k_lin(Dev d, Const
 #endif
 
 void LIN_LAUNCH(const Dev& d, const Consts& c, const Opt& opt, int mask_mode, const int* knots, int n_knots, cudaStream_t s) {
-    if (n_knots <= 0) return;
+    if (n_knots == 0) return;
     // 128-thread blocks; the Jacobian classes carry MHPC_RA_SMEM_SLOTS shared-memory spill slots per thread
     // (codegen/regalloc.py), sized so that LIN_MINBLOCKS blocks are resident per SM.
     if (LIN_SMEM > 48 * 1024) cudaFuncSetAttribute(k_lin, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LIN_SMEM);
+    if (n_knots < 0) {   // (knot, instance) pair list of -n_knots entries
+        const int n_pairs = -n_knots;
+        k_lin<<<(n_pairs + LIN_THREADS - 1) / LIN_THREADS, LIN_THREADS, LIN_SMEM, s>>>(d, c, opt, mask_mode, knots, n_pairs);
+        return;
+    }
     dim3 grid((d.n + LIN_THREADS - 1) / LIN_THREADS, n_knots);
-    k_lin<<<grid, LIN_THREADS, LIN_SMEM, s>>>(d, c, opt, mask_mode, knots);
+    k_lin<<<grid, LIN_THREADS, LIN_SMEM, s>>>(d, c, opt, mask_mode, knots, 0);
 }
 
 }  // namespace mhpc

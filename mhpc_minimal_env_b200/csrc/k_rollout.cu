@@ -1,7 +1,10 @@
 // Forward rollout (SinglePhase.cpp:62-144 + MultiPhaseDDP.cpp:28-76,351-379): one thread per
 // (line-search slot, instance); all step sizes of the Armijo search are evaluated as parallel
-// rollouts.  Time is sequential inside the thread; lanes are 32 consecutive instances, so every
-// load/store of the SoA trajectories is a full 256 B row.
+// rollouts.  Time is sequential inside the thread.  Lane mapping: with S = 2^k slots per launch a warp
+// holds the S trials of 32/S consecutive instances (lane = instance_in_warp * S + slot), so the trials
+// of one instance - which share its schedule, nominal trajectory and gains - never diverge and read K,
+// du, x_nom, u_nom as broadcasts, while each store still fills whole 32 B sectors (32/S consecutive
+// instances per row).  A single-slot launch (forward_sweep) maps lanes to 32 consecutive instances.
 #include "kernels.h"
 #include "model.cuh"
 
@@ -9,7 +12,15 @@ namespace mhpc {
 
 __global__ void __launch_bounds__(128) k_rollout(Dev d, Consts c, Opt opt, int mask_mode, int n_slots, int trial0, EpsList eps_list) {
     const int tid = blockIdx.x * blockDim.x + threadIdx.x;
-    const int w = tid / d.npad, i = tid - w * d.npad;
+    int w, i;
+    if (n_slots > 1 && n_slots <= 32 && (n_slots & (n_slots - 1)) == 0) {
+        const int lane = tid & 31, per_warp = 32 / n_slots;
+        w = lane % n_slots;
+        i = (tid >> 5) * per_warp + lane / n_slots;
+    } else {
+        w = tid / d.npad;
+        i = tid - w * d.npad;
+    }
     if (w >= n_slots || i >= d.n) return;
     if (!inst_enabled(d, i, mask_mode)) return;
     if (mask_mode == MASK_LS && d.si[(size_t)SI_LS_DONE * d.npad + i]) return;
