@@ -126,7 +126,10 @@ __device__ __forceinline__ bool value_update(bool on, int l, double* scr, const 
         double det = QM(0, 0) * scr[S_ADJ + 0 + 4 * 0];
 #pragma unroll
         for (int i = 1; i < 4; ++i) det += QM(i, 0) * scr[S_ADJ + 0 + 4 * i];
-        scr[S_INV + l] = scr[S_ADJ + l] / det;
+        // adj / det; a zero numerator (every off-diagonal entry in the rigid-body phases) would send the FP64 division
+        // through its slow path (quotient below the fast path's range check): 0 * det has the same value and sign
+        const double adj = scr[S_ADJ + l];
+        scr[S_INV + l] = (adj == 0.0) ? adj * det : adj / det;
 #undef QM
     }
     __syncwarp();
