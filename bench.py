@@ -200,6 +200,7 @@ def main():
     batch.set_stream(stream.cuda_stream)
 
     def step():
+        batch.set_option(opt)      # a fresh MHPCLocomotion per solve: solve() leaves _option modified (MultiPhaseDDP.cpp:178-183,273-277)
         batch.initialization()
         batch.solve()
 

@@ -100,6 +100,12 @@ int mhpc_batch_set_problems(mhpc_batch* b, const mhpc_problem* problems);
 /* MHPCLocomotion::initialization (MHPCLocomotion.cpp:47-53): memory_reset, build_problem (references,
  * AL/ReB parameters), warmstart (boundingPDControl.cpp) - all on the device. */
 int mhpc_batch_initialization(mhpc_batch* b);
+/* MultiPhaseDDP::set_initial_condition (MultiPhaseDDP.h:24-25) for every instance; x0 = [n][14] host doubles. */
+int mhpc_batch_set_initial_condition(mhpc_batch* b, const double* x0);
+/* MHPCLocomotion::update_problem (MHPCLocomotion.cpp:107-158): the receding-horizon shift - phase buffers of each
+ * model group rotate by one, the gait advances one mode, every phase is re-initialised, the reference is regenerated
+ * from the current x0.  (Never called by the reference's main, but part of its class; parity is checked against it.) */
+int mhpc_batch_update_problem(mhpc_batch* b);
 
 /* ---- MultiPhaseDDP<double> entry points, batched (all instances in lock step) -------------------- */
 int mhpc_batch_forward_sweep(mhpc_batch* b, double eps);                 /* MultiPhaseDDP.cpp:28-48   */

@@ -52,7 +52,7 @@ class Timing(C.Structure):
 
 EXPORTS = [
     "mhpc_default_option", "mhpc_default_problem", "mhpc_batch_create", "mhpc_batch_destroy", "mhpc_last_error",
-    "mhpc_batch_set_option", "mhpc_batch_set_stream", "mhpc_batch_set_problems", "mhpc_batch_initialization",
+    "mhpc_batch_set_option", "mhpc_batch_set_stream", "mhpc_batch_set_problems", "mhpc_batch_initialization", "mhpc_batch_set_initial_condition", "mhpc_batch_update_problem",
     "mhpc_batch_forward_sweep", "mhpc_batch_forward_sweep_dynamics_only", "mhpc_batch_forward_sweep_partials_only",
     "mhpc_batch_backward_sweep", "mhpc_batch_forward_iteration", "mhpc_batch_update_nominal_trajectory",
     "mhpc_batch_update_AL_ReB_param", "mhpc_batch_solve", "mhpc_batch_solve_host", "mhpc_batch_synchronize",
@@ -84,7 +84,8 @@ def load():
     L.mhpc_batch_set_option.argtypes = [vp, C.POINTER(HSDDPOption)]
     L.mhpc_batch_set_stream.argtypes = [vp, vp]
     L.mhpc_batch_set_problems.argtypes = [vp, C.POINTER(Problem)]
-    for f in ("mhpc_batch_initialization", "mhpc_batch_forward_sweep_partials_only", "mhpc_batch_update_nominal_trajectory",
+    L.mhpc_batch_set_initial_condition.argtypes = [vp, dp]
+    for f in ("mhpc_batch_initialization", "mhpc_batch_update_problem", "mhpc_batch_forward_sweep_partials_only", "mhpc_batch_update_nominal_trajectory",
               "mhpc_batch_update_AL_ReB_param", "mhpc_batch_synchronize"):
         getattr(L, f).argtypes = [vp]
     L.mhpc_batch_forward_sweep.argtypes = [vp, C.c_double]
@@ -181,6 +182,11 @@ class BatchedMHPC:
 
     def set_stream(self, cuda_stream_ptr: int): self._ck(self.L.mhpc_batch_set_stream(self.h, C.c_void_p(cuda_stream_ptr)))
     def initialization(self): self._ck(self.L.mhpc_batch_initialization(self.h))
+    def update_problem(self): self._ck(self.L.mhpc_batch_update_problem(self.h))
+
+    def set_initial_condition(self, x0):
+        a = np.ascontiguousarray(np.asarray(x0, dtype=np.float64).reshape(self.n, 14))
+        self._ck(self.L.mhpc_batch_set_initial_condition(self.h, _dp(a)))
     def forward_sweep(self, eps: float): self._ck(self.L.mhpc_batch_forward_sweep(self.h, eps))
     def forward_sweep_dynamics_only(self, eps: float): self._ck(self.L.mhpc_batch_forward_sweep_dynamics_only(self.h, eps))
     def forward_sweep_partials_only(self): self._ck(self.L.mhpc_batch_forward_sweep_partials_only(self.h))

@@ -61,6 +61,8 @@ struct mhpc_batch {
     void* stage = nullptr;
     size_t stage_bytes = 0;
     bool keep_dead_partials = false;
+    void* rot_tmp = nullptr;
+    size_t rot_bytes = 0;
 };
 
 static void fill_opt(Opt& o, const mhpc_hsddp_option& s) {
@@ -192,6 +194,7 @@ void mhpc_batch_destroy(mhpc_batch* b) {
     cudaStreamSynchronize(b->stream);
     free_all(b);
     if (b->stage) cudaFree(b->stage);
+    if (b->rot_tmp) cudaFree(b->rot_tmp);
     for (auto& e : b->evs) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
     if (b->own_stream && b->stream) cudaStreamDestroy(b->stream);
     delete b;
@@ -199,6 +202,11 @@ void mhpc_batch_destroy(mhpc_batch* b) {
 int mhpc_batch_set_option(mhpc_batch* b, const mhpc_hsddp_option* opt) {
     fill_opt(b->opt, *opt);
     fill_eps(b->eps, b->opt.alpha);
+    if (b->have_problems) {
+        CK(cudaSetDevice(b->device));
+        launch_reset_option_state(b->d, b->opt, b->stream);
+        CK(cudaGetLastError());
+    }
     return 0;
 }
 int mhpc_batch_set_stream(mhpc_batch* b, void* s) {
@@ -237,18 +245,19 @@ int mhpc_batch_set_problems(mhpc_batch* b, const mhpc_problem* pr) {
         b->h_nph[i] = np; b->h_nwb[i] = q.n_wbphase;
         const double dt_wb = q.dt_wb, dt_fb = q.dt_fb;   // float -> double (MHPCLocomotion.h:59)
         dtw[i] = dt_wb; dtf[i] = dt_fb; vel[i] = q.vel; hgt[i] = q.height;
-        int mode = q.cmode, off = 0;
+        int mode = q.cmode, used = 0;
         for (int p = 0; p < np; ++p) {   // Gait.h:55-77, MHPCLocomotion.cpp:76,85
             if (p > 0) mode = gait_next(q, mode);
             if (mode < 1 || mode > 4) return fail("set_problems: modes must be 1..4");
             const float timing = q.gait_timing[mode - 1];
             const int N = (int)std::round(timing / (p < q.n_wbphase ? dt_wb : dt_fb));
             if (N < 2) return fail("set_problems: a phase needs at least 2 knots");
-            b->h_mode[(size_t)p * npad + i] = mode; b->h_N[(size_t)p * npad + i] = N; b->h_off[(size_t)p * npad + i] = off;
-            off += N;
+            if (N > KSTRIDE) return fail("set_problems: a phase may have at most N_TIMESTEPS_MAX = 110 knots (MHPC_CPPTypes.h:9)");
+            b->h_mode[(size_t)p * npad + i] = mode; b->h_N[(size_t)p * npad + i] = N; b->h_off[(size_t)p * npad + i] = p * KSTRIDE;
+            used += N;
         }
-        b->h_nk[i] = off;
-        KT = std::max(KT, off);
+        b->h_nk[i] = used;
+        KT = std::max(KT, np * KSTRIDE);
         for (int e = 0; e < 14; ++e) x0[(size_t)e * npad + i] = q.x0[e];
     }
     // same schedule as the previous batch (the common MPC case): only the per-instance scalars change
@@ -294,6 +303,7 @@ int mhpc_batch_set_problems(mhpc_batch* b, const mhpc_problem* pr) {
         for (int c = 0; c < CLS_N; ++c) rc |= dalloc(b, &b->knot_list[c], KT);
         if (rc) return -1;
         b->alloc_KT = KT; b->alloc_P = P;
+        launch_reset_option_state(d, b->opt, b->stream);   // MultiPhaseDDP(n_phases, option): _option = option
     }
     Dev& d = b->d;
     // record lengths per (block, knot) and knot lists per class
@@ -415,14 +425,55 @@ int mhpc_batch_initialization(mhpc_batch* b) {
     return 0;
 }
 
+// MultiPhaseDDP::set_initial_condition (MultiPhaseDDP.h:24-25) for every instance: x0 is [n][14] on the host
+int mhpc_batch_set_initial_condition(mhpc_batch* b, const double* x0) {
+    if (need(b)) return -1;
+    std::vector<double> soa((size_t)14 * b->d.npad, 0.0);
+    for (int i = 0; i < b->n; ++i)
+        for (int e = 0; e < 14; ++e) { b->problems[i].x0[e] = x0[(size_t)i * 14 + e]; soa[(size_t)e * b->d.npad + i] = x0[(size_t)i * 14 + e]; }
+    CK(cudaMemcpyAsync(b->d.x0, soa.data(), soa.size() * sizeof(double), cudaMemcpyHostToDevice, b->stream));
+    CK(cudaStreamSynchronize(b->stream));
+    return 0;
+}
+
+// MHPCLocomotion::update_problem (MHPCLocomotion.cpp:107-158): receding-horizon shift by one phase.
+int mhpc_batch_update_problem(mhpc_batch* b) {
+    if (need(b)) return -1;
+    Dev& d = b->d;
+    // (1) rotate the phase buffers of each model group on the device (nominal, accepted rollout, K, du, G)
+    const size_t tmp_need = (size_t)d.KT * KDIM * d.npad * sizeof(double);
+    if (b->rot_bytes < tmp_need) {
+        if (b->rot_tmp) cudaFree(b->rot_tmp);
+        CK(cudaMalloc(&b->rot_tmp, tmp_need));
+        b->rot_bytes = tmp_need;
+    }
+    double* tmp = (double*)b->rot_tmp;
+    struct Arr { double* p; int elems; int acc; };
+    const Arr arrs[5] = {{d.st_nom, ST, 0}, {d.st_act, ST, 1}, {d.Kfb, KDIM, 0}, {d.dufb, 4, 0}, {d.Gv, 14, 0}};
+    for (const Arr& a : arrs) {
+        const size_t bytes = (size_t)d.KT * a.elems * d.npad * sizeof(double);
+        CK(cudaMemcpyAsync(tmp, a.p, bytes, cudaMemcpyDeviceToDevice, b->stream));      // rows of unused phases keep their content
+        launch_rotate(d, a.p, tmp, a.elems, a.acc, b->stream);
+        CK(cudaMemcpyAsync(a.p, tmp, bytes, cudaMemcpyDeviceToDevice, b->stream));      // (for st_act: the accepted rollout becomes slot 0)
+    }
+    CK(cudaStreamSynchronize(b->stream));
+    // (2) the gait advances one mode; schedule, knot lists and x0 are re-uploaded through the normal path
+    std::vector<mhpc_problem> pr = b->problems;
+    for (mhpc_problem& q : pr) q.cmode = gait_next(q, q.cmode);
+    if (mhpc_batch_set_problems(b, pr.data())) return -1;
+    // (3) every phase is re-initialised (AL/ReB parameters) and the reference regenerated from _x0
+    launch_setup_refs_params(d, b->c, b->stream);
+    launch_spread_last_knot(d, b->stream);
+    CK(cudaGetLastError());
+    return 0;
+}
+
 int mhpc_batch_forward_sweep(mhpc_batch* b, double eps) {
     if (need(b)) return -1;
     EpsList one{}; one.n = 1; one.eps[0] = eps;
     // the step-level API applies the option's ReB flag as is (the solve loop overrides it per AL iteration)
     CK(cudaMemsetAsync(b->d.si + (size_t)SI_STATUS * b->d.npad, 0, b->d.npad * sizeof(int), b->stream));
-    std::vector<int> reb(b->d.npad, b->opt.ReB_active);
-    CK(cudaMemcpyAsync(b->d.si + (size_t)SI_REB_ON * b->d.npad, reb.data(), reb.size() * sizeof(int), cudaMemcpyHostToDevice, b->stream));
-    CK(cudaStreamSynchronize(b->stream));
+    launch_reb_from_option(b->d, b->stream);
     launch_rollout(b->d, b->c, b->opt, MASK_ALL, 1, 0, one, b->stream);
     launch_accept_slot0(b->d, MASK_ALL, 2, b->stream);
     if (linearize(b, MASK_ALL)) return -1;
@@ -432,9 +483,7 @@ int mhpc_batch_forward_sweep(mhpc_batch* b, double eps) {
 int mhpc_batch_forward_sweep_dynamics_only(mhpc_batch* b, double eps) {
     if (need(b)) return -1;
     EpsList one{}; one.n = 1; one.eps[0] = eps;
-    std::vector<int> reb(b->d.npad, b->opt.ReB_active);
-    CK(cudaMemcpyAsync(b->d.si + (size_t)SI_REB_ON * b->d.npad, reb.data(), reb.size() * sizeof(int), cudaMemcpyHostToDevice, b->stream));
-    CK(cudaStreamSynchronize(b->stream));
+    launch_reb_from_option(b->d, b->stream);
     launch_rollout(b->d, b->c, b->opt, MASK_ALL, 1, 0, one, b->stream);
     launch_accept_slot0(b->d, MASK_ALL, 1, b->stream);
     CK(cudaGetLastError());
@@ -442,10 +491,10 @@ int mhpc_batch_forward_sweep_dynamics_only(mhpc_batch* b, double eps) {
 }
 int mhpc_batch_forward_sweep_partials_only(mhpc_batch* b) {
     if (need(b)) return -1;
-    std::vector<int> v(b->d.npad, 1), reb(b->d.npad, b->opt.ReB_active);
+    std::vector<int> v(b->d.npad, 1);
     CK(cudaMemcpyAsync(b->d.si + (size_t)SI_AL_PARTIALS * b->d.npad, v.data(), v.size() * sizeof(int), cudaMemcpyHostToDevice, b->stream));
-    CK(cudaMemcpyAsync(b->d.si + (size_t)SI_REB_ON * b->d.npad, reb.data(), reb.size() * sizeof(int), cudaMemcpyHostToDevice, b->stream));
     CK(cudaStreamSynchronize(b->stream));
+    launch_reb_from_option(b->d, b->stream);
     return linearize(b, MASK_ALL);
 }
 int mhpc_batch_backward_sweep(mhpc_batch* b, double reg, int* success) {
@@ -479,11 +528,11 @@ static int line_search(mhpc_batch* b, int mask_ls, int mask_sel) {
 }
 int mhpc_batch_forward_iteration(mhpc_batch* b, int* trials) {
     if (need(b)) return -1;
-    std::vector<int> reb(b->d.npad, b->opt.ReB_active), act(b->d.npad, 1);
+    std::vector<int> act(b->d.npad, 1);
     CK(cudaMemsetAsync(b->d.si + (size_t)SI_STATUS * b->d.npad, 0, b->d.npad * sizeof(int), b->stream));
-    CK(cudaMemcpyAsync(b->d.si + (size_t)SI_REB_ON * b->d.npad, reb.data(), reb.size() * sizeof(int), cudaMemcpyHostToDevice, b->stream));
     CK(cudaMemcpyAsync(b->d.si + (size_t)SI_DDP_ACTIVE * b->d.npad, act.data(), act.size() * sizeof(int), cudaMemcpyHostToDevice, b->stream));
     CK(cudaStreamSynchronize(b->stream));
+    launch_reb_from_option(b->d, b->stream);
     launch_ls_begin(b->d, MASK_ALL, b->stream);
     if (line_search(b, MASK_LS, MASK_ALL)) return -1;
     if (trials) {
@@ -780,11 +829,17 @@ int mhpc_batch_get_field(mhpc_batch* b, int inst, int phase, int field, double* 
 __global__ void k_gather_exec(Dev d, int kn, double* st_out, double* gain_out) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= d.n) return;
-    const int k = blockIdx.y;
-    if (st_out) for (int e = 0; e < ST; ++e) st_out[((size_t)i * kn + k) * ST + e] = d.st_nom[((size_t)k * ST + e) * d.npad + i];
+    const int k = blockIdx.y;   // k-th used knot of the horizon -> knot slot (phase blocks of KSTRIDE)
+    int kk = -1, c = k;
+    for (int p = 0; p < d.n_phases[i]; ++p) {
+        const int N = d.ph_N[ph_idx(d, p, i)];
+        if (c < N) { kk = p * KSTRIDE + c; break; }
+        c -= N;
+    }
+    if (st_out) for (int e = 0; e < ST; ++e) st_out[((size_t)i * kn + k) * ST + e] = kk >= 0 ? d.st_nom[((size_t)kk * ST + e) * d.npad + i] : 0.0;
     if (gain_out) {
-        for (int e = 0; e < KDIM; ++e) gain_out[((size_t)i * kn + k) * 60 + e] = d.Kfb[((size_t)k * KDIM + e) * d.npad + i];
-        for (int e = 0; e < 4; ++e) gain_out[((size_t)i * kn + k) * 60 + 56 + e] = d.dufb[((size_t)k * 4 + e) * d.npad + i];
+        for (int e = 0; e < KDIM; ++e) gain_out[((size_t)i * kn + k) * 60 + e] = kk >= 0 ? d.Kfb[((size_t)kk * KDIM + e) * d.npad + i] : 0.0;
+        for (int e = 0; e < 4; ++e) gain_out[((size_t)i * kn + k) * 60 + 56 + e] = kk >= 0 ? d.dufb[((size_t)kk * 4 + e) * d.npad + i] : 0.0;
     }
 }
 __global__ void k_results_pack(Dev d, mhpc_result* out) {
@@ -818,6 +873,7 @@ int mhpc_batch_solve_host(mhpc_batch* b, const mhpc_problem* problems, mhpc_resu
                           double* exec_state, double* exec_gain, int exec_knots) {
     if (!b) return fail("null handle");
     if (mhpc_batch_set_problems(b, problems)) return -1;
+    launch_reset_option_state(b->d, b->opt, b->stream);   // behaves like a freshly constructed MHPCLocomotion per call
     if (mhpc_batch_initialization(b)) return -1;
     if (mhpc_batch_solve(b, 0)) return -1;
     const Dev& d = b->d;

@@ -18,6 +18,9 @@ constexpr int ST = 22;            // x(14) u(4) y(4) per knot
 constexpr int KDIM = 56;          // K is 4x14 column-major (RB uses the first 24 = 4x6)
 constexpr int REC = 176;          // doubles per knot record
 constexpr int MAXP = 16;          // phases per instance (reference default 8)
+constexpr int KSTRIDE = 110;      // knot slots per phase = N_TIMESTEPS_MAX (MHPC_CPPTypes.h:9): phase p owns knots [p*110, p*110 + N_p),
+                                  // exactly like the reference's per-phase arrays, so the receding-horizon buffer rotation
+                                  // (MHPCLocomotion.cpp:107-158) moves whole blocks including their stale tails
 constexpr int MAX_TRIALS = 16;    // line-search step sizes (reference: 10)
 constexpr int NPAR = 9;           // per-phase AL/ReB parameters
 
@@ -54,9 +57,12 @@ constexpr int RB_TERM_LEN = 6;
 enum { PAR_SIGMA = 0, PAR_LAMBDA, PAR_DELTA_T, PAR_DELTA_J, PAR_DELTA_G, PAR_EPS_T, PAR_EPS_J, PAR_EPS_G, PAR_H };
 
 // per-instance solver scalars
-enum { SD_COST = 0, SD_COST_PREV, SD_DV, SD_VIOL, SD_REG, SD_REG_USED, SD_UPD_PENALTY, SD_EPS_ACC, SD_N };
+// SD_OPT_UPD / SI_OPT_REB are the per-instance copies of `_option.update_penalty` / `_option.ReB_active`, which
+// MultiPhaseDDP::solve overwrites and never restores (MultiPhaseDDP.cpp:160-161,178-183,273-277): they survive
+// initialization() and later solves exactly like the members of a re-used MHPCLocomotion object; *_BASE are solve()'s locals.
+enum { SD_COST = 0, SD_COST_PREV, SD_DV, SD_VIOL, SD_REG, SD_REG_USED, SD_UPD_PENALTY, SD_EPS_ACC, SD_OPT_UPD, SD_UPD_BASE, SD_N };
 enum { SI_STATUS = 0, SI_ITER_AL, SI_ITER_DDP, SI_DDP_ACTIVE, SI_REB_ON, SI_N_BWS, SI_N_FIT, SI_ACC_SLOT, SI_LS_DONE,
-       SI_AL_PARTIALS, SI_N_REC, SI_BWS_OK, SI_N };
+       SI_AL_PARTIALS, SI_N_REC, SI_BWS_OK, SI_OPT_REB, SI_REB_BASE, SI_N };
 enum { STATUS_RUNNING = 0, STATUS_CONVERGED = 1, STATUS_MAXITER = 2, STATUS_REG_ABORT = 3 };
 constexpr int REC_I = 4, REC_D = 6;  // per-iteration record: ints {iter_AL, iter_DDP, n_bws, n_fit}, doubles {reg, eps, cost, dV, viol, cost_prev}
 
@@ -74,8 +80,8 @@ struct Dev {
     int W;              // line-search trial slots
     int max_rec;        // iteration records per instance
     // schedule
-    int *n_phases, *n_wb, *n_knots;     // [npad]
-    int *ph_mode, *ph_N, *ph_off;       // [P][npad]
+    int *n_phases, *n_wb, *n_knots;     // [npad]; n_knots = sum of N_p (knots actually used)
+    int *ph_mode, *ph_N, *ph_off;       // [P][npad]; ph_off[p] = p * KSTRIDE
     double *dt_wb, *dt_fb, *vel, *height;  // [npad]
     double* x0;                         // [14][npad]
     double* pos_ref;                    // [KT][npad]

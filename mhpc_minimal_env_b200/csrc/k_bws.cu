@@ -205,26 +205,26 @@ __global__ void __launch_bounds__(BWS_THREADS, BWS_MINBLOCKS) k_bws(Dev d, Const
     double* const du_lane = d.dufb + (size_t)l * es + (valid ? i : 0);
     const size_t gv_knot = 14 * es, kf_knot = (size_t)KDIM * es, du_knot = 4 * es;
 
-    // per-instance schedule walker used both by the prefetcher (one knot ahead) and by the math
-    struct Walk { int p, off, N, mode; };
+    // per-instance schedule walker (phase p, in-phase knot k; knot slot = p*KSTRIDE + k), used both by the prefetcher
+    // (one knot ahead) and by the math; it visits the nk used knots from the last one backwards
+    struct Walk { int p, N, mode, k; };
+    auto walk_load = [&](Walk& w) {
+        w.N = d.ph_N[ph_idx(d, w.p, i)];
+        w.mode = d.ph_mode[ph_idx(d, w.p, i)];
+    };
     auto walk_init = [&](Walk& w) {
-        w.p = np - 1;
-        w.off = (enabled && np > 0) ? d.ph_off[ph_idx(d, w.p, i)] : 0;
-        w.N = (enabled && np > 0) ? d.ph_N[ph_idx(d, w.p, i)] : 0;
-        w.mode = (enabled && np > 0) ? d.ph_mode[ph_idx(d, w.p, i)] : 1;
+        w.p = np - 1; w.N = 0; w.mode = 1; w.k = 0;
+        if (enabled && np > 0) { walk_load(w); w.k = w.N - 1; }
     };
-    auto walk_to = [&](Walk& w, int kk) {
-        while (kk < w.off) {
-            --w.p;
-            w.off = d.ph_off[ph_idx(d, w.p, i)]; w.N = d.ph_N[ph_idx(d, w.p, i)]; w.mode = d.ph_mode[ph_idx(d, w.p, i)];
-        }
+    auto walk_step = [&](Walk& w) {   // to the previous knot
+        if (--w.k < 0 && w.p > 0) { --w.p; walk_load(w); w.k = w.N - 1; }
     };
-    auto prefetch = [&](Walk& w, int kk, double* dst) {
-        if (enabled && kk < nk) {
-            walk_to(w, kk);
-            const int len = knot_rec_len(w.p < nwb, kk - w.off == w.N - 1);
-            const double* src = lin_i + (size_t)kk * REC;
+    auto prefetch = [&](Walk& w, int it_next, double* dst) {
+        if (enabled && it_next < nk) {
+            const int len = knot_rec_len(w.p < nwb, w.k == w.N - 1);
+            const double* src = lin_i + (size_t)(w.p * KSTRIDE + w.k) * REC;
             for (int q = l; 2 * q < len; q += 16) __pipeline_memcpy_async(dst + 2 * q, src + 2 * q, 16);
+            walk_step(w);
         }
         __pipeline_commit();
     };
@@ -239,23 +239,23 @@ __global__ void __launch_bounds__(BWS_THREADS, BWS_MINBLOCKS) k_bws(Dev d, Const
         bool failed = false;
         Walk wk, wp;
         walk_init(wk); walk_init(wp);
-        int& p = wk.p; int& off = wk.off; int& Nn = wk.N; int& mode = wk.mode;
+        int& p = wk.p; int& Nn = wk.N; int& mode = wk.mode;
         __syncwarp();
-        if (ktb > 0) prefetch(wp, ktb - 1, bufs);
+        if (ktb > 0) prefetch(wp, 0, bufs);
         for (int it = 0; it < ktb; ++it) {
-            const int kk = ktb - 1 - it;
             double* buf = bufs + (size_t)(it & 1) * REC;
             double* nbuf = bufs + (size_t)((it & 1) ^ 1) * REC;
             __pipeline_wait_prior(0);
             __syncwarp();
             const int alive = (!done && !failed) ? 1 : 0;
             if (!__any_sync(0xffffffffu, alive)) break;
-            if (kk > 0) prefetch(wp, kk - 1, nbuf); else __pipeline_commit();
+            prefetch(wp, it + 1, nbuf);
 
             // ---- which kind of knot is this for my instance? ----
+            const int kk = wk.p * KSTRIDE + wk.k;   // knot slot of this step
+            const int off = wk.p * KSTRIDE;
             int ty = 0;  // 0 idle, 1 WB step, 2 RB step, 3 WB terminal, 4 RB terminal
-            if (alive && kk < nk) {
-                walk_to(wk, kk);
+            if (alive && it < nk) {
                 const bool wb = p < nwb, term = (kk - off == Nn - 1);
                 ty = wb ? (term ? 3 : 1) : (term ? 4 : 2);
             }
@@ -568,6 +568,7 @@ __global__ void __launch_bounds__(BWS_THREADS, BWS_MINBLOCKS) k_bws(Dev d, Const
                 __syncwarp();
             }
 #undef RBUF
+            if (enabled && it < nk) walk_step(wk);
         }
         __pipeline_wait_prior(0);
         __syncwarp();

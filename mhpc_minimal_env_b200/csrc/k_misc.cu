@@ -38,9 +38,8 @@ __global__ void k_setup(Dev d, Consts c) {
         d.par[par_idx(d, p, PAR_EPS_G, i)] = (wb && !flight) ? 0.01 * 1.0 : 0.0;
         d.par[par_idx(d, p, PAR_H, i)] = 0.0;
     }
-    for (int f = 0; f < SI_N; ++f) SI(f) = 0;
-    for (int f = 0; f < SD_N; ++f) SD(f) = 0.0;
-    SD(SD_UPD_PENALTY) = 0.0;
+    for (int f = 0; f < SI_N; ++f) if (f != SI_OPT_REB) SI(f) = 0;            // _option is not touched by initialization()
+    for (int f = 0; f < SD_N; ++f) if (f != SD_OPT_UPD) SD(f) = 0.0;
 }
 
 // planar homogeneous transform restricted to the (x,z) plane: R = [[r00 r02],[r20 r22]], t = (tx,tz)
@@ -135,7 +134,8 @@ __global__ void k_copy_nominal(Dev d, int mask_mode) {
     if (!inst_enabled(d, i, mask_mode)) return;
     const int row = blockIdx.y;   // kk * ST + e
     const int kk = row / ST;
-    if (kk >= d.n_knots[i]) return;
+    int p, k;
+    if (!knot_to_phase(d, i, kk, p, k)) return;   // memcpy of N_p knots per phase (SinglePhase.cpp:358-361)
     const int slot = SI(SI_ACC_SLOT);
     d.st_nom[(size_t)row * d.npad + i] = d.st_act[((size_t)slot * d.KT * ST + row) * d.npad + i];
 }
@@ -158,14 +158,17 @@ __global__ void k_solve_begin(Dev d) {
     SI(SI_ITER_AL) = 1;
     SI(SI_N_REC) = 0;
     SI(SI_DDP_ACTIVE) = 0;
+    SI(SI_REB_BASE) = SI(SI_OPT_REB);      // bool ReB_active = _option.ReB_active;   (MultiPhaseDDP.cpp:161)
+    SD(SD_UPD_BASE) = SD(SD_OPT_UPD);      // T update_penalty = _option.update_penalty; (:160)
 }
 
 // MultiPhaseDDP.cpp:178-195
 __global__ void k_al_begin(Dev d, Opt opt) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= d.n || SI(SI_STATUS) != STATUS_RUNNING) return;
-    int reb = opt.ReB_active;
+    int reb = SI(SI_REB_BASE);
     if ((SD(SD_VIOL) > 0.05) || 1 == SI(SI_ITER_AL)) reb = 0;
+    SI(SI_OPT_REB) = reb;
     SI(SI_REB_ON) = reb;
     SI(SI_ITER_DDP) = 1;
     SD(SD_REG) = 0.0;
@@ -234,13 +237,14 @@ __global__ void k_ddp_end(Dev d, Opt opt) {
 __global__ void k_al_end(Dev d, Opt opt, Consts c, int mask_mode, int solve_mode) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= d.n || !inst_enabled(d, i, mask_mode)) return;
-    double upd = opt.update_penalty;
-    int reb = opt.ReB_active;
-    if (solve_mode) {
-        if (SD(SD_VIOL) < 0.03) upd = 0;
-        reb = SI(SI_REB_ON);
-        SD(SD_UPD_PENALTY) = upd;
+    if (solve_mode) {   // _option.update_penalty = update_penalty; if (viol < 0.03) _option.update_penalty = 0;
+        double u = SD(SD_UPD_BASE);
+        if (SD(SD_VIOL) < 0.03) u = 0;
+        SD(SD_OPT_UPD) = u;
     }
+    const double upd = SD(SD_OPT_UPD);
+    const int reb = SI(SI_OPT_REB);
+    SD(SD_UPD_PENALTY) = upd;
     const int np = d.n_phases[i], nwb = d.n_wb[i];
     for (int p = 0; p < nwb && p < np; ++p) {
         const int mode = d.ph_mode[ph_idx(d, p, i)];
@@ -268,6 +272,79 @@ __global__ void k_al_end(Dev d, Opt opt, Consts c, int mask_mode, int solve_mode
     }
 }
 
+// MultiPhaseDDP(n_phases, option) / set_option: the per-instance copy of the option members solve() overwrites
+__global__ void k_reset_option_state(Dev d, Opt opt) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= d.n) return;
+    SI(SI_OPT_REB) = opt.ReB_active;
+    SD(SD_OPT_UPD) = opt.update_penalty;
+}
+// the bare sweep entry points read `_option.ReB_active` as it currently is
+__global__ void k_reb_from_option(Dev d) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= d.n) return;
+    SI(SI_REB_ON) = SI(SI_OPT_REB);
+}
+
+// update_problem (MHPCLocomotion.cpp:107-121,134-151): the whole-body and the rigid-body phase buffers rotate by one
+// (new phase p uses the buffer of old phase p+1, the last one of each group gets the first).  One thread per
+// (knot slot, element, instance); `src`/`dst` are different allocations.  The accepted rollout becomes slot 0.
+__global__ void k_rotate(Dev d, const double* __restrict__ src, double* __restrict__ dst, int elems, int use_acc_slot) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= d.n) return;
+    const int row = blockIdx.y;            // dst knot slot * elems + e
+    const int kk = row / elems, e = row - kk * elems;
+    const int p = kk / KSTRIDE, k = kk - p * KSTRIDE;
+    const int np = d.n_phases[i], nwb = d.n_wb[i];
+    if (p >= np) return;
+    int q;
+    if (p < nwb) q = (p + 1 < nwb) ? p + 1 : 0;
+    else q = (p + 1 < np) ? p + 1 : nwb;
+    const size_t slot_off = use_acc_slot ? (size_t)SI(SI_ACC_SLOT) * d.KT * elems * d.npad : 0;
+    dst[(size_t)row * d.npad + i] = src[slot_off + ((size_t)(q * KSTRIDE + k) * elems + e) * d.npad + i];
+}
+// after the rotation every line-search slot must carry the same never-recomputed u,y of the last knot of each phase
+//  as the single `act` buffer of the reference
+__global__ void k_spread_last_knot(Dev d) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= d.n) return;
+    const int p = blockIdx.y;
+    if (p >= d.n_phases[i]) return;
+    const int kk = p * KSTRIDE + d.ph_N[ph_idx(d, p, i)] - 1;
+    for (int w = 1; w < d.W; ++w)
+        for (int e = 14; e < ST; ++e) d.st_act[act_idx(d, w, kk, e, i)] = d.st_act[act_idx(d, 0, kk, e, i)];
+}
+// build_problem part of update_problem: references + re-initialised AL/ReB parameters (no other state is touched)
+__global__ void k_setup_refs_params(Dev d, Consts c) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= d.n) return;
+    const int np = d.n_phases[i], nwb = d.n_wb[i];
+    const double vel = d.vel[i];
+    double pos = d.x0[i];
+    for (int p = 0; p < np; ++p) {
+        const double dt = (p < nwb) ? d.dt_wb[i] : d.dt_fb[i];
+        const int off = d.ph_off[ph_idx(d, p, i)], N = d.ph_N[ph_idx(d, p, i)];
+        d.pos_ref[(size_t)off * d.npad + i] = pos;
+        for (int k = 1; k < N; ++k) {
+            pos = pos + vel * dt;
+            d.pos_ref[(size_t)(off + k) * d.npad + i] = pos;
+        }
+        const int mode = d.ph_mode[ph_idx(d, p, i)];
+        const bool wb = p < nwb;
+        const bool flight = (mode == 2 || mode == 4);
+        d.par[par_idx(d, p, PAR_SIGMA, i)] = (wb && flight) ? 5.0 : 0.0;
+        d.par[par_idx(d, p, PAR_LAMBDA, i)] = 0.0;
+        d.par[par_idx(d, p, PAR_DELTA_T, i)] = wb ? 0.1 : 0.0;
+        d.par[par_idx(d, p, PAR_DELTA_J, i)] = wb ? 0.1 : 0.0;
+        d.par[par_idx(d, p, PAR_DELTA_G, i)] = (wb && !flight) ? 0.1 : 0.0;
+        d.par[par_idx(d, p, PAR_EPS_T, i)] = wb ? 0.01 * 1.0 : 0.0;
+        d.par[par_idx(d, p, PAR_EPS_J, i)] = 0.0;
+        d.par[par_idx(d, p, PAR_EPS_G, i)] = (wb && !flight) ? 0.01 * 1.0 : 0.0;
+        d.par[par_idx(d, p, PAR_H, i)] = 0.0;     // TConstrStruct() re-created zeroed (SinglePhase.cpp:35-36)
+    }
+    SI(SI_ACC_SLOT) = 0;
+}
+
 __global__ void k_count_active(Dev d) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= d.n) return;
@@ -293,6 +370,17 @@ void launch_ddp_end(const Dev& d, const Opt& o, int, cudaStream_t s) { k_ddp_end
 void launch_al_end(const Dev& d, const Opt& o, const Consts& c, int mask_mode, int solve_mode, cudaStream_t s) {
     k_al_end<<<nb(d.n, 128), 128, 0, s>>>(d, o, c, mask_mode, solve_mode);
 }
+void launch_reset_option_state(const Dev& d, const Opt& o, cudaStream_t s) { k_reset_option_state<<<nb(d.n, 128), 128, 0, s>>>(d, o); }
+void launch_reb_from_option(const Dev& d, cudaStream_t s) { k_reb_from_option<<<nb(d.n, 128), 128, 0, s>>>(d); }
+void launch_rotate(const Dev& d, const double* src, double* dst, int elems, int use_acc_slot, cudaStream_t s) {
+    dim3 grid(nb(d.n, 128), d.KT * elems);
+    k_rotate<<<grid, 128, 0, s>>>(d, src, dst, elems, use_acc_slot);
+}
+void launch_spread_last_knot(const Dev& d, cudaStream_t s) {
+    dim3 grid(nb(d.n, 128), d.P);
+    k_spread_last_knot<<<grid, 128, 0, s>>>(d);
+}
+void launch_setup_refs_params(const Dev& d, const Consts& c, cudaStream_t s) { k_setup_refs_params<<<nb(d.n, 128), 128, 0, s>>>(d, c); }
 void launch_count_active(const Dev& d, cudaStream_t s) {
     cudaMemsetAsync(d.n_active, 0, sizeof(int), s);
     k_count_active<<<nb(d.n, 128), 128, 0, s>>>(d);

@@ -39,6 +39,11 @@ void launch_select(const Dev& d, const Opt& o, int mask_mode, int trial0, int n_
 void launch_ddp_end(const Dev& d, const Opt& o, int ddp_iter_host, cudaStream_t s);
 void launch_al_end(const Dev& d, const Opt& o, const Consts& c, int mask_mode, int use_state_penalty, cudaStream_t s);
 void launch_count_active(const Dev& d, cudaStream_t s);
+void launch_reset_option_state(const Dev& d, const Opt& o, cudaStream_t s);
+void launch_reb_from_option(const Dev& d, cudaStream_t s);
+void launch_rotate(const Dev& d, const double* src, double* dst, int elems, int use_acc_slot, cudaStream_t s);
+void launch_spread_last_knot(const Dev& d, cudaStream_t s);
+void launch_setup_refs_params(const Dev& d, const Consts& c, cudaStream_t s);
 // rollout (k_rollout.cu)
 void launch_rollout(const Dev& d, const Consts& c, const Opt& o, int mask_mode, int n_slots, int trial0, const EpsList& e, cudaStream_t s);
 // linearisation (k_lin.cu compiled once per knot class)

@@ -217,14 +217,11 @@ static __device__ __forceinline__ double rb_running_cost(const Consts& c, int mo
     return l;
 }
 
-// locate phase p and in-phase index k of global knot kk for instance i
+// phase p and in-phase index k of knot slot kk (phase p owns slots [p*KSTRIDE, p*KSTRIDE + N_p))
 static __device__ __forceinline__ bool knot_to_phase(const Dev& d, int i, int kk, int& p, int& k) {
-    const int np = d.n_phases[i];
-    for (int q = np - 1; q >= 0; --q) {
-        const int off = d.ph_off[ph_idx(d, q, i)];
-        if (kk >= off) { p = q; k = kk - off; return k < d.ph_N[ph_idx(d, q, i)]; }
-    }
-    return false;
+    p = kk / KSTRIDE;
+    k = kk - p * KSTRIDE;
+    return p < d.n_phases[i] && k < d.ph_N[ph_idx(d, p, i)];
 }
 
 }  // namespace mhpc

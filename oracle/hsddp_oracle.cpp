@@ -411,6 +411,9 @@ struct PhaseBase {
     virtual void set_CTG_next(double dVn, const double* G, const double* H) = 0;
     virtual int get_field(int field, double* out) const = 0;
     virtual double tconstr_h() const = 0;
+    virtual void zero_data() = 0;
+    virtual void swap_data(PhaseBase& other) = 0;
+    virtual void initialization() = 0;
 };
 
 template <int n, int m, int p>
@@ -440,7 +443,17 @@ struct Phase : PhaseBase {
         std::memset(&tcost, 0, sizeof(tcost));
         x0.setZero(); Gnext.setZero(); Hnext.setZero();
     }
-    void initialization() {  // SinglePhase.cpp:26-42
+    void zero_data() override {   // MHPCLocomotion.cpp:265-290 (memset of every per-phase array)
+        auto z = [](auto& v) { std::memset((void*)v.data(), 0, v.size() * sizeof(v[0])); };
+        z(act); z(nom); z(ref); z(dynpar); z(rcost); z(CTG);
+        std::memset(&tcost, 0, sizeof(tcost));
+    }
+    void swap_data(PhaseBase& other) override {   // set_data with rotated buffers (MHPCLocomotion.cpp:134-151)
+        auto& o = static_cast<Phase<n, m, p>&>(other);
+        act.swap(o.act); nom.swap(o.nom); ref.swap(o.ref); dynpar.swap(o.dynpar); rcost.swap(o.rcost); CTG.swap(o.CTG);
+        std::swap(tcost, o.tcost);
+    }
+    void initialization() override {  // SinglePhase.cpp:26-42
         if (is_wb) { num_pconstr = wbcon->num_pconstr[mode - 1]; num_tconstr = wbcon->num_tconstr[mode - 1]; param = wbcon->params[mode - 1]; }
         else { num_pconstr = 0; num_tconstr = 0; param = ALReBParam(); }  // MHPCConstraints.cpp:5-11
         pconstr.assign(num_pconstr, IneqConstrStruct<n, m, p>());
@@ -738,10 +751,34 @@ public:
     }
     // MHPCLocomotion.cpp:47-53
     void initialization() {
-        // memory_reset: phases were zero-constructed; re-create to allow re-initialisation
+        memory_reset();
         build_problem();
         warmstart();
     }
+    // MHPCLocomotion.cpp:265-290
+    void memory_reset() {
+        for (auto& ph : phases) ph->zero_data();
+    }
+    // MHPCLocomotion.cpp:107-158 (dead code in the reference's main, but it compiles and defines the receding-horizon
+    // shift): the whole-body / rigid-body phase buffers rotate by one, the gait advances one mode, every phase is
+    // re-initialised (AL/ReB parameters back to their initial values) and the reference is regenerated from _x0.
+    void update_problem() {
+        for (int i = 0; i + 1 < n_wb; ++i) phases[i]->swap_data(*phases[i + 1]);
+        if (n_fb > 0)
+            for (int i = n_wb; i + 1 < n_phases; ++i) phases[i]->swap_data(*phases[i + 1]);
+        prob.cmode = gait_next_mode(prob.cmode);
+        mode_seq[0] = prob.cmode;
+        for (int i = 0; i + 1 < n_phases; ++i) mode_seq[i + 1] = gait_next_mode(mode_seq[i]);
+        for (int i = 0; i < n_phases; ++i) timings[i] = prob.gait_timing[mode_seq[i] - 1];
+        for (int i = 0; i < n_phases; ++i) {
+            PhaseBase* ph = phases[i].get();
+            N_TIMESTEPS[i] = (int)std::round(timings[i] / ph->dt);
+            ph->mode = mode_seq[i]; ph->phaseidx = i; ph->N = N_TIMESTEPS[i];
+        }
+        for (int i = 0; i < n_phases; ++i) phases[i]->initialization();
+        generate_ref();
+    }
+    void set_x0(const double* x) { for (int i = 0; i < 14; ++i) x0[i] = x[i]; }
     // MHPCLocomotion.cpp:63-104
     void build_problem() {
         mode_seq.assign(n_phases, 1); timings.assign(n_phases, 0.f); N_TIMESTEPS.assign(n_phases, 0);
@@ -1023,6 +1060,8 @@ int orc_backward_sweep(void* h, double reg) { return ((Solver*)h)->backward_swee
 int orc_forward_iteration(void* h) { return ((Solver*)h)->forward_iteration(); }
 void orc_update_nominal_trajectory(void* h) { ((Solver*)h)->update_nominal_trajectory(); }
 void orc_update_AL_ReB_param(void* h) { ((Solver*)h)->update_AL_ReB_param(); }
+void orc_update_problem(void* h) { ((Solver*)h)->update_problem(); }
+void orc_set_x0(void* h, const double* x0) { ((Solver*)h)->set_x0(x0); }
 void orc_set_ReB_active(void* h, int on) { ((Solver*)h)->option.ReB_active = on != 0; }
 void orc_set_update_penalty(void* h, double v) { ((Solver*)h)->option.update_penalty = v; }
 int orc_solve(void* h) { ((Solver*)h)->solve(); return ((Solver*)h)->status; }

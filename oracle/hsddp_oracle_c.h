@@ -39,6 +39,8 @@ int orc_backward_sweep(void* h, double reg);
 int orc_forward_iteration(void* h);
 void orc_update_nominal_trajectory(void* h);
 void orc_update_AL_ReB_param(void* h);
+void orc_update_problem(void* h);
+void orc_set_x0(void* h, const double* x0_14);
 void orc_set_ReB_active(void* h, int on);
 void orc_set_update_penalty(void* h, double v);
 int orc_solve(void* h);

@@ -75,8 +75,10 @@ def lib(variant: str = "strict"):
     L = C.CDLL(build(variant))
     L.orc_create.restype = C.c_void_p
     L.orc_create.argtypes = [C.POINTER(OrcProblem)]
+    L.orc_set_x0.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
+    L.orc_set_x0.restype = None
     for fn in ("orc_destroy", "orc_initialization", "orc_forward_sweep_partials_only",
-               "orc_update_nominal_trajectory", "orc_update_AL_ReB_param"):
+               "orc_update_nominal_trajectory", "orc_update_AL_ReB_param", "orc_update_problem"):
         getattr(L, fn).argtypes = [C.c_void_p]
         getattr(L, fn).restype = None
     for fn in ("orc_forward_sweep", "orc_forward_sweep_dynamics_only", "orc_set_update_penalty"):
@@ -116,6 +118,12 @@ class OracleSolver:
             pass
 
     def initialization(self): self.L.orc_initialization(self.h)
+    def update_problem(self): self.L.orc_update_problem(self.h)
+
+    def set_x0(self, x0):
+        a = (C.c_double * 14)(*[float(v) for v in x0])
+        self.L.orc_set_x0(self.h, a)
+
     def forward_sweep(self, eps): self.L.orc_forward_sweep(self.h, eps)
     def forward_sweep_dynamics_only(self, eps): self.L.orc_forward_sweep_dynamics_only(self.h, eps)
     def forward_sweep_partials_only(self): self.L.orc_forward_sweep_partials_only(self.h)

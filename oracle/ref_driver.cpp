@@ -39,6 +39,12 @@ void* ref_create(const double* opt10, const int* flags3, int n_wb, int n_fb, flo
     h->loco->_tconstr_violation = 0;
     return h;
 }
+void ref_update_problem(void* p) { ((RefHandle*)p)->loco->update_problem(); }
+void ref_set_x0(void* p, const double* x0) {
+    MHPCLocomotion<double>* l = ((RefHandle*)p)->loco;
+    for (int i = 0; i < 14; ++i) l->x0[i] = x0[i];
+    l->set_initial_condition(l->x0);
+}
 void ref_initialization(void* p) { ((RefHandle*)p)->loco->initialization(); }
 void ref_forward_sweep(void* p, double eps) { ((RefHandle*)p)->loco->forward_sweep(eps); }
 void ref_update_nominal(void* p) { ((RefHandle*)p)->loco->update_nominal_trajectory(); }
@@ -59,7 +65,8 @@ int ref_get(void* p, int phase, int which, double* out) {
     MHPCLocomotion<double>* l = ((RefHandle*)p)->loco;
     const int N = l->N_TIMESTEPS[phase];
     if (phase < l->n_wbphase) {
-        auto* ms = l->ms_nom_WB[phase]; auto* ctg = l->CTG_WB[phase];
+        const int pidx = l->pidx_WB[phase];   // buffers rotate in update_problem (MHPCLocomotion.cpp:112-121)
+        auto* ms = l->ms_nom_WB[pidx]; auto* ctg = l->CTG_WB[pidx];
         const int dims[6] = {14, 4, 4, 56, 4, 14};
         for (int k = 0; k < N && out; ++k) {
             const double* src = which == 0 ? ms[k].x.data() : which == 1 ? ms[k].u.data() : which == 2 ? ms[k].y.data()
@@ -68,7 +75,7 @@ int ref_get(void* p, int phase, int which, double* out) {
         }
         return dims[which];
     }
-    const int q = phase - l->n_wbphase;
+    const int q = l->pidx_FB[phase - l->n_wbphase];
     auto* ms = l->ms_nom_FB[q]; auto* ctg = l->CTG_FB[q];
     const int dims[6] = {6, 4, 4, 24, 4, 6};
     for (int k = 0; k < N && out; ++k) {

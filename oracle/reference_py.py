@@ -66,6 +66,11 @@ class ReferenceSolver:
                                               C.c_float(spec["height"]), gm, gt, x0))
 
     def initialization(self): self.L.ref_initialization(self.h)
+    def update_problem(self): self.L.ref_update_problem(self.h)
+
+    def set_x0(self, x0):
+        a = (C.c_double * 14)(*[float(v) for v in x0])
+        self.L.ref_set_x0(self.h, a)
 
     def solve(self):
         with quiet_stdout():

@@ -279,6 +279,7 @@ def test_full_size_properties_4096():
     for cfg in (2, 4):
         gpu, res = _batch_vs_oracle(4096, cfg, check_every=128)
         a1 = gpu.results_array()
+        gpu.set_option(m.default_option())   # solve() leaves the option members modified, as in the reference; reset them
         gpu.initialization()
         gpu.solve()
         a2 = gpu.results_array()
@@ -356,3 +357,41 @@ def test_odd_shapes_and_start_modes():
             assert abs(a["cost"] - b["cost"]) <= 1e-5 * abs(b["cost"]), (i, variants[i], a["cost"], b["cost"])
         if not np.isnan(o.scalars()["cost"]):
             _cmp_fields(gpu, o, i, ["X_NOM", "U_NOM"], 1e-4, "odd shapes trajectory")
+
+
+def test_receding_horizon_update_problem():
+    """SURVEY 8(f2): MHPCLocomotion::update_problem (MHPCLocomotion.cpp:107-158) - three control ticks of
+    solve -> shift -> new initial state -> solve, against the oracle (itself bit-identical to the reference's own
+    update_problem, tests/test_oracle_vs_ref.py).  Includes the option members that solve() leaves modified."""
+    import mhpc_minimal_env_b200 as m
+    from oracle.oracle_py import OracleSolver
+    specs = make_specs(4, 2) + [dict(make_specs(6, 4)[0]), dict(make_specs(4, 2)[3], n_wbphase=3, n_fbphase=2)]
+    gpu = m.BatchedMHPC([to_gpu_problem(s) for s in specs])
+    orcs = [OracleSolver(to_orc_problem(s)) for s in specs]
+    gpu.initialization()
+    gpu.solve()
+    for o in orcs:
+        o.initialization()
+        o.solve()
+    for tick in range(3):
+        xnew = np.stack([o.field(0, "X_NOM")[12] for o in orcs])    # the state 12 knots into the first phase
+        gpu.update_problem()
+        gpu.set_initial_condition(xnew)
+        gpu.solve()
+        res = gpu.results()
+        for i, o in enumerate(orcs):
+            o.update_problem()
+            o.set_x0(xnew[i])
+            st = o.solve()
+            assert gpu.schedule(i) == o.schedule(), (tick, i)
+            ro, rg = o.records(), gpu.records(i)
+            assert [(r["iter_AL"], r["iter_DDP"], r["n_bws"], r["n_fit"], r["reg"], r["eps"]) for r in rg] == \
+                   [(r["iter_AL"], r["iter_DDP"], r["n_bws"], r["n_fit"], r["reg"], r["eps"]) for r in ro], (tick, i)
+            assert (res[i]["status"] == 3) == (st == 1)
+            for a, b in zip(rg, ro):
+                if np.isnan(b["cost"]):
+                    assert np.isnan(a["cost"])
+                else:
+                    assert abs(a["cost"] - b["cost"]) <= 1e-5 * abs(b["cost"]), (tick, i, a["cost"], b["cost"])
+            if not np.isnan(o.scalars()["cost"]):
+                _cmp_fields(gpu, o, i, ["X_NOM", "U_NOM", "Y_NOM"], 1e-4, "mpc tick %d" % tick)

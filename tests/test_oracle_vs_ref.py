@@ -67,3 +67,33 @@ def test_fast_build_agrees_to_rounding():
     ref.initialization(); orc.initialization()
     ref.solve(); orc.solve()
     assert abs(ref.scalars()["cost"] - orc.scalars()["cost"]) <= 1e-7 * abs(orc.scalars()["cost"])
+
+
+@pytest.mark.parametrize("cfg,idx,opt", [(1, 0, {}), (4, 0, {}), (2, 2, dict(DDP_thresh=-1.0, AL_thresh=-1.0)), (2, 3, dict(n_wbphase=3, n_fbphase=2))])
+def test_update_problem_receding_horizon_bit_exact(cfg, idx, opt):
+    """MHPCLocomotion::update_problem (MHPCLocomotion.cpp:107-158; never called by the reference's main but part of the
+    compiled class): three solve -> shift -> new x0 -> solve ticks, restatement vs the reference sources."""
+    from oracle.oracle_py import OracleSolver
+    opt = dict(opt)
+    spec = dict(make_specs(idx + 1, cfg)[idx])
+    for k in ("n_wbphase", "n_fbphase"):
+        if k in opt:
+            spec[k] = opt.pop(k)
+    ref = reference_py.ReferenceSolver(spec, "strict", **opt)
+    orc = OracleSolver(to_orc_problem(spec, **opt), variant="strict")
+    for s in (ref, orc):
+        s.initialization()
+        s.solve()
+    for tick in range(3):
+        xnew = orc.field(0, "X_NOM")[12]
+        for s in (ref, orc):
+            s.update_problem()
+            s.set_x0(xnew)
+            s.solve()
+        modes, N, _ = orc.schedule()
+        assert (modes, N) == ref.schedule()
+        a, b = ref.scalars(), orc.scalars()
+        assert a["cost"] == b["cost"] and a["viol"] == b["viol"] and a["exp_cost_change"] == b["exp_cost_change"]
+        for p in range(len(N)):
+            for nm in ("X_NOM", "U_NOM", "Y_NOM", "K", "DU", "G"):
+                assert np.array_equal(orc.field(p, nm), ref.field(p, nm), equal_nan=True), (tick, p, nm)
