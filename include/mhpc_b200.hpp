@@ -109,6 +109,18 @@ public:
     void set_option(HSDDP_OPTION<T>& option) { _option = option; mhpc_hsddp_option o = to_c(option); ck(mhpc_batch_set_option(_h, &o)); }   // MultiPhaseDDP.h:22
 
     void initialization() { upload(); ck(mhpc_batch_initialization(_h)); }                 // MHPCLocomotion.cpp:47-53
+    // MHPCLocomotion::update_problem (MHPCLocomotion.cpp:107-158): receding-horizon shift by one phase; initial states set
+    // with set_initial_condition() since the last upload are sent along (update_problem itself leaves _x0 untouched)
+    void update_problem() {
+        ck(mhpc_batch_update_problem(_h));
+        for (auto& p : _problems) p.cmode = next_mode(p);
+        if (_dirty) {
+            std::vector<double> x0((size_t)_n_instances * 14);
+            for (int i = 0; i < _n_instances; ++i) for (int e = 0; e < 14; ++e) x0[(size_t)i * 14 + e] = _problems[i].x0[e];
+            ck(mhpc_batch_set_initial_condition(_h, x0.data()));
+            _dirty = false;
+        }
+    }
     void warmstart() { initialization(); }                                                  // :200-215 (part of initialization on the device)
     void solve_mhpc() { ck(mhpc_batch_solve(_h, 0)); refresh(); }                           // :167-195
     void solve() { solve_mhpc(); }                                                          // MultiPhaseDDP.cpp:154-289
@@ -189,6 +201,10 @@ private:
         return o;
     }
     static void ck(int rc) { if (rc < 0) throw std::runtime_error(mhpc_last_error()); }
+    static int next_mode(const mhpc_problem& p) {   // Gait::get_next_mode
+        for (int i = 0; i < 4; ++i) if (p.cmode == p.gait_mode[i]) return p.gait_mode[(i + 1) % 4];
+        return p.cmode;
+    }
     void upload() { ck(mhpc_batch_set_problems(_h, _problems.data())); _dirty = false; }
     void refresh() {
         _actual_cost.resize(_n_instances); _exp_cost_change.resize(_n_instances); _tconstr_violation.resize(_n_instances);
