@@ -24,6 +24,7 @@ import os
 import sys
 
 from .emit import emit_c, emit_inc
+from .implicit import implicit_jacobian, structured_primal
 from .regalloc import emit_c_regalloc, emit_inc_regalloc
 from .sxdag import CONST, SXFunction, parse_casadi_c, share_reciprocals
 
@@ -38,6 +39,13 @@ FUNCTIONS = [
 
 # the large Jacobian bodies additionally get a generator-side register allocation (codegen/regalloc.py)
 REGALLOC_FUNCTIONS = ["Dyn_BS_par", "Dyn_FS_par", "Dyn_FL_par", "Imp_F_par", "Imp_B_par"]
+# dynamics Jacobians re-derived by implicit differentiation of the primal's linear solve (codegen/implicit.py); the
+# flat CasADi DAGs stay the CPU check (gen_/genra_) and MHPC_IMPLICIT_JAC=0 puts them back on the device
+IMPLICIT_FUNCTIONS = {"Dyn_BS_par": "Dyn_BS", "Dyn_FS_par": "Dyn_FS", "Dyn_FL_par": "Dyn_FL"}
+IMPLICIT_JAC = os.environ.get("MHPC_IMPLICIT_JAC", "1") == "1"
+# the primal dynamics with their symbolic Gram-Schmidt QR replaced by an LDL^T solve of the same system (rollouts)
+STRUCT_PRIMAL = os.environ.get("MHPC_STRUCT_PRIMAL", "1") == "1"
+USE_LDLT = os.environ.get("MHPC_LDLT", "1") == "1"
 RA_CAP = int(os.environ.get("MHPC_RA_CAP", "104"))
 RA_LOOKAHEAD = int(os.environ.get("MHPC_RA_LOOKAHEAD", "24"))
 RA_WINDOW = int(os.environ.get("MHPC_RA_WINDOW", "0"))
@@ -148,6 +156,15 @@ def generate(ref: str = DEFAULT_REF, out: str = DEFAULT_OUT, verbose: bool = Tru
 
     # device bodies: shared reciprocals (<= 1 ulp per quotient); the exact-division DAGs stay the CPU check below
     dev = {name: (share_reciprocals(fn) if SHARE_RCP else fn) for name, fn in fns.items()}
+    restated = []
+    if IMPLICIT_JAC:
+        for name, primal in IMPLICIT_FUNCTIONS.items():
+            dev[name] = implicit_jacobian(fns[primal], fns[name], USE_LDLT)
+            restated.append(name)
+    if STRUCT_PRIMAL:
+        for primal in IMPLICIT_FUNCTIONS.values():
+            dev[primal] = structured_primal(fns[primal], USE_LDLT)
+            restated.append(primal)
     for name, fn in dev.items():
         write(name + ".inc", emit_inc(fn))
     ra_stats = {}
@@ -157,10 +174,14 @@ def generate(ref: str = DEFAULT_REF, out: str = DEFAULT_OUT, verbose: bool = Tru
         ra_stats[name] = st
     write("gen_check.c", "".join(emit_c(fn, "gen_" + name) for name, fn in fns.items()) +
           "".join(emit_c_regalloc(fns[name], "genra_" + name, RA_CAP, RA_LOOKAHEAD, RA_WINDOW, RA_SMEM, RA_FAR) for name in REGALLOC_FUNCTIONS) +
-          "".join(emit_c_regalloc(dev[name], "gendev_" + name, RA_CAP, RA_LOOKAHEAD, RA_WINDOW, RA_SMEM, RA_FAR) for name in REGALLOC_FUNCTIONS))
+          "".join(emit_c_regalloc(dev[name], "gendev_" + name, RA_CAP, RA_LOOKAHEAD, RA_WINDOW, RA_SMEM, RA_FAR) for name in REGALLOC_FUNCTIONS) +
+          "".join(emit_c(dev[name], "gendev_" + name) for name in restated if name not in REGALLOC_FUNCTIONS))
     write("gen_meta.h", emit_meta_h(metas) + f"#define MHPC_RA_SMEM_SLOTS {RA_SMEM}\n")
     metas["_source_sha256"] = h.hexdigest()
-    metas["_regalloc"] = {"cap": RA_CAP, "lookahead": RA_LOOKAHEAD, "window": RA_WINDOW, "share_reciprocals": SHARE_RCP, "smem_slots": RA_SMEM, "far_lookahead": RA_FAR, "stats": ra_stats}
+    metas["_regalloc"] = {"cap": RA_CAP, "lookahead": RA_LOOKAHEAD, "window": RA_WINDOW, "share_reciprocals": SHARE_RCP, "smem_slots": RA_SMEM, "far_lookahead": RA_FAR, "stats": ra_stats,
+                         "implicit_jacobians": sorted(restated), "ldlt": USE_LDLT,
+                         "device_nodes": {name: len(dev[name].nodes) for name in FUNCTIONS},
+                         "device_flops": {name: dev[name].flops() for name in FUNCTIONS}}
     write("gen_meta.json", json.dumps(metas, indent=1))
     if verbose:
         for name in FUNCTIONS:

@@ -219,15 +219,33 @@ def _oracle_counts(args):
         o = OracleSolver(to_orc_problem(specs[i], **optkw), variant="strict")
         o.initialization()
         st = o.solve()
-        # the reference's own sensitivity to FMA contraction (its CMake build uses -O3 -march=native): same algorithm, "fast" build
-        f = OracleSolver(to_orc_problem(specs[i], **optkw), variant="fast")
-        f.initialization()
-        f.solve()
-        fc = [r["cost"] for r in f.records()]
         recs = o.records()
-        sens = [abs(fc[k] - r["cost"]) if k < len(fc) else 0.0 for k, r in enumerate(recs)]
-        out.append((i, st, [(r["iter_AL"], r["iter_DDP"], r["n_bws"], r["n_fit"], r["reg"], r["eps"], r["cost"], sens[k]) for k, r in enumerate(recs)]))
+        out.append((i, st, [(r["iter_AL"], r["iter_DDP"], r["n_bws"], r["n_fit"], r["reg"], r["eps"], r["cost"]) for r in recs]))
     return out
+
+
+def _oracle_cost_sensitivity(spec, optkw, rel=1e-12, trials=4):
+    """Largest change of each per-iteration cost of the CPU oracle when the initial state moves in its 12th digit - the
+    forward error a backward-stable solve of the 9x9 dynamics system (condition ~2e4) leaves in every qdd.  Iterations that
+    amplify such a perturbation beyond 1e-6 (|dV| ~ 1e8 on a few instances) cannot be compared more tightly than this."""
+    import copy
+    from oracle.oracle_py import OracleSolver
+
+    def run(sp):
+        o = OracleSolver(to_orc_problem(sp, **optkw), variant="strict")
+        o.initialization()
+        o.solve()
+        return o.records()
+    base = run(spec)
+    rng = np.random.default_rng(857)
+    sens = [0.0] * len(base)
+    for _ in range(trials):
+        sp = copy.deepcopy(spec)
+        sp["x0"] = list(np.array(spec["x0"]) * (1.0 + rel * rng.choice([-1.0, 1.0], 14)))
+        r = run(sp)
+        for k in range(min(len(r), len(base))):
+            sens[k] = max(sens[k], abs(r[k]["cost"] - base[k]["cost"]))
+    return sens
 
 
 def _batch_vs_oracle(n, cfg, optkw=None, check_every=1):
@@ -246,7 +264,7 @@ def _batch_vs_oracle(n, cfg, optkw=None, check_every=1):
     chunks = [(idx[k::nproc], cfg, optkw) for k in range(nproc) if idx[k::nproc]]
     with mp.get_context("fork").Pool(len(chunks)) as pool:
         outs = [x for part in pool.map(_oracle_counts, chunks) for x in part]
-    bad = []
+    bad, ill = [], []
     for i, st, recs in outs:
         rg = gpu.records(i)
         got = [(r["iter_AL"], r["iter_DDP"], r["n_bws"], r["n_fit"], r["reg"], r["eps"]) for r in rg]
@@ -254,12 +272,18 @@ def _batch_vs_oracle(n, cfg, optkw=None, check_every=1):
         if got != exp or (res[i]["status"] == 3) != (st == 1):
             bad.append((i, got, exp))
             continue
-        for a, b in zip(rg, recs):
-            # 1e-6 relative, widened only where the CPU reference itself moves by more than that between its -ffp-contract=off
-            # and FMA-contracted builds (ill-conditioned iterations: |dV| ~ 1e8 amplifies rounding)
-            tol = max(TOL_COST * abs(b[6]), 8.0 * b[7])
-            assert abs(a["cost"] - b[6]) <= tol, (i, a["cost"], b[6], b[7])
+        sens = None
+        for k, (a, b) in enumerate(zip(rg, recs)):
+            # 1e-6 relative; an iteration that misses it must be one where the CPU oracle itself moves by more than the
+            # discrepancy under a 1e-12 relative change of x0 (see _oracle_cost_sensitivity)
+            err = abs(a["cost"] - b[6])
+            if err > TOL_COST * abs(b[6]):
+                if sens is None:
+                    sens = _oracle_cost_sensitivity(specs[i], optkw)
+                    ill.append(i)
+                assert err <= sens[k], (i, k, a["cost"], b[6], sens[k])
     assert not bad, (len(bad), bad[:3])
+    assert len(ill) <= max(1, n // 256), ill     # the ill-conditioned exception must stay an exception
     return gpu, res
 
 
