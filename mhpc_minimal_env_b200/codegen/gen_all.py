@@ -53,6 +53,25 @@ SHARE_RCP = os.environ.get("MHPC_SHARE_RCP", "1") == "1"
 RA_FAR = int(os.environ.get("MHPC_RA_FAR", "128"))           # prefetch distance for operands in local memory (0: same as lookahead)
 RA_SMEM = int(os.environ.get("MHPC_RA_SMEM", "108"))      # per-thread shared-memory slots of the second spill level
 
+QUAD_OUT = os.environ.get("MHPC_QUAD_OUT", "1") == "1"
+
+
+def wb_record_element(st):
+    """Knot-record element (csrc/common.cuh: R_AB, R_BB, R_CB, R_DB) a Dyn_*_par output non-zero lands in, or None for
+    the rows the kernels do not store (the identity block of A).  k_lin.cu static_asserts the same mapping."""
+    if st.out == 0:
+        return (st.col - 2) * 7 + (st.row - 7) if st.row >= 7 else None
+    if st.out == 1:
+        return 84 + st.col * 7 + (st.row - 7)
+    if st.out == 2:
+        return 112 + (st.col - 2) * 2 + (st.row & 1)
+    return 136 + st.col * 2 + (st.row & 1)
+
+
+def quad_map(name):
+    return wb_record_element if (QUAD_OUT and name in IMPLICIT_FUNCTIONS) else None
+
+
 HERE = os.path.dirname(os.path.abspath(__file__))
 DEFAULT_OUT = os.path.normpath(os.path.join(HERE, "..", "csrc", "gen"))
 DEFAULT_REF = "/root/reference"
@@ -169,12 +188,12 @@ def generate(ref: str = DEFAULT_REF, out: str = DEFAULT_OUT, verbose: bool = Tru
         write(name + ".inc", emit_inc(fn))
     ra_stats = {}
     for name in REGALLOC_FUNCTIONS:
-        text, st = emit_inc_regalloc(dev[name], RA_CAP, RA_LOOKAHEAD, RA_WINDOW, RA_SMEM, RA_FAR)
+        text, st = emit_inc_regalloc(dev[name], RA_CAP, RA_LOOKAHEAD, RA_WINDOW, RA_SMEM, RA_FAR, quad_map(name))
         write(name + "_ra.inc", text)
         ra_stats[name] = st
     write("gen_check.c", "".join(emit_c(fn, "gen_" + name) for name, fn in fns.items()) +
           "".join(emit_c_regalloc(fns[name], "genra_" + name, RA_CAP, RA_LOOKAHEAD, RA_WINDOW, RA_SMEM, RA_FAR) for name in REGALLOC_FUNCTIONS) +
-          "".join(emit_c_regalloc(dev[name], "gendev_" + name, RA_CAP, RA_LOOKAHEAD, RA_WINDOW, RA_SMEM, RA_FAR) for name in REGALLOC_FUNCTIONS) +
+          "".join(emit_c_regalloc(dev[name], "gendev_" + name, RA_CAP, RA_LOOKAHEAD, RA_WINDOW, RA_SMEM, RA_FAR, quad_map(name)) for name in REGALLOC_FUNCTIONS) +
           "".join(emit_c(dev[name], "gendev_" + name) for name in restated if name not in REGALLOC_FUNCTIONS))
     write("gen_meta.h", emit_meta_h(metas) + f"#define MHPC_RA_SMEM_SLOTS {RA_SMEM}\n")
     metas["_source_sha256"] = h.hexdigest()

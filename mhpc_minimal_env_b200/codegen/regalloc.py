@@ -81,9 +81,12 @@ def ilp_schedule(instrs, operands_of, window: int = 48, lat_fp: int = 6, lat_slo
 
 
 def allocate(fn: SXFunction, cap: int = 104, lookahead: int = 48, window: int = 0, smem_slots: int = 0,
-             far_lookahead: int = 0) -> Tuple[List[str], Dict[str, int]]:
+             far_lookahead: int = 0, quad_of=None) -> Tuple[List[str], Dict[str, int]]:
     """`lookahead`: prefetch distance (instructions) for operands held in shared memory / produced recently;
-    `far_lookahead` (> lookahead, 0 = off): longer distance used for operands that sit in LOCAL memory (HBM latency)."""
+    `far_lookahead` (> lookahead, 0 = off): longer distance used for operands that sit in LOCAL memory (HBM latency);
+    `quad_of(store) -> element index | None`: outputs that land in a record are held back until the four elements of
+    their aligned quad exist and leave together through SX_OUT4 (one full 32-byte sector per thread instead of four
+    partial ones)."""
     nodes = fn.nodes
     n = len(nodes)
     is_const = [nd.op == CONST for nd in nodes]
@@ -110,9 +113,44 @@ def allocate(fn: SXFunction, cap: int = 104, lookahead: int = 48, window: int = 
             skip.add(partner[i])
         else:
             instrs.append((i,))
+    # output quads: a flush pseudo-instruction (negative id) right after the instruction that completes the quad
+    quads: Dict[int, Dict[int, object]] = {}
+    quad_stores = set()
+    if quad_of is not None and window <= 1:
+        elem = {}
+        for st in fn.stores:
+            e = quad_of(st)
+            if e is not None:
+                elem[id(st)] = e
+                quads.setdefault(e // 4, {})[e % 4] = st
+        quads = {g: m for g, m in quads.items() if len(m) == 4}
+        if quads:
+            pos_of = {}
+            for t, ins in enumerate(instrs):
+                for v in ins:
+                    pos_of[v] = t
+            after: Dict[int, List[int]] = {}
+            for g, m in quads.items():
+                last = max((pos_of[st.node] for st in m.values() if not is_const[st.node]), default=-1)
+                after.setdefault(last, []).append(g)
+                for st in m.values():
+                    quad_stores.add(id(st))
+            new_instrs: List[Tuple[int, ...]] = [(-1 - g,) for g in sorted(after.get(-1, []))]
+            for t, ins in enumerate(instrs):
+                new_instrs.append(ins)
+                for g in sorted(after.get(t, [])):
+                    new_instrs.append((-1 - g,))
+            instrs = new_instrs
     T = len(instrs)
 
     def operands(ins) -> List[int]:
+        if ins[0] < 0:
+            ops = []
+            for k in range(4):
+                p = quads[-1 - ins[0]][k].node
+                if not is_const[p] and p not in ops:
+                    ops.append(p)
+            return ops
         nd = nodes[ins[0]]
         ops = []
         for p in (nd.a, nd.b):
@@ -125,6 +163,8 @@ def allocate(fn: SXFunction, cap: int = 104, lookahead: int = 48, window: int = 
         instrs = [instrs[k] for k in perm]
     def_pos: Dict[int, int] = {}
     for t, ins in enumerate(instrs):
+        if ins[0] < 0:
+            continue
         for v in ins:
             def_pos[v] = t
 
@@ -146,7 +186,7 @@ def allocate(fn: SXFunction, cap: int = 104, lookahead: int = 48, window: int = 
     out: List[str] = []
     # constant outputs
     for st in fn.stores:
-        if is_const[st.node]:
+        if is_const[st.node] and id(st) not in quad_stores:
             out.append(f"SX_OUT({st.out}, {st.nz}, {st.row}, {st.col}, {nodes[st.node].lit});")
 
     reg_of: Dict[int, int] = {}          # value -> register
@@ -259,7 +299,6 @@ def allocate(fn: SXFunction, cap: int = 104, lookahead: int = 48, window: int = 
         if t + lookahead < T:
             make_resident(t + lookahead, t)
         v = ins[0]
-        nd = nodes[v]
         ops = operands(ins)
         for p in ops:   # safety net: an operand defined inside the lookahead window may have been evicted since
             if p not in reg_of:
@@ -267,6 +306,19 @@ def allocate(fn: SXFunction, cap: int = 104, lookahead: int = 48, window: int = 
                 reg_of[p] = r
                 reload(p, r)
                 stats["late_loads"] = stats.get("late_loads", 0) + 1
+        if v < 0:       # flush one complete output quad
+            g = -1 - v
+            args = []
+            for k in range(4):
+                st = quads[g][k]
+                args.append(f"{st.out}, {st.nz}, {st.row}, {st.col}, {opnd(st.node)}")
+            out.append(f"SX_OUT4({4 * g}, " + ", ".join(args) + ");")
+            stats["quads"] = stats.get("quads", 0) + 1
+            for p in ops:
+                if next_use(p, t) == INF and pins.get(p, -1) <= t:
+                    release(p)
+            continue
+        nd = nodes[v]
         a = opnd(nd.a) if nd.a >= 0 else None
         b = opnd(nd.b) if nd.b >= 0 else None
         # operands that die here free their registers before the destination is chosen
@@ -303,7 +355,8 @@ def allocate(fn: SXFunction, cap: int = 104, lookahead: int = 48, window: int = 
             raise AssertionError(nd.op)
         for w, r in dests:
             for st in stores_of.get(w, []):
-                out.append(f"SX_OUT({st.out}, {st.nz}, {st.row}, {st.col}, r{r});")
+                if id(st) not in quad_stores:
+                    out.append(f"SX_OUT({st.out}, {st.nz}, {st.row}, {st.col}, r{r});")
             if not uses.get(w):
                 release(w)
     stats["slots"] = n_slots
@@ -313,8 +366,8 @@ def allocate(fn: SXFunction, cap: int = 104, lookahead: int = 48, window: int = 
 
 
 def emit_inc_regalloc(fn: SXFunction, cap: int = 104, lookahead: int = 48, window: int = 0, smem_slots: int = 0,
-                      far_lookahead: int = 0) -> Tuple[str, Dict[str, int]]:
-    body, stats = allocate(fn, cap, lookahead, window, smem_slots, far_lookahead)
+                      far_lookahead: int = 0, quad_of=None) -> Tuple[str, Dict[str, int]]:
+    body, stats = allocate(fn, cap, lookahead, window, smem_slots, far_lookahead, quad_of)
     hdr = [
         f"// GENERATED at build time by mhpc_minimal_env_b200/codegen (regalloc) from the CasADi SX function `{fn.name}`.",
         f"// register file {cap} FP64, lookahead {lookahead}, ILP window {window}: {stats['instrs']} instructions, {stats['loads']} reloads, "
@@ -324,8 +377,8 @@ def emit_inc_regalloc(fn: SXFunction, cap: int = 104, lookahead: int = 48, windo
 
 
 def emit_c_regalloc(fn: SXFunction, symbol: str, cap: int = 104, lookahead: int = 48, window: int = 0, smem_slots: int = 0,
-                    far_lookahead: int = 0) -> str:
-    body, stats = allocate(fn, cap, lookahead, window, smem_slots, far_lookahead)
+                    far_lookahead: int = 0, quad_of=None) -> str:
+    body, stats = allocate(fn, cap, lookahead, window, smem_slots, far_lookahead, quad_of)
     return "\n".join([
         "#include <math.h>",
         f"void {symbol}(const double** arg, double** res) {{",
@@ -333,8 +386,10 @@ def emit_c_regalloc(fn: SXFunction, symbol: str, cap: int = 104, lookahead: int 
         "#define SX_SMEM(s) sx_smem_c[s]",
         "#define SX_IN(i, j) (arg[i][j])",
         "#define SX_OUT(k, nz, row, col, v) res[k][nz] = (v)",
+        "#define SX_OUT4(e0, k0, n0, r0, c0, v0, k1, n1, r1, c1, v1, k2, n2, r2, c2, v2, k3, n3, r3, c3, v3) "
+        "do { res[k0][n0] = (v0); res[k1][n1] = (v1); res[k2][n2] = (v2); res[k3][n3] = (v3); } while (0)",
         "#define SX_SINCOS(a, s, c) do { const double t_ = (a); (s) = sin(t_); (c) = cos(t_); } while (0)",
         *("  " + s for s in body),
-        "#undef SX_IN", "#undef SX_OUT", "#undef SX_SINCOS", "#undef SX_SMEM",
+        "#undef SX_IN", "#undef SX_OUT", "#undef SX_OUT4", "#undef SX_SINCOS", "#undef SX_SMEM",
         "}", "",
     ])

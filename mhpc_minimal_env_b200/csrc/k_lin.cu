@@ -44,6 +44,28 @@ __device__ __forceinline__ void wb_par_out(double* __restrict__ rec, int j, doub
         REC_AT(R_DB(ROW & 1, COL)) = v;
     }
 }
+// One aligned quad of record elements leaves as a single 32-byte store: the record is AoS (1408 bytes per knot and
+// instance), so a scalar store per element touches a 32-byte sector four times with 8 bytes each - 4x the L2 write
+// transactions and partial-sector merges - while a quad is exactly one full sector per thread.
+__device__ __forceinline__ void st_quad(double* p, double a, double b, double c, double d) {
+    asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
+}
+template <int K, int ROW, int COL>
+__device__ __forceinline__ constexpr int wb_par_elem() {
+    return K == 0 ? R_AB(ROW - 7, COL - 2) : K == 1 ? R_BB(ROW - 7, COL) : K == 2 ? R_CB(ROW & 1, COL - 2) : R_DB(ROW & 1, COL);
+}
+template <int K, int ROW, int COL>
+__device__ __forceinline__ double wb_par_val(double dt, double v) {
+    return K == 0 ? (ROW == COL ? 1.0 : 0.0) + v * dt : K == 1 ? v * dt : v;
+}
+template <int E0, int K0, int R0, int C0, int K1, int R1, int C1, int K2, int R2, int C2, int K3, int R3, int C3>
+__device__ __forceinline__ void wb_par_out4(double* __restrict__ rec, double dt, double v0, double v1, double v2, double v3) {
+    static_assert((E0 & 3) == 0 && wb_par_elem<K0, R0, C0>() == E0 && wb_par_elem<K1, R1, C1>() == E0 + 1 &&
+                  wb_par_elem<K2, R2, C2>() == E0 + 2 && wb_par_elem<K3, R3, C3>() == E0 + 3,
+                  "codegen/gen_all.py: wb_record_element disagrees with the record layout");
+    st_quad(rec + E0, wb_par_val<K0, R0, C0>(dt, v0), wb_par_val<K1, R1, C1>(dt, v1), wb_par_val<K2, R2, C2>(dt, v2),
+            wb_par_val<K3, R3, C3>(dt, v3));
+}
 template <int ROW, int COL>
 __device__ __forceinline__ void imp_par_out(double* __restrict__ rec, int j, double v) {
     if (ROW >= 7) REC_AT(R_AB(ROW - 7, COL - 2)) = v;
@@ -55,6 +77,8 @@ __device__ __forceinline__ void imp_par_out(double* __restrict__ rec, int j, dou
 #define SX_IN(i, j_) ((i) == 0 ? st[(size_t)(j_) * es] : st[(size_t)(14 + (j_)) * es])
 #define SX_SMEM(s) sx_sm[(s) * LIN_THREADS]     /* second spill level: per-thread shared-memory slots, conflict-free */
 #define SX_OUT(k, nz, row, col, v) wb_par_out<k, row, col>(rec, j, dt, v)
+#define SX_OUT4(e0, k0, n0, r0, c0, v0, k1, n1, r1, c1, v1, k2, n2, r2, c2, v2, k3, n3, r3, c3, v3) \
+    wb_par_out4<e0, k0, r0, c0, k1, r1, c1, k2, r2, c2, k3, r3, c3>(rec, dt, v0, v1, v2, v3)
 #if LIN_CLS == 0
 __device__ __forceinline__ void dyn_par(const double* __restrict__ st, size_t es, double* __restrict__ rec, int j, double dt, volatile double* sx_sm) {
 #include "gen/Dyn_BS_par_ra.inc"
@@ -80,6 +104,7 @@ __device__ __forceinline__ void imp_par(const double* __restrict__ st, size_t es
 }
 #endif
 #undef SX_OUT
+#undef SX_OUT4
 #undef SX_IN
 #undef SX_SMEM
 
@@ -135,12 +160,16 @@ __device__ inline void wb_cost_partials(const Consts& c, int mode, double dt, co
             }
         }
     }
-#pragma unroll
-    for (int i = 0; i < 14; ++i) REC_AT(R_LX + i) = lx[i];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) { REC_AT(R_LU + i) = lu[i]; REC_AT(R_LXXQ + i) = lxxq[i]; REC_AT(R_LUU + i) = luu[i]; }
-    REC_AT(R_LY) = ly2[0]; REC_AT(R_LY + 1) = ly2[1];
-    REC_AT(R_LYY) = lyy[0]; REC_AT(R_LYY + 1) = lyy[1]; REC_AT(R_LYY + 2) = lyy[2];
+    static_assert(R_LX == 144 && R_LU == 158 && R_LY == 162 && R_LXXQ == 164 && R_LUU == 168 && R_LYY == 172 && REC == 176,
+                  "the eight quads below spell out the cost part of the record");
+    st_quad(rec + 144, lx[0], lx[1], lx[2], lx[3]);
+    st_quad(rec + 148, lx[4], lx[5], lx[6], lx[7]);
+    st_quad(rec + 152, lx[8], lx[9], lx[10], lx[11]);
+    st_quad(rec + 156, lx[12], lx[13], lu[0], lu[1]);
+    st_quad(rec + 160, lu[2], lu[3], ly2[0], ly2[1]);
+    st_quad(rec + 164, lxxq[0], lxxq[1], lxxq[2], lxxq[3]);
+    st_quad(rec + 168, luu[0], luu[1], luu[2], luu[3]);
+    st_quad(rec + 172, lyy[0], lyy[1], lyy[2], 0.0);
 }
 
 #ifndef LIN_MINBLOCKS
@@ -196,7 +225,7 @@ __global__ void __launch_bounds__(LIN_THREADS, LIN_MINBLOCKS) k_lin(Dev d, Const
         for (int e = 0; e < 4; ++e) { u[e] = st[(14 + e) * es]; y[e] = st[(18 + e) * es]; }
 #if LIN_CLS == 2
 #pragma unroll
-        for (int e = R_CB(0, 0); e < R_LX; ++e) REC_AT(e) = 0.0;   // C = D = 0 in flight
+        for (int e = R_CB(0, 0); e < R_LX; e += 4) st_quad(rec + e, 0.0, 0.0, 0.0, 0.0);   // C = D = 0 in flight
 #endif
         const bool reb = d.si[(size_t)SI_REB_ON * d.npad + i] != 0;
         double par[6];
@@ -276,14 +305,18 @@ __global__ void __launch_bounds__(LIN_THREADS, LIN_MINBLOCKS) k_lin(Dev d, Const
         rb_foothold(c, mode, x0p, dt * (double)N, fh);
         rb_contact(mode, ct);
         fb_dyn_par(x, u, fh, ct, a2, b8);
-        REC_AT(R_RA) = a2[0] * dt; REC_AT(R_RA + 1) = a2[1] * dt;
-#pragma unroll
-        for (int q = 0; q < 8; ++q) REC_AT(R_RB + q) = b8[q] * dt;
         const double two_dt = 2 * dt;
+        double rlx[6], rlu[4];
 #pragma unroll
-        for (int e = 0; e < 6; ++e) REC_AT(R_RLX + e) = (two_dt * c.rbQ[e]) * (x[e] - rb_xref(e, pos, vel, height));
+        for (int e = 0; e < 6; ++e) rlx[e] = (two_dt * c.rbQ[e]) * (x[e] - rb_xref(e, pos, vel, height));
 #pragma unroll
-        for (int e = 0; e < 4; ++e) REC_AT(R_RLU + e) = (two_dt * c.rbR[mode - 1][e]) * (u[e] - grf_ref(c, e));
+        for (int e = 0; e < 4; ++e) rlu[e] = (two_dt * c.rbR[mode - 1][e]) * (u[e] - grf_ref(c, e));
+        static_assert(R_RA == 0 && R_RB == 2 && R_RLX == 10 && R_RLU == 16 && RB_STEP_LEN == 20, "five quads = one rigid-body step record");
+        st_quad(rec + 0, a2[0] * dt, a2[1] * dt, b8[0] * dt, b8[1] * dt);
+        st_quad(rec + 4, b8[2] * dt, b8[3] * dt, b8[4] * dt, b8[5] * dt);
+        st_quad(rec + 8, b8[6] * dt, b8[7] * dt, rlx[0], rlx[1]);
+        st_quad(rec + 12, rlx[2], rlx[3], rlx[4], rlx[5]);
+        st_quad(rec + 16, rlu[0], rlu[1], rlu[2], rlu[3]);
     } else {
 #pragma unroll
         for (int e = 0; e < 6; ++e) REC_AT(R_RPHIX + e) = c.rbQf[e] * (st[e * es] - rb_xref(e, pos, vel, height));
