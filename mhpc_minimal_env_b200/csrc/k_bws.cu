@@ -2,13 +2,18 @@
 // MHPC_CompoundTypes.h:116-144) with the regularisation retry loop of MultiPhaseDDP::solve
 // (MultiPhaseDDP.cpp:209-227) folded in.
 //
-// A half-warp owns one instance, lane r owns row r of the value Hessian H (registers).  Time is
-// sequential; every warp streams the knot records of its two instances into warp-private shared
-// memory with 16-byte cp.async, one knot ahead of the math (double buffered, synchronised with
-// __syncwarp only: warps never wait for each other, there is no CTA barrier in the sweep).
+// EIGHT lanes own one instance (four instances per warp, one warp per CTA).  In the whole-body phases sub-lane m
+// (m < 7) owns rows m and m+7 of the value Hessian H in registers; in the rigid-body phases sub-lane m (m < 6) owns
+// row m.  Two rows per lane means every shared operand of the 14x14 products (a column of A, a row of M = H A, a row of
+// Qux) is read from shared memory once and used twice, and a warp instruction serves four instances: the kernel is
+// issue- and latency-bound (712 dependent knots, ~1 warp per scheduler at 4096 instances), so instructions per instance
+// are what counts.  Time is sequential; every warp streams the knot records of its four instances into warp-private
+// shared memory with 16-byte cp.async, one knot ahead of the math (double buffered, synchronised with __syncwarp only:
+// warps never wait for each other, there is no CTA barrier in the sweep).
 // The structure of the reference's matrices is used instead of dense 14x14 products:
 //   A = [I7  dt*I7 ; 0(7x2) Ab(7x12)],  B = [0 ; Bb],  C/D = two stance rows,  lxx/luu diagonal,
-// which removes only exact-zero / exact-one terms of the dense sums.
+// which removes only exact-zero / exact-one terms of the dense sums; every stored entry is produced by the same
+// operation sequence (ascending inner index) as in the reference, whichever lane computes it.
 #include <cuda_pipeline.h>
 
 #include "kernels.h"
@@ -16,12 +21,13 @@
 
 namespace mhpc {
 
-constexpr int BWS_THREADS = 128;             // 4 warps = 8 instances per CTA
-constexpr int BWS_INST = BWS_THREADS / 16;
+constexpr int BWS_LPI = 8;                   // lanes per instance
+constexpr int BWS_THREADS = 32;              // one warp per CTA
+constexpr int BWS_INST = BWS_THREADS / BWS_LPI;
 constexpr int MQ_LD = 15;
 // per-instance scratch (doubles)
 constexpr int S_G = 0;        // 16
-constexpr int S_MQ = 16;      // 14 x 15 : M = H*A, later Qxx for the symmetrisation
+constexpr int S_MQ = 16;      // 14 x 15 : rows 7..13 of M = H*A (at rows 0..6), later Qxx for the symmetrisation
 constexpr int S_N = 226;      // 7 x 4  : rows 7..13 of H*B   (RB: 6 x 4)
 constexpr int S_QUX = 254;    // 4 x 14
 constexpr int S_QUU = 310;    // 16
@@ -30,11 +36,15 @@ constexpr int S_QU = 326;     // 4
 constexpr int S_ADJ = S_MQ;         // 16 adjugate of Quu
 constexpr int S_INV = S_MQ + 16;    // 16 Quu^-1
 constexpr int S_QI = S_MQ + 32;     // 16 symmetrised Quu^-1
-constexpr int SCR = 331;
+constexpr int SCR = 330;
+// doubles per instance in shared memory: two record stages + scratch; = 8 (mod 16) so that the two instances of a
+// half-warp sit in disjoint banks for every access pattern below
+constexpr int BWS_REGION = 2 * REC + SCR + 14;
+static_assert(BWS_REGION % 16 == 8 && SCR >= S_QU + 4, "bank layout of the per-instance shared-memory region");
+constexpr size_t BWS_SMEM = (size_t)BWS_REGION * BWS_INST * sizeof(double);
 #ifndef BWS_MINBLOCKS
-#define BWS_MINBLOCKS 4
+#define BWS_MINBLOCKS 7
 #endif
-constexpr size_t BWS_SMEM = (size_t)(2 * REC + SCR + 1) * BWS_INST * sizeof(double);
 
 // Eigen::LDLT<>::isPositive() restated (diagonal pivoting on the largest |a_ii|, sign of D tracked;
 // Eigen/src/Cholesky/LDLT.h); call site SinglePhase.cpp:202-205.
@@ -97,29 +107,35 @@ __device__ __forceinline__ bool ldlt4_is_positive(const double q[4][4]) {
 }
 
 // value-function update shared by the WB and RB steps (MHPC_CompoundTypes.h:128-144).  Called by ALL lanes of the warp
-// (`on` = this half-warp takes part).  Quu^-1 is the closed-form cofactor inverse (what a fixed-size Matrix4d::inverse()
-// computes): lane l forms ONE adjugate entry and does ONE division, the 16 entries are shared through scratch.
-// In: Quu/Qu/Qux in scratch, this lane's Qux column qux[4], Qx value qx, symmetrised Qxx row in Hn[].
-// Out: Hn[] = H row, G entry, K column, du, dV of the step.
-template <int NX>
-__device__ __forceinline__ bool value_update(bool on, int l, double* scr, const double qux[4], double qx, double Hn[14],
-                                             double quu_shift, double kcol[4], double du[4], double& Gout, double& dVstep) {
+// (`on` = this instance takes part; `rows` = this lane owns rows).  Quu^-1 is the closed-form cofactor inverse (what a
+// fixed-size Matrix4d::inverse() computes): every lane forms TWO adjugate entries and does TWO divisions, the 16 entries
+// are shared through scratch.
+// In: Quu/Qu/Qux in scratch; per owned row (A = row m, B = row m+7 when TWO): Qux column qux[4], Qx value qx,
+// symmetrised Qxx row in H[].  Out: H[] = new H row, G entry, K column per row; du; dV of the step.
+template <int NX, bool TWO>
+__device__ __forceinline__ bool value_update(bool on, bool rows, int m, double* scr, const double quxa[4], const double quxb[4],
+                                             double qxa, double qxb, double Ha[14], double Hb[14], double quu_shift,
+                                             double ka[4], double kb[4], double du[4], double& Ga, double& Gb, double& dVstep) {
     bool pd = true;
+#define QM(r, c) scr[S_QUU + (r) + 4 * (c)]
     if (on) {
         double tst[4][4];
 #pragma unroll
         for (int r = 0; r < 4; ++r)
 #pragma unroll
-            for (int c = 0; c < 4; ++c) tst[r][c] = scr[S_QUU + r + 4 * c] - (r == c ? 1.0 * quu_shift : 0.0);
+            for (int c = 0; c < 4; ++c) tst[r][c] = QM(r, c) - (r == c ? 1.0 * quu_shift : 0.0);
         pd = ldlt4_is_positive(tst);
         // adjugate entry r[jj][i] from the cofactor of (i, jj)
-        const int i = l & 3, jj = l >> 2;
-        const int i1 = (i + 1) & 3, i2 = (i + 2) & 3, i3 = (i + 3) & 3, j1 = (jj + 1) & 3, j2 = (jj + 2) & 3, j3 = (jj + 3) & 3;
-#define QM(r, c) scr[S_QUU + (r) + 4 * (c)]
-        const double cf = QM(i1, j1) * (QM(i2, j2) * QM(i3, j3) - QM(i2, j3) * QM(i3, j2)) +
-                          QM(i2, j1) * (QM(i3, j2) * QM(i1, j3) - QM(i3, j3) * QM(i1, j2)) +
-                          QM(i3, j1) * (QM(i1, j2) * QM(i2, j3) - QM(i1, j3) * QM(i2, j2));
-        scr[S_ADJ + jj + 4 * i] = ((i + jj) & 1) ? -cf : cf;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int l = m + 8 * h;
+            const int i = l & 3, jj = l >> 2;
+            const int i1 = (i + 1) & 3, i2 = (i + 2) & 3, i3 = (i + 3) & 3, j1 = (jj + 1) & 3, j2 = (jj + 2) & 3, j3 = (jj + 3) & 3;
+            const double cf = QM(i1, j1) * (QM(i2, j2) * QM(i3, j3) - QM(i2, j3) * QM(i3, j2)) +
+                              QM(i2, j1) * (QM(i3, j2) * QM(i1, j3) - QM(i3, j3) * QM(i1, j2)) +
+                              QM(i3, j1) * (QM(i1, j2) * QM(i2, j3) - QM(i1, j3) * QM(i2, j2));
+            scr[S_ADJ + jj + 4 * i] = ((i + jj) & 1) ? -cf : cf;
+        }
     }
     __syncwarp();
     if (on) {
@@ -128,42 +144,80 @@ __device__ __forceinline__ bool value_update(bool on, int l, double* scr, const 
         for (int i = 1; i < 4; ++i) det += QM(i, 0) * scr[S_ADJ + 0 + 4 * i];
         // adj / det; a zero numerator (every off-diagonal entry in the rigid-body phases) would send the FP64 division
         // through its slow path (quotient below the fast path's range check): 0 * det has the same value and sign
-        const double adj = scr[S_ADJ + l];
-        scr[S_INV + l] = (adj == 0.0) ? adj * det : adj / det;
-#undef QM
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int l = m + 8 * h;
+            const double adj = scr[S_ADJ + l];
+            scr[S_INV + l] = (adj == 0.0) ? adj * det : adj / det;
+        }
     }
+#undef QM
     __syncwarp();
     if (on) {
-        const int r = l & 3, c = l >> 2;
-        scr[S_QI + l] = (scr[S_INV + r + 4 * c] + scr[S_INV + c + 4 * r]) / 2;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int l = m + 8 * h;
+            const int r = l & 3, c = l >> 2;
+            scr[S_QI + l] = (scr[S_INV + r + 4 * c] + scr[S_INV + c + 4 * r]) / 2;
+        }
     }
     __syncwarp();
     if (!on || !pd) return !on ? true : false;
-    double Qu[4], T[4];
+    double Qu[4], Ta[4], Tb[4];
 #pragma unroll
     for (int c = 0; c < 4; ++c) Qu[c] = scr[S_QU + c];
+    {   // Qi(r, c) at S_QI + r + 4c; the four columns c are independent chains
+        double e4[4];
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {   // Qi(r, c) at S_QI + r + 4c
-        double sacc = (-scr[S_QI + c + 4 * 0]) * qux[0], t = qux[0] * scr[S_QI + 0 + 4 * c], e = (-scr[S_QI + c + 4 * 0]) * Qu[0];
+        for (int c = 0; c < 4; ++c) {
+            const double n0 = -scr[S_QI + c + 4 * 0], p0 = scr[S_QI + 0 + 4 * c];
+            ka[c] = n0 * quxa[0]; Ta[c] = quxa[0] * p0; kb[c] = n0 * quxb[0]; Tb[c] = quxb[0] * p0; e4[c] = n0 * Qu[0];
+        }
 #pragma unroll
         for (int cc = 1; cc < 4; ++cc) {
-            sacc += (-scr[S_QI + c + 4 * cc]) * qux[cc];
-            t += qux[cc] * scr[S_QI + cc + 4 * c];
-            e += (-scr[S_QI + c + 4 * cc]) * Qu[cc];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const double nn = -scr[S_QI + c + 4 * cc], pp = scr[S_QI + cc + 4 * c];
+                ka[c] += nn * quxa[cc];
+                Ta[c] += quxa[cc] * pp;
+                if (TWO) { kb[c] += nn * quxb[cc]; Tb[c] += quxb[cc] * pp; }
+                e4[c] += nn * Qu[cc];
+            }
         }
-        kcol[c] = sacc; T[c] = t; du[c] = e;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) du[c] = e4[c];
     }
-    double g = T[0] * Qu[0];
+    double ga = Ta[0] * Qu[0], gb = Tb[0] * Qu[0];
 #pragma unroll
-    for (int c = 1; c < 4; ++c) g += T[c] * Qu[c];
-    Gout = qx - g;
-    if (l < NX) {
+    for (int c = 1; c < 4; ++c) { ga += Ta[c] * Qu[c]; gb += Tb[c] * Qu[c]; }
+    Ga = qxa - ga;
+    Gb = qxb - gb;
+    if (rows) {
 #pragma unroll
-        for (int jc = 0; jc < NX; ++jc) {
-            double sacc = T[0] * scr[S_QUX + jc];
+        for (int j0 = 0; j0 < NX; j0 += 7) {   // seven columns (up to fourteen chains) at a time
+            double sa[7], sb[7];
 #pragma unroll
-            for (int c = 1; c < 4; ++c) sacc += T[c] * scr[S_QUX + c * 14 + jc];
-            Hn[jc] = Hn[jc] - sacc;
+            for (int k = 0; k < 7; ++k) {
+                if (j0 + k < NX) { const double u0 = scr[S_QUX + j0 + k]; sa[k] = Ta[0] * u0; sb[k] = Tb[0] * u0; }
+            }
+#pragma unroll
+            for (int c = 1; c < 4; ++c) {
+#pragma unroll
+                for (int k = 0; k < 7; ++k) {
+                    if (j0 + k < NX) {
+                        const double uc = scr[S_QUX + c * 14 + j0 + k];
+                        sa[k] += Ta[c] * uc;
+                        if (TWO) sb[k] += Tb[c] * uc;
+                    }
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < 7; ++k) {
+                if (j0 + k < NX) {
+                    Ha[j0 + k] = Ha[j0 + k] - sa[k];
+                    if (TWO) Hb[j0 + k] = Hb[j0 + k] - sb[k];
+                }
+            }
         }
     }
     double dv = 0.0;
@@ -182,13 +236,67 @@ __device__ __forceinline__ int knot_rec_len(bool wb, bool term) {
     return wb ? (term ? WB_TERM_LEN : WB_STEP_LEN) : (term ? RB_TERM_LEN : RB_STEP_LEN);
 }
 
+// ---- per-row pieces of the phase-boundary value reset (called once per owned row; rare: one knot per phase) ----------
+// WB index -> RB index of the projection P (MultiPhaseDDP.cpp:330-331): (x, z, pitch) and their rates
+__device__ __forceinline__ int wb_to_rb(int l) { return (l < 3) ? l : (l >= 7 && l < 10) ? l - 4 : -1; }
+
+__device__ __forceinline__ void embed_row(int l, const double* scr, double H[14]) {   // H <- row l of P^T H6 P
+    const int pl = wb_to_rb(l);
+#pragma unroll
+    for (int q = 0; q < 14; ++q) {
+        const int pq = wb_to_rb(q);
+        H[q] = (pl >= 0 && pq >= 0) ? scr[S_MQ + pl * MQ_LD + pq] : 0.0;
+    }
+}
+__device__ __forceinline__ void px_right_row(int l, const double* buf, double* scr, const double H[14]) {   // row l of H' Px
+#pragma unroll
+    for (int jc = 0; jc < 14; ++jc) {
+        double acc = (jc < 7) ? H[jc] : 0.0;
+        if (jc >= 2) {
+#pragma unroll
+            for (int s = 0; s < 7; ++s) acc += H[7 + s] * buf[R_AB(s, jc - 2)];
+        }
+        scr[S_MQ + l * MQ_LD + jc] = acc;
+    }
+}
+__device__ __forceinline__ double px_left_row(int l, const double* buf, const double* scr, double H[14]) {   // row l of Px^T (.), returns G entry
+    double pb[7];
+#pragma unroll
+    for (int s = 0; s < 7; ++s) pb[s] = (l >= 2) ? buf[R_AB(s, l - 2)] : 0.0;
+#pragma unroll
+    for (int jc = 0; jc < 14; ++jc) {
+        double acc = (l < 7) ? scr[S_MQ + l * MQ_LD + jc] : 0.0;
+        if (l >= 2) {
+#pragma unroll
+            for (int s = 0; s < 7; ++s) acc += pb[s] * scr[S_MQ + (7 + s) * MQ_LD + jc];
+        }
+        H[jc] = acc;
+    }
+    double g_new = (l < 7) ? scr[S_G + l] : 0.0;
+    if (l >= 2) {
+#pragma unroll
+        for (int s = 0; s < 7; ++s) g_new += pb[s] * scr[S_G + 7 + s];
+    }
+    return g_new;
+}
+__device__ __forceinline__ double wb_terminal_row(int l, const double* buf, double gnext, double H[14]) {   // Phixx + H, returns Phix + G
+#pragma unroll
+    for (int jc = 0; jc < 14; ++jc) {
+        double ph = (jc == l) ? buf[R_PHIXXD + l] : 0.0;
+        if (l >= 1 && l <= 6 && jc >= 1 && jc <= 6) ph = ph + buf[R_PHIXXB + (l - 1) + 6 * (jc - 1)];
+        H[jc] = ph + H[jc];
+    }
+    return buf[R_PHIX + l] + gnext;
+}
+
 __global__ void __launch_bounds__(BWS_THREADS, BWS_MINBLOCKS) k_bws(Dev d, Consts c, Opt opt, int mask_mode, int single_attempt) {
     extern __shared__ __align__(16) double smem[];
+    const unsigned FULL = 0xffffffffu;
     const int tid = threadIdx.x;
-    const int hw = tid >> 4, l = tid & 15;          // half-warp = instance slot in the CTA, lane within
-    const int i = blockIdx.x * BWS_INST + hw;
-    double* bufs = smem + (size_t)hw * 2 * REC;                        // [2 stages][REC] of my instance
-    double* scr = smem + (size_t)BWS_INST * 2 * REC + (size_t)hw * SCR;
+    const int q4 = tid >> 3, m = tid & 7;           // instance slot in the warp, sub-lane
+    const int i = blockIdx.x * BWS_INST + q4;
+    double* bufs = smem + (size_t)q4 * BWS_REGION;                     // [2 stages][REC] of my instance
+    double* scr = bufs + 2 * REC;
     const size_t es = d.npad;
     const bool valid = i < d.n;
     const bool enabled = valid && inst_enabled(d, i, mask_mode);
@@ -197,12 +305,15 @@ __global__ void __launch_bounds__(BWS_THREADS, BWS_MINBLOCKS) k_bws(Dev d, Const
     double reg = enabled ? d.sd[(size_t)SD_REG * es + i] : 0.0;
     int n_bws = 1;
     bool done = !enabled;
-    const int ktb = max(nk, __shfl_xor_sync(0xffffffffu, nk, 16));     // knots this warp walks
+    int ktb = max(nk, __shfl_xor_sync(FULL, nk, 8));                   // knots this warp walks
+    ktb = max(ktb, __shfl_xor_sync(FULL, ktb, 16));
     const double* lin_i = d.lin + (size_t)(valid ? i : 0) * d.KT * REC;
-    // lane-constant parts of the output addresses (SoA over instances): only `kk * stride` is added per knot
-    double* const gv_lane = d.Gv + (size_t)l * es + (valid ? i : 0);
-    double* const kf_lane = d.Kfb + (size_t)(4 * l) * es + (valid ? i : 0);
-    double* const du_lane = d.dufb + (size_t)l * es + (valid ? i : 0);
+    const bool rowl = m < 7;                                           // this sub-lane owns WB rows m and m + 7
+    // lane-constant parts of the output addresses (SoA over instances: the four instances of a warp fill one 32-byte
+    // sector per element): only `kk * stride` is added per knot
+    double* const gv_lane = d.Gv + (size_t)m * es + (valid ? i : 0);
+    double* const kf_lane = d.Kfb + (size_t)(4 * m) * es + (valid ? i : 0);
+    double* const du_lane = d.dufb + (size_t)m * es + (valid ? i : 0);
     const size_t gv_knot = 14 * es, kf_knot = (size_t)KDIM * es, du_knot = 4 * es;
 
     // per-instance schedule walker (phase p, in-phase knot k; knot slot = p*KSTRIDE + k), used both by the prefetcher
@@ -223,7 +334,7 @@ __global__ void __launch_bounds__(BWS_THREADS, BWS_MINBLOCKS) k_bws(Dev d, Const
         if (enabled && it_next < nk) {
             const int len = knot_rec_len(w.p < nwb, w.k == w.N - 1);
             const double* src = lin_i + (size_t)(w.p * KSTRIDE + w.k) * REC;
-            for (int q = l; 2 * q < len; q += 16) __pipeline_memcpy_async(dst + 2 * q, src + 2 * q, 16);
+            for (int q = m; 2 * q < len; q += BWS_LPI) __pipeline_memcpy_async(dst + 2 * q, src + 2 * q, 16);
             walk_step(w);
         }
         __pipeline_commit();
@@ -231,10 +342,11 @@ __global__ void __launch_bounds__(BWS_THREADS, BWS_MINBLOCKS) k_bws(Dev d, Const
 
     while (true) {
         // ---- one attempt -----------------------------------------------------------------
-        double Hn[14];
+        double Ha[14], Hb[14];
 #pragma unroll
-        for (int q = 0; q < 14; ++q) Hn[q] = 0.0;
-        scr[S_G + l] = 0.0;
+        for (int q = 0; q < 14; ++q) { Ha[q] = 0.0; Hb[q] = 0.0; }
+        scr[S_G + m] = 0.0;
+        scr[S_G + m + 8] = 0.0;
         double dV = 0.0;
         bool failed = false;
         Walk wk, wp;
@@ -243,114 +355,78 @@ __global__ void __launch_bounds__(BWS_THREADS, BWS_MINBLOCKS) k_bws(Dev d, Const
         __syncwarp();
         if (ktb > 0) prefetch(wp, 0, bufs);
         for (int it = 0; it < ktb; ++it) {
-            double* buf = bufs + (size_t)(it & 1) * REC;
+            const double* buf = bufs + (size_t)(it & 1) * REC;
             double* nbuf = bufs + (size_t)((it & 1) ^ 1) * REC;
             __pipeline_wait_prior(0);
             __syncwarp();
             const int alive = (!done && !failed) ? 1 : 0;
-            if (!__any_sync(0xffffffffu, alive)) break;
+            if (!__any_sync(FULL, alive)) break;
             prefetch(wp, it + 1, nbuf);
 
             // ---- which kind of knot is this for my instance? ----
             const int kk = wk.p * KSTRIDE + wk.k;   // knot slot of this step
-            const int off = wk.p * KSTRIDE;
             int ty = 0;  // 0 idle, 1 WB step, 2 RB step, 3 WB terminal, 4 RB terminal
             if (alive && it < nk) {
-                const bool wb = p < nwb, term = (kk - off == Nn - 1);
+                const bool wb = p < nwb, term = (wk.k == Nn - 1);
                 ty = wb ? (term ? 3 : 1) : (term ? 4 : 2);
             }
-            const int ty_o = __shfl_xor_sync(0xffffffffu, ty, 16);
+            const unsigned b1 = __ballot_sync(FULL, ty == 1), b2 = __ballot_sync(FULL, ty == 2), bt34 = __ballot_sync(FULL, ty >= 3);
 #define RBUF(e) buf[(e)]
 
             // ============ terminal knots: value reset across the phase boundary ============
-            if (ty == 3 || ty_o == 3 || ty == 4 || ty_o == 4) {
+            if (bt34) {
                 const bool on = (ty == 3 || ty == 4);
                 const bool last = on && (p == np - 1);
                 const bool wbp = (ty == 3);
                 const bool next_rb = on && !last && (p + 1 >= nwb);
                 // (a) WB <- RB: embed the 6-dim value into 14 dims through P^T (.) P  (MultiPhaseDDP.cpp:330-331)
                 const bool embed = wbp && next_rb;
-                double g_old = 0.0;
+                double goa = 0.0, gob = 0.0;
                 if (embed) {
-                    if (l < 6) {
+                    if (m < 6) {
 #pragma unroll
-                        for (int q = 0; q < 6; ++q) scr[S_MQ + l * MQ_LD + q] = Hn[q];
+                        for (int q = 0; q < 6; ++q) scr[S_MQ + m * MQ_LD + q] = Ha[q];
                     }
-                    const int pl = (l < 3) ? l : (l >= 7 && l < 10) ? l - 4 : -1;
-                    g_old = (pl >= 0) ? scr[S_G + pl] : 0.0;
-                }
-                __syncwarp();
-                if (embed) {
-                    const int pl = (l < 3) ? l : (l >= 7 && l < 10) ? l - 4 : -1;
-#pragma unroll
-                    for (int q = 0; q < 14; ++q) {
-                        const int pq = (q < 3) ? q : (q >= 7 && q < 10) ? q - 4 : -1;
-                        Hn[q] = (pl >= 0 && pq >= 0) ? scr[S_MQ + pl * MQ_LD + pq] : 0.0;
+                    if (rowl) {
+                        const int pa = wb_to_rb(m), pb = wb_to_rb(m + 7);
+                        goa = (pa >= 0) ? scr[S_G + pa] : 0.0;
+                        gob = (pb >= 0) ? scr[S_G + pb] : 0.0;
                     }
                 }
                 __syncwarp();
-                if (embed && l < 14) scr[S_G + l] = g_old;
+                if (embed && rowl) { embed_row(m, scr, Ha); embed_row(m + 7, scr, Hb); }
+                __syncwarp();
+                if (embed && rowl) { scr[S_G + m] = goa; scr[S_G + m + 7] = gob; }
                 __syncwarp();
                 // (b) WB phase end: G = Px^T G', H = Px^T H' Px  (MultiPhaseDDP.cpp:320-326), Px = [I7 0; 0 Pb]
                 const bool px = wbp && !last;
-                if (px && l < 14) {
-#pragma unroll
-                    for (int jc = 0; jc < 14; ++jc) {
-                        double acc = (jc < 7) ? Hn[jc] : 0.0;
-                        if (jc >= 2) {
-#pragma unroll
-                            for (int s = 0; s < 7; ++s) acc += Hn[7 + s] * RBUF(R_AB(s, jc - 2));
-                        }
-                        scr[S_MQ + l * MQ_LD + jc] = acc;
-                    }
-                }
+                if (px && rowl) { px_right_row(m, buf, scr, Ha); px_right_row(m + 7, buf, scr, Hb); }
                 __syncwarp();
-                double g_new = 0.0;
-                if (px && l < 14) {
-                    double pb[7];
-#pragma unroll
-                    for (int s = 0; s < 7; ++s) pb[s] = (l >= 2) ? RBUF(R_AB(s, l - 2)) : 0.0;
-#pragma unroll
-                    for (int jc = 0; jc < 14; ++jc) {
-                        double acc = (l < 7) ? scr[S_MQ + l * MQ_LD + jc] : 0.0;
-                        if (l >= 2) {
-#pragma unroll
-                            for (int s = 0; s < 7; ++s) acc += pb[s] * scr[S_MQ + (7 + s) * MQ_LD + jc];
-                        }
-                        Hn[jc] = acc;
-                    }
-                    g_new = (l < 7) ? scr[S_G + l] : 0.0;
-                    if (l >= 2) {
-#pragma unroll
-                        for (int s = 0; s < 7; ++s) g_new += pb[s] * scr[S_G + 7 + s];
-                    }
-                }
+                double gna = 0.0, gnb = 0.0;
+                if (px && rowl) { gna = px_left_row(m, buf, scr, Ha); gnb = px_left_row(m + 7, buf, scr, Hb); }
                 __syncwarp();
-                if (px && l < 14) scr[S_G + l] = g_new;
+                if (px && rowl) { scr[S_G + m] = gna; scr[S_G + m + 7] = gnb; }
                 __syncwarp();
                 // (c) terminal cost: G = Phix + Gnext, H = Phixx + Hnext  (SinglePhase.cpp:190-191)
                 if (on) {
                     if (last) {
 #pragma unroll
-                        for (int q = 0; q < 14; ++q) Hn[q] = 0.0;
+                        for (int q = 0; q < 14; ++q) { Ha[q] = 0.0; Hb[q] = 0.0; }
                     }
-                    const int nx = wbp ? 14 : 6;
-                    if (l < nx) {
-                        double gv = last ? 0.0 : scr[S_G + l];
-                        if (wbp) {
-#pragma unroll
-                            for (int jc = 0; jc < 14; ++jc) {
-                                double ph = (jc == l) ? RBUF(R_PHIXXD + l) : 0.0;
-                                if (l >= 1 && l <= 6 && jc >= 1 && jc <= 6) ph = ph + RBUF(R_PHIXXB + (l - 1) + 6 * (jc - 1));
-                                Hn[jc] = ph + Hn[jc];
-                            }
-                            gv = RBUF(R_PHIX + l) + gv;
-                        } else {
-#pragma unroll
-                            for (int jc = 0; jc < 6; ++jc) Hn[jc] = ((jc == l) ? c.rbQf[l] : 0.0) + Hn[jc];
-                            gv = RBUF(R_RPHIX + l) + gv;
+                    if (wbp) {
+                        if (rowl) {
+                            const double ga = wb_terminal_row(m, buf, last ? 0.0 : scr[S_G + m], Ha);
+                            const double gb = wb_terminal_row(m + 7, buf, last ? 0.0 : scr[S_G + m + 7], Hb);
+                            scr[S_G + m] = ga; scr[S_G + m + 7] = gb;
+                            gv_lane[(size_t)kk * gv_knot] = ga;
+                            gv_lane[(size_t)kk * gv_knot + 7 * es] = gb;
                         }
-                        scr[S_G + l] = gv;
+                    } else if (m < 6) {
+                        double gv = last ? 0.0 : scr[S_G + m];
+#pragma unroll
+                        for (int jc = 0; jc < 6; ++jc) Ha[jc] = ((jc == m) ? c.rbQf[m] : 0.0) + Ha[jc];
+                        gv = RBUF(R_RPHIX + m) + gv;
+                        scr[S_G + m] = gv;
                         gv_lane[(size_t)kk * gv_knot] = gv;
                     }
                 }
@@ -358,79 +434,145 @@ __global__ void __launch_bounds__(BWS_THREADS, BWS_MINBLOCKS) k_bws(Dev d, Const
             }
 
             // ============ whole-body step ============
-            if (ty == 1 || ty_o == 1) {
+            if (b1) {
                 const bool on = (ty == 1);
+                const bool rw = on && rowl;
                 const double dt = dtw;
-                const int r0 = (mode == 1) ? 2 : 0;
-                if (on && l < 14) {
+                const int la = m, lb = m + 7;
+                double Ma[14];
+                if (rw) {
+                    // M = H A, rows la and lb; rows 7..13 are shared through scratch.  Columns go in blocks of four so that
+                    // eight accumulation chains (4 columns x 2 rows) are in flight; each chain keeps the ascending-s order.
+                    Ma[0] = Ha[0]; Ma[1] = Ha[1];
+                    scr[S_MQ + m * MQ_LD + 0] = Hb[0]; scr[S_MQ + m * MQ_LD + 1] = Hb[1];
 #pragma unroll
-                    for (int jc = 0; jc < 14; ++jc) {   // M = H A
-                        double acc;
-                        if (jc < 2) acc = Hn[jc];
-                        else {
-                            acc = (jc < 7) ? Hn[jc] : Hn[jc - 7] * dt;
+                    for (int j0 = 2; j0 < 14; j0 += 4) {
+                        double xa[4], xb[4];
 #pragma unroll
-                            for (int s = 0; s < 7; ++s) acc += Hn[7 + s] * RBUF(R_AB(s, jc - 2));
+                        for (int k = 0; k < 4; ++k) {
+                            const int jc = j0 + k;
+                            xa[k] = (jc < 7) ? Ha[jc] : Ha[jc - 7] * dt;
+                            xb[k] = (jc < 7) ? Hb[jc] : Hb[jc - 7] * dt;
                         }
-                        scr[S_MQ + l * MQ_LD + jc] = acc;
+#pragma unroll
+                        for (int s = 0; s < 7; ++s) {
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                const double e = RBUF(R_AB(s, j0 + k - 2));
+                                xa[k] += Ha[7 + s] * e;
+                                xb[k] += Hb[7 + s] * e;
+                            }
+                        }
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) { Ma[j0 + k] = xa[k]; scr[S_MQ + m * MQ_LD + j0 + k] = xb[k]; }
                     }
-                    if (l >= 7) {
+                    {   // N = H B (rows 7..13 are all B^T N needs)
+                        double nn[4];
 #pragma unroll
-                        for (int cc = 0; cc < 4; ++cc) {   // N = H B (rows 7..13 are all B^T N needs)
-                            double acc = Hn[7] * RBUF(R_BB(0, cc));
+                        for (int cc = 0; cc < 4; ++cc) nn[cc] = Hb[7] * RBUF(R_BB(0, cc));
 #pragma unroll
-                            for (int s = 1; s < 7; ++s) acc += Hn[7 + s] * RBUF(R_BB(s, cc));
-                            scr[S_N + (l - 7) * 4 + cc] = acc;
-                        }
+                        for (int s = 1; s < 7; ++s)
+#pragma unroll
+                            for (int cc = 0; cc < 4; ++cc) nn[cc] += Hb[7 + s] * RBUF(R_BB(s, cc));
+#pragma unroll
+                        for (int cc = 0; cc < 4; ++cc) scr[S_N + m * 4 + cc] = nn[cc];
                     }
                 }
                 __syncwarp();
-                double qux[4] = {0, 0, 0, 0}, qx = 0.0;
+                double quxa[4] = {0, 0, 0, 0}, quxb[4] = {0, 0, 0, 0}, qxa = 0.0, qxb = 0.0;
                 if (on) {
                     const double L00 = RBUF(R_LYY), L01 = RBUF(R_LYY + 1), L11 = RBUF(R_LYY + 2);
                     const double ly0 = RBUF(R_LY), ly1 = RBUF(R_LY + 1);
-                    if (l < 14) {
-                        double ab[7];
+                    if (rowl) {
+                        double aba[7], abb[7];
 #pragma unroll
-                        for (int s = 0; s < 7; ++s) ab[s] = (l >= 2) ? RBUF(R_AB(s, l - 2)) : 0.0;
-                        const double c0 = (l >= 2) ? RBUF(R_CB(0, l - 2)) : 0.0, c1 = (l >= 2) ? RBUF(R_CB(1, l - 2)) : 0.0;
-                        const double w0 = c0 * L00 + c1 * L01, w1 = c0 * L01 + c1 * L11;   // row l of C^T lyy
-                        const double lxxd = (l >= 3 && l < 7) ? RBUF(R_LXXQ + (l - 3)) : (2 * dt) * c.wbQ[l];
+                        for (int s = 0; s < 7; ++s) { aba[s] = (la >= 2) ? RBUF(R_AB(s, la - 2)) : 0.0; abb[s] = RBUF(R_AB(s, lb - 2)); }
+                        const double c0a = (la >= 2) ? RBUF(R_CB(0, la - 2)) : 0.0, c1a = (la >= 2) ? RBUF(R_CB(1, la - 2)) : 0.0;
+                        const double c0b = RBUF(R_CB(0, lb - 2)), c1b = RBUF(R_CB(1, lb - 2));
+                        const double w0a = c0a * L00 + c1a * L01, w1a = c0a * L01 + c1a * L11;   // row of C^T lyy
+                        const double w0b = c0b * L00 + c1b * L01, w1b = c0b * L01 + c1b * L11;
+                        const double lxxda = (la >= 3) ? RBUF(R_LXXQ + (la - 3)) : (2 * dt) * c.wbQ[la];
+                        const double lxxdb = (2 * dt) * c.wbQ[lb];
+                        // Qxx rows = (lxx + C^T lyy C) + A^T M, four columns (eight chains) at a time
+                        double Qa[14], Qb[14];
 #pragma unroll
-                        for (int jc = 0; jc < 14; ++jc) {   // Qxx row l = (lxx + C^T lyy C) + A^T M
-                            double q;
-                            if (l < 2) q = scr[S_MQ + l * MQ_LD + jc];
-                            else {
-                                q = (l < 7) ? scr[S_MQ + l * MQ_LD + jc] : scr[S_MQ + (l - 7) * MQ_LD + jc] * dt;
+                        for (int j0 = 0; j0 < 14; j0 += 4) {
+                            double qa[4], qb[4];
 #pragma unroll
-                                for (int s = 0; s < 7; ++s) q += ab[s] * scr[S_MQ + (7 + s) * MQ_LD + jc];
+                            for (int k = 0; k < 4; ++k) {
+                                if (j0 + k < 14) { qa[k] = Ma[j0 + k]; qb[k] = Ma[j0 + k] * dt; }
                             }
-                            double lc = (jc == l) ? lxxd : 0.0;
-                            if (l >= 2 && jc >= 2) lc = lc + (w0 * RBUF(R_CB(0, jc - 2)) + w1 * RBUF(R_CB(1, jc - 2)));
-                            Hn[jc] = lc + q;
-                            if (jc == l) Hn[jc] += 1.0 * reg;
+#pragma unroll
+                            for (int s = 0; s < 7; ++s) {
+#pragma unroll
+                                for (int k = 0; k < 4; ++k) {
+                                    if (j0 + k < 14) {
+                                        const double mr = scr[S_MQ + s * MQ_LD + j0 + k];
+                                        if (la >= 2) qa[k] += aba[s] * mr;
+                                        qb[k] += abb[s] * mr;
+                                    }
+                                }
+                            }
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                const int jc = j0 + k;
+                                if (jc < 14) {
+                                    double lca = (jc == la) ? lxxda : 0.0, lcb = (jc == lb) ? lxxdb : 0.0;
+                                    if (jc >= 2) {
+                                        const double cj0 = RBUF(R_CB(0, jc - 2)), cj1 = RBUF(R_CB(1, jc - 2));
+                                        if (la >= 2) lca = lca + (w0a * cj0 + w1a * cj1);
+                                        lcb = lcb + (w0b * cj0 + w1b * cj1);
+                                    }
+                                    Qa[jc] = lca + qa[k];
+                                    if (jc == la) Qa[jc] += 1.0 * reg;
+                                    Qb[jc] = lcb + qb[k];
+                                    if (jc == lb) Qb[jc] += 1.0 * reg;
+                                }
+                            }
                         }
+#pragma unroll
+                        for (int jc = 0; jc < 14; ++jc) { Ha[jc] = Qa[jc]; Hb[jc] = Qb[jc]; }
                         // Qx = (lx + A^T G) + C^T ly
-                        double ag;
-                        if (l < 2) ag = scr[S_G + l];
+                        double aga, agb;
+                        if (la < 2) aga = scr[S_G + la];
                         else {
-                            ag = (l < 7) ? scr[S_G + l] : scr[S_G + l - 7] * dt;
+                            aga = scr[S_G + la];
 #pragma unroll
-                            for (int s = 0; s < 7; ++s) ag += ab[s] * scr[S_G + 7 + s];
+                            for (int s = 0; s < 7; ++s) aga += aba[s] * scr[S_G + 7 + s];
                         }
-                        qx = (RBUF(R_LX + l) + ag) + (c0 * ly0 + c1 * ly1);
-                        // Qux column l = (0 + D^T lyy C) + B^T M
+                        agb = scr[S_G + la] * dt;
 #pragma unroll
-                        for (int cc = 0; cc < 4; ++cc) {
-                            double acc = RBUF(R_BB(0, cc)) * scr[S_MQ + 7 * MQ_LD + l];
+                        for (int s = 0; s < 7; ++s) agb += abb[s] * scr[S_G + 7 + s];
+                        qxa = (RBUF(R_LX + la) + aga) + (c0a * ly0 + c1a * ly1);
+                        qxb = (RBUF(R_LX + lb) + agb) + (c0b * ly0 + c1b * ly1);
+                        // Qux columns la, lb = (0 + D^T lyy C) + B^T M
+                        {
+                            double xa[4], xb[4];
+                            const double m0a = scr[S_MQ + 0 * MQ_LD + la], m0b = scr[S_MQ + 0 * MQ_LD + lb];
 #pragma unroll
-                            for (int s = 1; s < 7; ++s) acc += RBUF(R_BB(s, cc)) * scr[S_MQ + (7 + s) * MQ_LD + l];
-                            const double d0 = RBUF(R_DB(0, cc)), d1 = RBUF(R_DB(1, cc));
-                            const double v0 = d0 * L00 + d1 * L01, v1 = d0 * L01 + d1 * L11;
-                            qux[cc] = (0.0 + (v0 * c0 + v1 * c1)) + acc;
+                            for (int cc = 0; cc < 4; ++cc) { const double b0 = RBUF(R_BB(0, cc)); xa[cc] = b0 * m0a; xb[cc] = b0 * m0b; }
+#pragma unroll
+                            for (int s = 1; s < 7; ++s) {
+                                const double msa = scr[S_MQ + s * MQ_LD + la], msb = scr[S_MQ + s * MQ_LD + lb];
+#pragma unroll
+                                for (int cc = 0; cc < 4; ++cc) {
+                                    const double bs = RBUF(R_BB(s, cc));
+                                    xa[cc] += bs * msa;
+                                    xb[cc] += bs * msb;
+                                }
+                            }
+#pragma unroll
+                            for (int cc = 0; cc < 4; ++cc) {
+                                const double d0 = RBUF(R_DB(0, cc)), d1 = RBUF(R_DB(1, cc));
+                                const double v0 = d0 * L00 + d1 * L01, v1 = d0 * L01 + d1 * L11;
+                                quxa[cc] = (0.0 + (v0 * c0a + v1 * c1a)) + xa[cc];
+                                quxb[cc] = (0.0 + (v0 * c0b + v1 * c1b)) + xb[cc];
+                            }
                         }
                     }
-                    {   // Quu entry (row l&3, col l>>2) = (luu + D^T lyy D) + B^T N
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {   // Quu entries (row l&3, col l>>2), l = m and m + 8: (luu + D^T lyy D) + B^T N
+                        const int l = m + 8 * h;
                         const int rr = l & 3, cc = l >> 2;
                         double acc = RBUF(R_BB(0, rr)) * scr[S_N + 0 * 4 + cc];
 #pragma unroll
@@ -441,42 +583,47 @@ __global__ void __launch_bounds__(BWS_THREADS, BWS_MINBLOCKS) k_bws(Dev d, Const
                         if (rr == cc) q += 1.0 * reg;
                         scr[S_QUU + rr + 4 * cc] = q;
                     }
-                    if (l < 4) {   // Qu = (lu + B^T G) + D^T ly
-                        double acc = RBUF(R_BB(0, l)) * scr[S_G + 7];
+                    if (m < 4) {   // Qu = (lu + B^T G) + D^T ly
+                        double acc = RBUF(R_BB(0, m)) * scr[S_G + 7];
 #pragma unroll
-                        for (int s = 1; s < 7; ++s) acc += RBUF(R_BB(s, l)) * scr[S_G + 7 + s];
-                        scr[S_QU + l] = (RBUF(R_LU + l) + acc) + (RBUF(R_DB(0, l)) * ly0 + RBUF(R_DB(1, l)) * ly1);
+                        for (int s = 1; s < 7; ++s) acc += RBUF(R_BB(s, m)) * scr[S_G + 7 + s];
+                        scr[S_QU + m] = (RBUF(R_LU + m) + acc) + (RBUF(R_DB(0, m)) * ly0 + RBUF(R_DB(1, m)) * ly1);
                     }
-                    (void)r0;
                 }
                 __syncwarp();   // everyone is done reading M
-                if (on && l < 14) {
+                if (rw) {
 #pragma unroll
-                    for (int jc = 0; jc < 14; ++jc) scr[S_MQ + l * MQ_LD + jc] = Hn[jc];
+                    for (int jc = 0; jc < 14; ++jc) { scr[S_MQ + la * MQ_LD + jc] = Ha[jc]; scr[S_MQ + lb * MQ_LD + jc] = Hb[jc]; }
 #pragma unroll
-                    for (int cc = 0; cc < 4; ++cc) scr[S_QUX + cc * 14 + l] = qux[cc];
+                    for (int cc = 0; cc < 4; ++cc) { scr[S_QUX + cc * 14 + la] = quxa[cc]; scr[S_QUX + cc * 14 + lb] = quxb[cc]; }
                 }
                 __syncwarp();
-                if (on && l < 14) {
+                if (rw) {
 #pragma unroll
-                    for (int jc = 0; jc < 14; ++jc) Hn[jc] = (Hn[jc] + scr[S_MQ + jc * MQ_LD + l]) / 2;   // Qxx = (Qxx + Qxx^T)/2
+                    for (int jc = 0; jc < 14; ++jc) {   // Qxx = (Qxx + Qxx^T)/2
+                        Ha[jc] = (Ha[jc] + scr[S_MQ + jc * MQ_LD + la]) / 2;
+                        Hb[jc] = (Hb[jc] + scr[S_MQ + jc * MQ_LD + lb]) / 2;
+                    }
                 }
-                double kcol[4], du[4], gout = 0.0, dvs = 0.0;
-                bool ok = true;
+                double ka[4], kb[4], du[4], goa = 0.0, gob = 0.0, dvs = 0.0;
                 __syncwarp();
-                ok = value_update<14>(on, l, scr, qux, qx, Hn, opt.quu_shift, kcol, du, gout, dvs);
+                const bool ok = value_update<14, true>(on, rw, m, scr, quxa, quxb, qxa, qxb, Ha, Hb, opt.quu_shift, ka, kb, du, goa, gob, dvs);
                 __syncwarp();
                 if (on) {
                     if (!ok) failed = true;
                     else {
                         dV += dvs;
-                        if (l < 14) {
-                            scr[S_G + l] = gout;
-                            gv_lane[(size_t)kk * gv_knot] = gout;
+                        if (rowl) {
+                            scr[S_G + la] = goa; scr[S_G + lb] = gob;
+                            gv_lane[(size_t)kk * gv_knot] = goa;
+                            gv_lane[(size_t)kk * gv_knot + 7 * es] = gob;
 #pragma unroll
-                            for (int cc = 0; cc < 4; ++cc) kf_lane[(size_t)kk * kf_knot + (size_t)cc * es] = kcol[cc];
+                            for (int cc = 0; cc < 4; ++cc) {
+                                kf_lane[(size_t)kk * kf_knot + (size_t)cc * es] = ka[cc];
+                                kf_lane[(size_t)kk * kf_knot + (size_t)(28 + cc) * es] = kb[cc];
+                            }
                         }
-                        if (l < 4) du_lane[(size_t)kk * du_knot] = du[l];
+                        if (m < 4) du_lane[(size_t)kk * du_knot] = du[m];
                     }
                 }
                 __syncwarp();
@@ -485,25 +632,27 @@ __global__ void __launch_bounds__(BWS_THREADS, BWS_MINBLOCKS) k_bws(Dev d, Const
             // ============ rigid-body step ============
             // A = I + dt*[0 I3; 0 0] + e5 (a0, a1, 0, 0, 0, 0), B has two non-zeros per column (rows 3 + (c&1) and 5):
             // only exact-zero terms of the reference's dense 6x6 products are dropped, the remaining terms keep the
-            // ascending inner-index order.
-            if (ty == 2 || ty_o == 2) {
+            // ascending inner-index order.  Sub-lane m < 6 owns row m (in Ha).
+            if (b2) {
                 const bool on = (ty == 2);
+                const bool rw = on && m < 6;
+                const int l = m;
                 const double dt = dtf;
                 const double a0 = on ? RBUF(R_RA) : 0.0, a1 = on ? RBUF(R_RA + 1) : 0.0;
                 double bt[4], b5[4];   // B(3 + (c&1), c), B(5, c)
 #pragma unroll
                 for (int cc = 0; cc < 4; ++cc) { bt[cc] = on ? RBUF(R_RB + 2 * cc) : 0.0; b5[cc] = on ? RBUF(R_RB + 2 * cc + 1) : 0.0; }
-                if (on && l < 6) {
+                if (rw) {
                     // M = H A (row l)
-                    scr[S_MQ + l * MQ_LD + 0] = Hn[0] + Hn[5] * a0;
-                    scr[S_MQ + l * MQ_LD + 1] = Hn[1] + Hn[5] * a1;
-                    scr[S_MQ + l * MQ_LD + 2] = Hn[2];
-                    scr[S_MQ + l * MQ_LD + 3] = Hn[0] * dt + Hn[3];
-                    scr[S_MQ + l * MQ_LD + 4] = Hn[1] * dt + Hn[4];
-                    scr[S_MQ + l * MQ_LD + 5] = Hn[2] * dt + Hn[5];
+                    scr[S_MQ + l * MQ_LD + 0] = Ha[0] + Ha[5] * a0;
+                    scr[S_MQ + l * MQ_LD + 1] = Ha[1] + Ha[5] * a1;
+                    scr[S_MQ + l * MQ_LD + 2] = Ha[2];
+                    scr[S_MQ + l * MQ_LD + 3] = Ha[0] * dt + Ha[3];
+                    scr[S_MQ + l * MQ_LD + 4] = Ha[1] * dt + Ha[4];
+                    scr[S_MQ + l * MQ_LD + 5] = Ha[2] * dt + Ha[5];
                     // N = H B (row l)
 #pragma unroll
-                    for (int cc = 0; cc < 4; ++cc) scr[S_N + l * 4 + cc] = Hn[3 + (cc & 1)] * bt[cc] + Hn[5] * b5[cc];
+                    for (int cc = 0; cc < 4; ++cc) scr[S_N + l * 4 + cc] = Ha[3 + (cc & 1)] * bt[cc] + Ha[5] * b5[cc];
                 }
                 __syncwarp();
                 double qux[4] = {0, 0, 0, 0}, qx = 0.0;
@@ -516,8 +665,8 @@ __global__ void __launch_bounds__(BWS_THREADS, BWS_MINBLOCKS) k_bws(Dev d, Const
                             if (l < 2) q = scr[S_MQ + l * MQ_LD + jc] + acol * scr[S_MQ + 5 * MQ_LD + jc];
                             else if (l == 2) q = scr[S_MQ + 2 * MQ_LD + jc];
                             else q = dt * scr[S_MQ + (l - 3) * MQ_LD + jc] + scr[S_MQ + l * MQ_LD + jc];
-                            Hn[jc] = ((jc == l) ? (2 * dt) * c.rbQ[l] : 0.0) + q;
-                            if (jc == l) Hn[jc] += 1.0 * reg;
+                            Ha[jc] = ((jc == l) ? (2 * dt) * c.rbQ[l] : 0.0) + q;
+                            if (jc == l) Ha[jc] += 1.0 * reg;
                         }
                         double ag;
                         if (l < 2) ag = scr[S_G + l] + acol * scr[S_G + 5];
@@ -528,30 +677,38 @@ __global__ void __launch_bounds__(BWS_THREADS, BWS_MINBLOCKS) k_bws(Dev d, Const
                         for (int cc = 0; cc < 4; ++cc)   // Qux column l = B^T M
                             qux[cc] = bt[cc] * scr[S_MQ + (3 + (cc & 1)) * MQ_LD + l] + b5[cc] * scr[S_MQ + 5 * MQ_LD + l];
                     }
-                    {
-                        const int rr = l & 3, cc = l >> 2;
-                        const double acc = bt[rr] * scr[S_N + (3 + (rr & 1)) * 4 + cc] + b5[rr] * scr[S_N + 5 * 4 + cc];
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const int e = m + 8 * h;
+                        const int rr = e & 3, cc = e >> 2;
+                        const double btr = (rr == 0) ? bt[0] : (rr == 1) ? bt[1] : (rr == 2) ? bt[2] : bt[3];
+                        const double b5r = (rr == 0) ? b5[0] : (rr == 1) ? b5[1] : (rr == 2) ? b5[2] : b5[3];
+                        const double acc = btr * scr[S_N + (3 + (rr & 1)) * 4 + cc] + b5r * scr[S_N + 5 * 4 + cc];
                         double q = ((rr == cc) ? (2 * dt) * c.rbR[mode - 1][rr] : 0.0) + acc;
                         if (rr == cc) q += 1.0 * reg;
                         scr[S_QUU + rr + 4 * cc] = q;
                     }
-                    if (l < 4) scr[S_QU + l] = RBUF(R_RLU + l) + (bt[l] * scr[S_G + 3 + (l & 1)] + b5[l] * scr[S_G + 5]);
+                    if (m < 4) {
+                        const double btm = (m == 0) ? bt[0] : (m == 1) ? bt[1] : (m == 2) ? bt[2] : bt[3];
+                        const double b5m = (m == 0) ? b5[0] : (m == 1) ? b5[1] : (m == 2) ? b5[2] : b5[3];
+                        scr[S_QU + m] = RBUF(R_RLU + m) + (btm * scr[S_G + 3 + (m & 1)] + b5m * scr[S_G + 5]);
+                    }
                 }
                 __syncwarp();
-                if (on && l < 6) {
+                if (rw) {
 #pragma unroll
-                    for (int jc = 0; jc < 6; ++jc) scr[S_MQ + l * MQ_LD + jc] = Hn[jc];
+                    for (int jc = 0; jc < 6; ++jc) scr[S_MQ + l * MQ_LD + jc] = Ha[jc];
 #pragma unroll
                     for (int cc = 0; cc < 4; ++cc) scr[S_QUX + cc * 14 + l] = qux[cc];
                 }
                 __syncwarp();
-                if (on && l < 6) {
+                if (rw) {
 #pragma unroll
-                    for (int jc = 0; jc < 6; ++jc) Hn[jc] = (Hn[jc] + scr[S_MQ + jc * MQ_LD + l]) / 2;
+                    for (int jc = 0; jc < 6; ++jc) Ha[jc] = (Ha[jc] + scr[S_MQ + jc * MQ_LD + l]) / 2;
                 }
-                double kcol[4], du[4], gout = 0.0, dvs = 0.0;
+                double ka[4], kb[4], du[4], gout = 0.0, gdummy = 0.0, dvs = 0.0;
                 __syncwarp();
-                bool ok = value_update<6>(on, l, scr, qux, qx, Hn, opt.quu_shift, kcol, du, gout, dvs);
+                const bool ok = value_update<6, false>(on, rw, m, scr, qux, qux, qx, qx, Ha, Hb, opt.quu_shift, ka, kb, du, gout, gdummy, dvs);
                 if (on) {
                     if (!ok) failed = true;
                     else {
@@ -560,9 +717,9 @@ __global__ void __launch_bounds__(BWS_THREADS, BWS_MINBLOCKS) k_bws(Dev d, Const
                             scr[S_G + l] = gout;
                             gv_lane[(size_t)kk * gv_knot] = gout;
 #pragma unroll
-                            for (int cc = 0; cc < 4; ++cc) kf_lane[(size_t)kk * kf_knot + (size_t)cc * es] = kcol[cc];
+                            for (int cc = 0; cc < 4; ++cc) kf_lane[(size_t)kk * kf_knot + (size_t)cc * es] = ka[cc];
                         }
-                        if (l < 4) du_lane[(size_t)kk * du_knot] = du[l];
+                        if (m < 4) du_lane[(size_t)kk * du_knot] = du[m];
                     }
                 }
                 __syncwarp();
@@ -577,17 +734,17 @@ __global__ void __launch_bounds__(BWS_THREADS, BWS_MINBLOCKS) k_bws(Dev d, Const
         int retry = 0;
         if (!done) {
             if (single_attempt) {
-                if (l == 0) { d.si[(size_t)SI_BWS_OK * es + i] = failed ? 0 : 1; if (!failed) d.sd[(size_t)SD_DV * es + i] = dV; }
+                if (m == 0) { d.si[(size_t)SI_BWS_OK * es + i] = failed ? 0 : 1; if (!failed) d.sd[(size_t)SD_DV * es + i] = dV; }
                 done = true;
             } else if (failed) {
                 reg = fmax(reg * opt.update_regularization, 1e-03);
                 ++n_bws;
                 if (reg > 1000) {
-                    if (l == 0) { d.si[(size_t)SI_STATUS * es + i] = STATUS_REG_ABORT; d.si[(size_t)SI_DDP_ACTIVE * es + i] = 0; d.si[(size_t)SI_N_BWS * es + i] = n_bws; }
+                    if (m == 0) { d.si[(size_t)SI_STATUS * es + i] = STATUS_REG_ABORT; d.si[(size_t)SI_DDP_ACTIVE * es + i] = 0; d.si[(size_t)SI_N_BWS * es + i] = n_bws; }
                     done = true;
                 } else retry = 1;
             } else {
-                if (l == 0) {
+                if (m == 0) {
                     d.sd[(size_t)SD_DV * es + i] = dV;
                     d.sd[(size_t)SD_REG_USED * es + i] = reg;
                     double r2 = reg / 20;
@@ -599,7 +756,7 @@ __global__ void __launch_bounds__(BWS_THREADS, BWS_MINBLOCKS) k_bws(Dev d, Const
                 done = true;
             }
         }
-        if (!__any_sync(0xffffffffu, retry)) break;
+        if (!__any_sync(FULL, retry)) break;
     }
 }
 
