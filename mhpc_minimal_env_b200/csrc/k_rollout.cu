@@ -3,25 +3,51 @@
 // rollouts.  Time is sequential inside the thread.  Lane mapping: with S = 2^k slots per launch a warp
 // holds the S trials of 32/S consecutive instances (lane = instance_in_warp * S + slot), so the trials
 // of one instance - which share its schedule, nominal trajectory and gains - never diverge and read K,
-// du, x_nom, u_nom as broadcasts, while each store still fills whole 32 B sectors (32/S consecutive
-// instances per row).  A single-slot launch (forward_sweep) maps lanes to 32 consecutive instances.
+// du, x_nom, u_nom as shared-memory broadcasts, while each store still fills whole 32 B sectors (32/S
+// consecutive instances per row).  A single-slot launch (forward_sweep) maps lanes to 32 consecutive instances.
+#include <cuda_pipeline.h>
+
+#include <algorithm>
+
 #include "kernels.h"
 #include "model.cuh"
 
 namespace mhpc {
 
-__global__ void __launch_bounds__(128) k_rollout(Dev d, Consts c, Opt opt, int mask_mode, int n_slots, int trial0, EpsList eps_list) {
-    const int tid = blockIdx.x * blockDim.x + threadIdx.x;
-    int w, i;
-    if (n_slots > 1 && n_slots <= 32 && (n_slots & (n_slots - 1)) == 0) {
-        const int lane = tid & 31, per_warp = 32 / n_slots;
-        w = lane % n_slots;
-        i = (tid >> 5) * per_warp + lane / n_slots;
-    } else {
-        w = tid / d.npad;
-        i = tid - w * d.npad;
+// Everything a step reads from HBM besides its own state (nominal x/u, the gain K, du, the reference position) sits at
+// addresses known in advance; the trajectories and gains of a batch (GBs) do not stay in L2 between kernels, so read in
+// place each step exposes several dependent DRAM/L2 round trips (ncu: 54 % of the warp time on the long scoreboard).
+// The lanes that hold the trials of one instance stream that instance's next knot into shared memory with cp.async, one
+// step ahead of the math (double buffered, synchronised inside the lane group only, so instances with different phase
+// lengths may share a warp).
+constexpr int RO_X = 0, RO_U = 14, RO_K = 18, RO_DU = 74, RO_POS = 78, RO_STAGE = 80;
+
+template <int NXP>   // 14 whole-body, 6 rigid-body
+__device__ __forceinline__ void stage_knot(const Dev& d, int kk, int i, int w, int n_lanes, double* dst) {
+    const size_t es = d.npad;
+    const double* sn = d.st_nom + st_idx(d, kk, 0, i);
+    const double* kf = d.Kfb + (size_t)kk * KDIM * es + i;
+    const double* du = d.dufb + (size_t)kk * 4 * es + i;
+    for (int t = w; t < 4 * NXP; t += n_lanes) __pipeline_memcpy_async(dst + RO_K + t, kf + (size_t)t * es, 8);
+    for (int t = w; t < NXP; t += n_lanes) __pipeline_memcpy_async(dst + RO_X + t, sn + (size_t)t * es, 8);
+    for (int t = w; t < 4; t += n_lanes) {
+        __pipeline_memcpy_async(dst + RO_U + t, sn + (size_t)(14 + t) * es, 8);
+        __pipeline_memcpy_async(dst + RO_DU + t, du + (size_t)t * es, 8);
     }
-    if (w >= n_slots || i >= d.n) return;
+    if (w == n_lanes - 1) __pipeline_memcpy_async(dst + RO_POS, d.pos_ref + (size_t)kk * es + i, 8);
+    __pipeline_commit();
+}
+
+__global__ void __launch_bounds__(128) k_rollout(Dev d, Consts c, Opt opt, int mask_mode, int n_slots, int n_used, int trial0, EpsList eps_list) {
+    extern __shared__ __align__(16) double ro_smem[];
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+    // n_slots is a power of two <= 32 (launch_rollout): lane = instance_in_warp * n_slots + slot; slots >= n_used are padding
+    const int lane = tid & 31, per_warp = 32 / n_slots;
+    const int w = lane % n_slots;
+    const int i = (tid >> 5) * per_warp + lane / n_slots;
+    const unsigned grp = (n_used == 32 ? 0xffffffffu : ((1u << n_used) - 1u)) << (lane - w);   // lanes holding the trials of my instance
+    double* stage = ro_smem + (size_t)(threadIdx.x / n_slots) * 2 * RO_STAGE;                // [2][RO_STAGE] of my instance
+    if (w >= n_used || i >= d.n) return;
     if (!inst_enabled(d, i, mask_mode)) return;
     if (mask_mode == MASK_LS && d.si[(size_t)SI_LS_DONE * d.npad + i]) return;
     const double eps = eps_list.eps[trial0 + w];
@@ -44,24 +70,30 @@ __global__ void __launch_bounds__(128) k_rollout(Dev d, Consts c, Opt opt, int m
             double par[6];
 #pragma unroll
             for (int q = 0; q < 6; ++q) par[q] = d.par[par_idx(d, p, PAR_DELTA_T + q, i)];
+            __syncwarp(grp);
+            if (N > 1) stage_knot<14>(d, off, i, w, n_used, stage);
             for (int k = 0; k < N - 1; ++k) {
                 const int kk = off + k;
                 const size_t b = st_idx(d, kk, 0, i);
                 double dx[14], u[4], y[4], xn[14];
+                const double* sg = stage + (k & 1) * RO_STAGE;
+                __pipeline_wait_prior(0);
+                __syncwarp(grp);
+                if (k + 1 < N - 1) stage_knot<14>(d, kk + 1, i, w, n_used, stage + ((k & 1) ^ 1) * RO_STAGE);
 #pragma unroll
-                for (int e = 0; e < 14; ++e) { act[b + e * es] = x[e]; dx[e] = x[e] - d.st_nom[b + e * es]; }
+                for (int e = 0; e < 14; ++e) { act[b + e * es] = x[e]; dx[e] = x[e] - sg[RO_X + e]; }
                 // u = u_nom + eps*du + K (x - x_nom)   (SinglePhase.cpp:76)
 #pragma unroll
                 for (int r = 0; r < 4; ++r) {
-                    double s = d.Kfb[((size_t)kk * KDIM + r) * es + i] * dx[0];
+                    double s = sg[RO_K + r] * dx[0];
 #pragma unroll
-                    for (int e = 1; e < 14; ++e) s += d.Kfb[((size_t)kk * KDIM + r + 4 * e) * es + i] * dx[e];
-                    u[r] = (d.st_nom[b + (14 + r) * es] + eps * d.dufb[((size_t)kk * 4 + r) * es + i]) + s;
+                    for (int e = 1; e < 14; ++e) s += sg[RO_K + r + 4 * e] * dx[e];
+                    u[r] = (sg[RO_U + r] + eps * sg[RO_DU + r]) + s;
                 }
                 wb_step(mode, dt, x, u, xn, y);
 #pragma unroll
                 for (int r = 0; r < 4; ++r) { act[b + (14 + r) * es] = u[r]; act[b + (18 + r) * es] = y[r]; }
-                V += wb_running_cost(c, mode, dt, x, u, y, d.pos_ref[(size_t)kk * es + i], vel, height, reb, par);
+                V += wb_running_cost(c, mode, dt, x, u, y, sg[RO_POS], vel, height, reb, par);
 #pragma unroll
                 for (int e = 0; e < 14; ++e) x[e] = xn[e];
             }
@@ -106,23 +138,29 @@ __global__ void __launch_bounds__(128) k_rollout(Dev d, Consts c, Opt opt, int m
             const double dt = d.dt_fb[i];
             double fh[4];
             rb_foothold(c, mode, x, dt * (double)N, fh);
+            __syncwarp(grp);
+            if (N > 1) stage_knot<6>(d, off, i, w, n_used, stage);
             for (int k = 0; k < N - 1; ++k) {
                 const int kk = off + k;
                 const size_t b = st_idx(d, kk, 0, i);
                 double dx[6], u[4], xn[6];
+                const double* sg = stage + (k & 1) * RO_STAGE;
+                __pipeline_wait_prior(0);
+                __syncwarp(grp);
+                if (k + 1 < N - 1) stage_knot<6>(d, kk + 1, i, w, n_used, stage + ((k & 1) ^ 1) * RO_STAGE);
 #pragma unroll
-                for (int e = 0; e < 6; ++e) { act[b + e * es] = x[e]; dx[e] = x[e] - d.st_nom[b + e * es]; }
+                for (int e = 0; e < 6; ++e) { act[b + e * es] = x[e]; dx[e] = x[e] - sg[RO_X + e]; }
 #pragma unroll
                 for (int r = 0; r < 4; ++r) {
-                    double s = d.Kfb[((size_t)kk * KDIM + r) * es + i] * dx[0];
+                    double s = sg[RO_K + r] * dx[0];
 #pragma unroll
-                    for (int e = 1; e < 6; ++e) s += d.Kfb[((size_t)kk * KDIM + r + 4 * e) * es + i] * dx[e];
-                    u[r] = (d.st_nom[b + (14 + r) * es] + eps * d.dufb[((size_t)kk * 4 + r) * es + i]) + s;
+                    for (int e = 1; e < 6; ++e) s += sg[RO_K + r + 4 * e] * dx[e];
+                    u[r] = (sg[RO_U + r] + eps * sg[RO_DU + r]) + s;
                 }
                 rb_step(mode, dt, x, u, fh, xn);
 #pragma unroll
                 for (int r = 0; r < 4; ++r) { act[b + (14 + r) * es] = u[r]; act[b + (18 + r) * es] = 0.0; }
-                V += rb_running_cost(c, mode, dt, x, u, d.pos_ref[(size_t)kk * es + i], vel, height);
+                V += rb_running_cost(c, mode, dt, x, u, sg[RO_POS], vel, height);
 #pragma unroll
                 for (int e = 0; e < 6; ++e) x[e] = xn[e];
             }
@@ -149,9 +187,17 @@ __global__ void __launch_bounds__(128) k_rollout(Dev d, Consts c, Opt opt, int m
 }
 
 void launch_rollout(const Dev& d, const Consts& c, const Opt& opt, int mask_mode, int n_slots, int trial0, const EpsList& eps, cudaStream_t s) {
-    const int threads = 128;
-    const long total = (long)n_slots * d.npad;
-    k_rollout<<<(unsigned)((total + threads - 1) / threads), threads, 0, s>>>(d, c, opt, mask_mode, n_slots, trial0, eps);
+    // slots per launch rounded up to a power of two (unused slots return at once); at most 32 instances (40 KB of staging)
+    // per block: 128-thread blocks for the line search, one warp per block for single-slot sweeps so that their 4096
+    // threads spread over all SMs
+    int ns = 1;
+    while (ns < n_slots) ns *= 2;
+    if (ns > 32) ns = 32;
+    const int threads = std::min(128, 32 * ns);
+    const int inst_per_block = threads / ns;
+    const size_t smem = (size_t)inst_per_block * 2 * RO_STAGE * sizeof(double);
+    const unsigned blocks = (unsigned)((d.npad + inst_per_block - 1) / inst_per_block);
+    k_rollout<<<blocks, threads, smem, s>>>(d, c, opt, mask_mode, ns, n_slots, trial0, eps);
 }
 
 }  // namespace mhpc
