@@ -289,28 +289,51 @@ def main():
         except Exception:
             pass
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-        lin_tflops = LIN_FLOP_PER_INSTANCE * n / (lin_ms * 1e-3) / 1e12
-        bws_gbs = BWS_BYTES_PER_INSTANCE * n / (bws_ms * 1e-3) / 1e9
-        n_bs_knots = 79                                   # back-stance step knots per default horizon (phase 0)
-        bs_flop = BS_FLOP_PER_KNOT * n_bs_knots * n       # 27 569 flop per WB-stance knot
-        bs_tflops = bs_flop / (lin_bs_ms * 1e-3) / 1e12
-        traffic = None
-        try:   # dram bytes of ONE k_lin<BS> launch at this batch size from the committed ncu --set full capture
-            prof = json.load(open(os.path.join(ROOT, "profiles", "r1_lin_bs_ncu_traffic.json")))
-            if prof.get("instances") == n:
-                traffic = prof["dram_bytes_per_launch"]
+        # flops the device forms actually execute (the Jacobians are re-derived by implicit differentiation,
+        # codegen/implicit.py: ~5x fewer operations than the reference's flat CasADi DAGs that SURVEY.md 8(d) counts)
+        exe = {}
+        try:
+            exe = json.load(open(os.path.join(ROOT, "mhpc_minimal_env_b200", "csrc", "gen", "gen_meta.json")))["_regalloc"]["device_flops"]
         except Exception:
             pass
-        roofline = {"kernel": "k_lin<BS> (Dyn_BS_par + Euler A,B + cost/barrier partials, 79 back-stance knots x instances)",
-                    "bound": "fp64", "achieved": bs_tflops, "peak": fp64_peak, "unit": "TFLOP/s", "frac": bs_tflops / fp64_peak,
-                    "traffic": traffic, "algorithmic_bytes": 1352.0 * n_bs_knots * n, "ms_per_launch": lin_bs_ms,
-                    "peak_source": "FP64 FMA probe measured live on this GPU (MEASURED_PEAKS.json has no FP64 entry)"}
+        n_bs_knots = 79                                   # back-stance step knots per default horizon (phase 0)
+        wb_cost_flop = 150.0                              # running-cost / barrier partials of a WB step knot
+        exe_bs = (exe.get("Dyn_BS_par", 4880) + wb_cost_flop) * n_bs_knots * n
+        exe_lin = n * (79 * (exe.get("Dyn_BS_par", 4880) + wb_cost_flop) + 79 * (exe.get("Dyn_FS_par", 4880) + wb_cost_flop)
+                       + 198 * (exe.get("Dyn_FL_par", 3710) + wb_cost_flop) + exe.get("Imp_F_par", 15166) + exe.get("Imp_B_par", 15166)
+                       + 352 * (exe.get("FBDynamics_par", 27) + 60.0))
+        lin_tflops = LIN_FLOP_PER_INSTANCE * n / (lin_ms * 1e-3) / 1e12
+        bws_gbs = BWS_BYTES_PER_INSTANCE * n / (bws_ms * 1e-3) / 1e9
+        bs_flop = BS_FLOP_PER_KNOT * n_bs_knots * n       # 27 569 flop per WB-stance knot (reference formulation)
+        bs_tflops = bs_flop / (lin_bs_ms * 1e-3) / 1e12
+
+        def ncu_traffic(name):   # dram bytes of ONE launch at this batch size from the committed ncu --set full capture
+            try:
+                prof = json.load(open(os.path.join(ROOT, "profiles", name)))
+                if prof.get("instances") == n:
+                    return prof["dram_bytes_per_launch"]
+            except Exception:
+                pass
+            return None
+        # the dominant kernel of a step is the backward sweep (stage_ms below); it moves its algorithmic bytes once (ncu
+        # traffic <= algorithmic) and is bound by the 712 dependent Riccati steps, not by bandwidth
+        roofline = {"kernel": "k_bws (impact-aware Riccati sweep over 712 knots, one attempt, all instances)", "bound": "hbm",
+                    "achieved": bws_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": bws_gbs / hbm_peak,
+                    "traffic": ncu_traffic("r1_bws_ncu_traffic.json"), "algorithmic_bytes": BWS_BYTES_PER_INSTANCE * n,
+                    "ms_per_launch": bws_ms, "us_per_knot": 1e3 * bws_ms / 712,
+                    "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
+                    "note": "latency-bound: 712 sequential knots x ~4.9 us; ncu: FP64 pipe 26 %, issue slots 32 %, 1.7 warps/scheduler at 4096 instances"}
+        roofline_lin_bs = {"kernel": "k_lin<BS> (Dyn_BS_par + Euler A,B + cost/barrier partials, 79 back-stance knots x instances)",
+                           "bound": "fp64", "achieved": bs_tflops, "peak": fp64_peak, "unit": "TFLOP/s", "frac": bs_tflops / fp64_peak,
+                           "executed_tflops": exe_bs / (lin_bs_ms * 1e-3) / 1e12, "executed_frac": exe_bs / (lin_bs_ms * 1e-3) / 1e12 / fp64_peak,
+                           "traffic": ncu_traffic("r1_lin_bs_ncu_traffic.json"), "algorithmic_bytes": 1352.0 * n_bs_knots * n,
+                           "hbm_frac_algorithmic": 1352.0 * n_bs_knots * n / (lin_bs_ms * 1e-3) / 1e9 / hbm_peak, "ms_per_launch": lin_bs_ms,
+                           "peak_source": "FP64 FMA probe measured live on this GPU (MEASURED_PEAKS.json has no FP64 entry)",
+                           "note": "achieved counts the reference formulation's flops (SURVEY.md 8(d)); executed_* counts what the re-derived Jacobian runs"}
         roofline_lin_group = {"kernel": "linearisation launch group (k_lin<BS,FS,FL,IMPF,IMPB,light>)", "bound": "fp64",
                               "achieved": lin_tflops, "peak": fp64_peak, "unit": "TFLOP/s", "frac": lin_tflops / fp64_peak,
+                              "executed_tflops": exe_lin / (lin_ms * 1e-3) / 1e12, "executed_frac": exe_lin / (lin_ms * 1e-3) / 1e12 / fp64_peak,
                               "ms_per_launch": lin_ms, "us_per_horizon_linearize": 1e3 * lin_ms / n}
-        roofline_bws = {"kernel": "k_bws (impact-aware Riccati sweep, one attempt)", "bound": "hbm", "achieved": bws_gbs, "peak": hbm_peak,
-                        "unit": "GB/s", "frac": bws_gbs / hbm_peak, "traffic": None, "ms_per_launch": bws_ms,
-                        "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s"}
         cpu_v = cpu_baseline_single(args.cpu_sample)
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
@@ -322,7 +345,7 @@ def main():
                         "note": f"mhpc_batch_solve_host: pinned host problems in, results + first {ek} knots of x,u,y,K,du out"},
                 "gpu_launches": int(tm["n_launches"] + 3) * args.steps,
                 "clocks": sampler.summary(),
-                "roofline": roofline, "roofline_lin_group": roofline_lin_group, "roofline_bws": roofline_bws,
+                "roofline": roofline, "roofline_lin_bs": roofline_lin_bs, "roofline_lin_group": roofline_lin_group,
                 "stage_ms": {k: tm[k] for k in ("total_ms", "rollout_ms", "linearize_ms", "bws_ms", "linesearch_ms", "other_ms")},
                 "cpu_baseline": {"value": cpu_v, "unit": UNIT, "cores": 1, "kind": _cpu_kind(),
                                  "sample": f"first {args.cpu_sample} instances of the workload, reference sources (-O3 -mavx2 -mfma, Eigen stand-in), one core; "

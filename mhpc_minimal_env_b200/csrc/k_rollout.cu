@@ -38,6 +38,7 @@ __device__ __forceinline__ void stage_knot(const Dev& d, int kk, int i, int w, i
     __pipeline_commit();
 }
 
+template <bool STAGED>   // STAGED: the trials of an instance share a lane group that streams the knot data through shared memory
 __global__ void __launch_bounds__(128) k_rollout(Dev d, Consts c, Opt opt, int mask_mode, int n_slots, int n_used, int trial0, EpsList eps_list) {
     extern __shared__ __align__(16) double ro_smem[];
     const int tid = blockIdx.x * blockDim.x + threadIdx.x;
@@ -70,30 +71,39 @@ __global__ void __launch_bounds__(128) k_rollout(Dev d, Consts c, Opt opt, int m
             double par[6];
 #pragma unroll
             for (int q = 0; q < 6; ++q) par[q] = d.par[par_idx(d, p, PAR_DELTA_T + q, i)];
-            __syncwarp(grp);
-            if (N > 1) stage_knot<14>(d, off, i, w, n_used, stage);
+            if (STAGED) {
+                __syncwarp(grp);
+                if (N > 1) stage_knot<14>(d, off, i, w, n_used, stage);
+            }
             for (int k = 0; k < N - 1; ++k) {
                 const int kk = off + k;
                 const size_t b = st_idx(d, kk, 0, i);
                 double dx[14], u[4], y[4], xn[14];
                 const double* sg = stage + (k & 1) * RO_STAGE;
-                __pipeline_wait_prior(0);
-                __syncwarp(grp);
-                if (k + 1 < N - 1) stage_knot<14>(d, kk + 1, i, w, n_used, stage + ((k & 1) ^ 1) * RO_STAGE);
+                if (STAGED) {
+                    __pipeline_wait_prior(0);
+                    __syncwarp(grp);
+                    if (k + 1 < N - 1) stage_knot<14>(d, kk + 1, i, w, n_used, stage + ((k & 1) ^ 1) * RO_STAGE);
+                }
+#define RO_NOM(e) (STAGED ? sg[RO_X + (e)] : d.st_nom[b + (size_t)(e) * es])
+#define RO_UNOM(r) (STAGED ? sg[RO_U + (r)] : d.st_nom[b + (size_t)(14 + (r)) * es])
+#define RO_KF(q) (STAGED ? sg[RO_K + (q)] : d.Kfb[((size_t)kk * KDIM + (q)) * es + i])
+#define RO_DUF(r) (STAGED ? sg[RO_DU + (r)] : d.dufb[((size_t)kk * 4 + (r)) * es + i])
+#define RO_PREF() (STAGED ? sg[RO_POS] : d.pos_ref[(size_t)kk * es + i])
 #pragma unroll
-                for (int e = 0; e < 14; ++e) { act[b + e * es] = x[e]; dx[e] = x[e] - sg[RO_X + e]; }
+                for (int e = 0; e < 14; ++e) { act[b + e * es] = x[e]; dx[e] = x[e] - RO_NOM(e); }
                 // u = u_nom + eps*du + K (x - x_nom)   (SinglePhase.cpp:76)
 #pragma unroll
                 for (int r = 0; r < 4; ++r) {
-                    double s = sg[RO_K + r] * dx[0];
+                    double s = RO_KF(r) * dx[0];
 #pragma unroll
-                    for (int e = 1; e < 14; ++e) s += sg[RO_K + r + 4 * e] * dx[e];
-                    u[r] = (sg[RO_U + r] + eps * sg[RO_DU + r]) + s;
+                    for (int e = 1; e < 14; ++e) s += RO_KF(r + 4 * e) * dx[e];
+                    u[r] = (RO_UNOM(r) + eps * RO_DUF(r)) + s;
                 }
                 wb_step(mode, dt, x, u, xn, y);
 #pragma unroll
                 for (int r = 0; r < 4; ++r) { act[b + (14 + r) * es] = u[r]; act[b + (18 + r) * es] = y[r]; }
-                V += wb_running_cost(c, mode, dt, x, u, y, sg[RO_POS], vel, height, reb, par);
+                V += wb_running_cost(c, mode, dt, x, u, y, RO_PREF(), vel, height, reb, par);
 #pragma unroll
                 for (int e = 0; e < 14; ++e) x[e] = xn[e];
             }
@@ -138,29 +148,33 @@ __global__ void __launch_bounds__(128) k_rollout(Dev d, Consts c, Opt opt, int m
             const double dt = d.dt_fb[i];
             double fh[4];
             rb_foothold(c, mode, x, dt * (double)N, fh);
-            __syncwarp(grp);
-            if (N > 1) stage_knot<6>(d, off, i, w, n_used, stage);
+            if (STAGED) {
+                __syncwarp(grp);
+                if (N > 1) stage_knot<6>(d, off, i, w, n_used, stage);
+            }
             for (int k = 0; k < N - 1; ++k) {
                 const int kk = off + k;
                 const size_t b = st_idx(d, kk, 0, i);
                 double dx[6], u[4], xn[6];
                 const double* sg = stage + (k & 1) * RO_STAGE;
-                __pipeline_wait_prior(0);
-                __syncwarp(grp);
-                if (k + 1 < N - 1) stage_knot<6>(d, kk + 1, i, w, n_used, stage + ((k & 1) ^ 1) * RO_STAGE);
+                if (STAGED) {
+                    __pipeline_wait_prior(0);
+                    __syncwarp(grp);
+                    if (k + 1 < N - 1) stage_knot<6>(d, kk + 1, i, w, n_used, stage + ((k & 1) ^ 1) * RO_STAGE);
+                }
 #pragma unroll
-                for (int e = 0; e < 6; ++e) { act[b + e * es] = x[e]; dx[e] = x[e] - sg[RO_X + e]; }
+                for (int e = 0; e < 6; ++e) { act[b + e * es] = x[e]; dx[e] = x[e] - RO_NOM(e); }
 #pragma unroll
                 for (int r = 0; r < 4; ++r) {
-                    double s = sg[RO_K + r] * dx[0];
+                    double s = RO_KF(r) * dx[0];
 #pragma unroll
-                    for (int e = 1; e < 6; ++e) s += sg[RO_K + r + 4 * e] * dx[e];
-                    u[r] = (sg[RO_U + r] + eps * sg[RO_DU + r]) + s;
+                    for (int e = 1; e < 6; ++e) s += RO_KF(r + 4 * e) * dx[e];
+                    u[r] = (RO_UNOM(r) + eps * RO_DUF(r)) + s;
                 }
                 rb_step(mode, dt, x, u, fh, xn);
 #pragma unroll
                 for (int r = 0; r < 4; ++r) { act[b + (14 + r) * es] = u[r]; act[b + (18 + r) * es] = 0.0; }
-                V += rb_running_cost(c, mode, dt, x, u, sg[RO_POS], vel, height);
+                V += rb_running_cost(c, mode, dt, x, u, RO_PREF(), vel, height);
 #pragma unroll
                 for (int e = 0; e < 6; ++e) x[e] = xn[e];
             }
@@ -186,6 +200,12 @@ __global__ void __launch_bounds__(128) k_rollout(Dev d, Consts c, Opt opt, int m
     d.tr_viol2[(size_t)w * es + i] = viol2;
 }
 
+#undef RO_NOM
+#undef RO_UNOM
+#undef RO_KF
+#undef RO_DUF
+#undef RO_PREF
+
 void launch_rollout(const Dev& d, const Consts& c, const Opt& opt, int mask_mode, int n_slots, int trial0, const EpsList& eps, cudaStream_t s) {
     // slots per launch rounded up to a power of two (unused slots return at once); at most 32 instances (40 KB of staging)
     // per block: 128-thread blocks for the line search, one warp per block for single-slot sweeps so that their 4096
@@ -195,9 +215,13 @@ void launch_rollout(const Dev& d, const Consts& c, const Opt& opt, int mask_mode
     if (ns > 32) ns = 32;
     const int threads = std::min(128, 32 * ns);
     const int inst_per_block = threads / ns;
-    const size_t smem = (size_t)inst_per_block * 2 * RO_STAGE * sizeof(double);
     const unsigned blocks = (unsigned)((d.npad + inst_per_block - 1) / inst_per_block);
-    k_rollout<<<blocks, threads, smem, s>>>(d, c, opt, mask_mode, ns, n_slots, trial0, eps);
+    if (n_slots > 1) {
+        const size_t smem = (size_t)inst_per_block * 2 * RO_STAGE * sizeof(double);
+        k_rollout<true><<<blocks, threads, smem, s>>>(d, c, opt, mask_mode, ns, n_slots, trial0, eps);
+    } else {   // one trial per instance: nothing to share, every lane reads its own instance in place
+        k_rollout<false><<<blocks, threads, 0, s>>>(d, c, opt, mask_mode, ns, n_slots, trial0, eps);
+    }
 }
 
 }  // namespace mhpc

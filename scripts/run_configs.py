@@ -9,7 +9,7 @@ from helpers import make_specs, to_gpu_problem
 
 rows = []
 for name, cfg, n in (("config2 (1024, default split)", 2, 1024), ("config2 at 4096", 2, 4096), ("config3 (4096, all whole-body)", 3, 4096),
-                     ("config4 (4096, varied splits/timings, 8-way line search)", 4, 4096), ("config5 (32768 on ONE GPU)", 2, 32768)):
+                     ("config4 (4096, varied splits/timings, 8-way line search)", 4, 4096), ("config2 at 16384", 2, 16384), ("config5 (32768 on ONE GPU)", 2, 32768)):
     t0 = time.time()
     probs = [to_gpu_problem(s) for s in make_specs(n, cfg)]
     for label, kw in (("default thresholds", {}), ("fixed 2x3", dict(DDP_thresh=-1.0, AL_thresh=-1.0))):
