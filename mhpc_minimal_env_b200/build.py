@@ -29,7 +29,8 @@ FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xptxas", "-v
 # resident 128-thread blocks per SM the Jacobian kernels are compiled for (register cap = 65536 / (128 * LIN_MINBLOCKS))
 LIN_MINBLOCKS = int(os.environ.get("MHPC_LIN_MINBLOCKS", "2"))
 
-LIN_EXTRA = os.environ.get("MHPC_LIN_EXTRA", "").split()   # dev: extra nvcc flags for the Jacobian kernel classes
+LIN_EXTRA = os.environ.get("MHPC_LIN_EXTRA", "").split()
+BWS_EXTRA = os.environ.get("MHPC_BWS_EXTRA", "").split()   # dev: extra nvcc flags for the backward sweep   # dev: extra nvcc flags for the Jacobian kernel classes
 FL_OPT = os.environ.get("MHPC_LIN_FL_OPT", "O1")          # ptxas level for the flight-knot Jacobian (12 k nodes)
 FL_MINBLOCKS = int(os.environ.get("MHPC_LIN_FL_MINBLOCKS", str(LIN_MINBLOCKS)))
 
@@ -44,7 +45,7 @@ def _lin_flags(c):
 
 # (source, object name, extra defines)
 UNITS = [("capi.cu", "capi.o", []), ("k_misc.cu", "k_misc.o", []), ("k_rollout.cu", "k_rollout.o", []),
-         ("k_bws.cu", "k_bws.o", []), ("k_eval.cu", "k_eval.o", [])] + \
+         ("k_bws.cu", "k_bws.o", BWS_EXTRA), ("k_eval.cu", "k_eval.o", [])] + \
         [("k_lin.cu", f"k_lin_{c}.o", [f"-DLIN_CLS={c}"] + _lin_flags(c)) for c in range(6)]
 # ptxas -O3 degenerates on the 26k-node Jacobian bodies (32 registers, ~100 KB of spill stores per thread);
 # at -O1 it keeps the generator's instruction order and allocates 255 registers (~24 KB of spill stores).
@@ -90,7 +91,7 @@ def build(ref: str = "/root/reference", force: bool = False, verbose: bool = Tru
     srcs += [os.path.join(GEN, f) for f in os.listdir(GEN) if f.endswith(".inc")]
     srcs += [os.path.join(HERE, "..", "include", "mhpc_b200.h"), os.path.abspath(__file__)]
     stamp = os.path.join(OBJ, "stamp.txt")
-    dig = _digest(srcs) + f":mb{LIN_MINBLOCKS}:{FL_OPT}:{FL_MINBLOCKS}:{os.environ.get('MHPC_RA_CAP', '')}:{os.environ.get('MHPC_RA_LOOKAHEAD', '')}:{os.environ.get('MHPC_RA_WINDOW', '')}:{os.environ.get('MHPC_SHARE_RCP', '')}:{os.environ.get('MHPC_RA_SMEM', '')}:{os.environ.get('MHPC_RA_FAR', '')}:{os.environ.get('MHPC_LIN_EXTRA', '')}"
+    dig = _digest(srcs) + f":mb{LIN_MINBLOCKS}:{FL_OPT}:{FL_MINBLOCKS}:{os.environ.get('MHPC_RA_CAP', '')}:{os.environ.get('MHPC_RA_LOOKAHEAD', '')}:{os.environ.get('MHPC_RA_WINDOW', '')}:{os.environ.get('MHPC_SHARE_RCP', '')}:{os.environ.get('MHPC_RA_SMEM', '')}:{os.environ.get('MHPC_RA_FAR', '')}:{os.environ.get('MHPC_LIN_EXTRA', '')}:{os.environ.get('MHPC_BWS_EXTRA', '')}"
     if not force and os.path.exists(LIB) and os.path.exists(stamp) and open(stamp).read() == dig:
         if verbose:
             print(f"[build] up to date: {LIB}")

@@ -66,6 +66,8 @@ def _statements(fn: SXFunction, order: Optional[List[int]] = None,
             out.append(f"const double {v} = SX_IN({nd.arg}, {nd.idx});")
         elif nd.op == CONST:
             out.append(f"const double {v} = {nd.lit};")
+        elif nd.op == DIV and nodes[nd.a].op == CONST and nodes[nd.a].val == 1.0 and nodes[nd.b].op != CONST:
+            out.append(f"const double {v} = SX_RCP(v{nd.b});")      # reciprocal of a pivot: the includer picks the sequence
         elif nd.op in _BIN:
             out.append(f"const double {v} = v{nd.a} {_BIN[nd.op]} v{nd.b};")
         elif nd.op == NEG:
@@ -109,10 +111,12 @@ def emit_c(fn: SXFunction, symbol: str, order: Optional[List[int]] = None) -> st
         "#include <math.h>",
         "#define SX_IN(i, j) (arg[i][j])",
         "#define SX_OUT(k, nz, row, col, v) res[k][nz] = (v)",
+        "#define SX_RCP(x) (1.0 / (x))",
         f"void {symbol}(const double** arg, double** res) {{",
         *("  " + s for s in body),
         "}",
         "#undef SX_IN",
         "#undef SX_OUT",
+        "#undef SX_RCP",
         "",
     ])

@@ -339,6 +339,8 @@ def allocate(fn: SXFunction, cap: int = 104, lookahead: int = 48, window: int = 
             out.append(f"SX_SINCOS({a}, r{reg_of[s_id]}, r{reg_of[c_id]});")
         elif nd.op == IN:
             out.append(f"r{dests[0][1]} = SX_IN({nd.arg}, {nd.idx});")
+        elif nd.op == DIV and is_const[nd.a] and nodes[nd.a].val == 1.0 and not is_const[nd.b]:
+            out.append(f"r{dests[0][1]} = SX_RCP({b});")
         elif nd.op in _BIN:
             out.append(f"r{dests[0][1]} = {a} {_BIN[nd.op]} {b};")
         elif nd.op == NEG:
@@ -389,7 +391,8 @@ def emit_c_regalloc(fn: SXFunction, symbol: str, cap: int = 104, lookahead: int 
         "#define SX_OUT4(e0, k0, n0, r0, c0, v0, k1, n1, r1, c1, v1, k2, n2, r2, c2, v2, k3, n3, r3, c3, v3) "
         "do { res[k0][n0] = (v0); res[k1][n1] = (v1); res[k2][n2] = (v2); res[k3][n3] = (v3); } while (0)",
         "#define SX_SINCOS(a, s, c) do { const double t_ = (a); (s) = sin(t_); (c) = cos(t_); } while (0)",
+        "#define SX_RCP(x) (1.0 / (x))",
         *("  " + s for s in body),
-        "#undef SX_IN", "#undef SX_OUT", "#undef SX_OUT4", "#undef SX_SINCOS", "#undef SX_SMEM",
+        "#undef SX_IN", "#undef SX_OUT", "#undef SX_OUT4", "#undef SX_SINCOS", "#undef SX_RCP", "#undef SX_SMEM",
         "}", "",
     ])

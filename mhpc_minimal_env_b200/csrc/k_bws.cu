@@ -608,8 +608,8 @@ __global__ void __launch_bounds__(BWS_THREADS, BWS_MINBLOCKS) k_bws(Dev d, Const
                 double ka[4], kb[4], du[4], goa = 0.0, gob = 0.0, dvs = 0.0;
                 __syncwarp();
                 const bool ok = value_update<14, true>(on, rw, m, scr, quxa, quxb, qxa, qxb, Ha, Hb, opt.quu_shift, ka, kb, du, goa, gob, dvs);
-                __syncwarp();
-                if (on) {
+                if (on) {   // (no hand-over needed here or after the stores: S_G is not read by value_update, and the next reader
+                            //  of anything written below sits behind the __syncwarp at the top of the knot loop)
                     if (!ok) failed = true;
                     else {
                         dV += dvs;
@@ -626,7 +626,6 @@ __global__ void __launch_bounds__(BWS_THREADS, BWS_MINBLOCKS) k_bws(Dev d, Const
                         if (m < 4) du_lane[(size_t)kk * du_knot] = du[m];
                     }
                 }
-                __syncwarp();
             }
 
             // ============ rigid-body step ============
@@ -722,7 +721,6 @@ __global__ void __launch_bounds__(BWS_THREADS, BWS_MINBLOCKS) k_bws(Dev d, Const
                         if (m < 4) du_lane[(size_t)kk * du_knot] = du[m];
                     }
                 }
-                __syncwarp();
             }
 #undef RBUF
             if (enabled && it < nk) walk_step(wk);

@@ -132,12 +132,17 @@ __global__ void k_copy_nominal(Dev d, int mask_mode) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= d.n) return;
     if (!inst_enabled(d, i, mask_mode)) return;
-    const int row = blockIdx.y;   // kk * ST + e
-    const int kk = row / ST;
+    const int kk = blockIdx.y;    // one knot (22 rows of the SoA trajectory) per thread: the index work is done once
     int p, k;
     if (!knot_to_phase(d, i, kk, p, k)) return;   // memcpy of N_p knots per phase (SinglePhase.cpp:358-361)
     const int slot = SI(SI_ACC_SLOT);
-    d.st_nom[(size_t)row * d.npad + i] = d.st_act[((size_t)slot * d.KT * ST + row) * d.npad + i];
+    const double* __restrict__ src = d.st_act + ((size_t)slot * d.KT + kk) * ST * d.npad + i;
+    double* __restrict__ dst = d.st_nom + (size_t)kk * ST * d.npad + i;
+    double v[ST];
+#pragma unroll
+    for (int e = 0; e < ST; ++e) v[e] = src[(size_t)e * d.npad];
+#pragma unroll
+    for (int e = 0; e < ST; ++e) dst[(size_t)e * d.npad] = v[e];
 }
 
 __global__ void k_accept_slot0(Dev d, int mask_mode, int lin_mode) {
@@ -356,7 +361,7 @@ static inline unsigned nb(int n, int t) { return (unsigned)((n + t - 1) / t); }
 void launch_setup(const Dev& d, const Consts& c, cudaStream_t s) { k_setup<<<nb(d.n, 128), 128, 0, s>>>(d, c); }
 void launch_warmstart(const Dev& d, const Consts& c, cudaStream_t s) { k_warmstart<<<nb(d.n, 128), 128, 0, s>>>(d, c); }
 void launch_copy_nominal(const Dev& d, int mask_mode, cudaStream_t s) {
-    dim3 grid(nb(d.n, 128), d.KT * ST);
+    dim3 grid(nb(d.n, 128), d.KT);
     k_copy_nominal<<<grid, 128, 0, s>>>(d, mask_mode);
 }
 void launch_accept_slot0(const Dev& d, int mask_mode, int lin_mode, cudaStream_t s) { k_accept_slot0<<<nb(d.n, 128), 128, 0, s>>>(d, mask_mode, lin_mode); }

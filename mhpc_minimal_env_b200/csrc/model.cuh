@@ -27,6 +27,23 @@ struct Consts {
 };
 
 #define SX_SINCOS(a, s, c) sincos((a), &(s), &(c))
+// Reciprocal of a factorisation pivot (codegen emits SX_RCP for every 1/d node).  `1.0 / d` is a ~127-cycle dependent
+// sequence on this GPU (range checks, slow-path branch; scripts/micro/fp64_lat.cu) and the dynamics have nine of them in
+// a row; the pivots are ordinary well-scaled numbers, so the hardware seed (~20 bits) plus two Newton steps (error
+// <= 2 ulp, ~60 cycles) is enough.  MHPC_EXACT_RCP restores the IEEE division.
+#ifdef MHPC_EXACT_RCP
+#define SX_RCP(x) (1.0 / (x))
+#else
+static __device__ __forceinline__ double sx_rcp(double x) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    double e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-x, r, 1.0);
+    return fma(r, e, r);
+}
+#define SX_RCP(x) sx_rcp(x)
+#endif
 
 // ---- whole-body continuous dynamics  xdot(14), y(4) --------------------------------------
 #define SX_IN(i, j) ((i) == 0 ? x[j] : u[j])
