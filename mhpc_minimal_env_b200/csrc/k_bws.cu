@@ -95,7 +95,11 @@ __device__ __forceinline__ bool ldlt4_is_positive(const double q[4][4]) {
         if (k == 0 && !valid && !result_known) { result_known = true; result = true; }
         if (valid) {
             // one reciprocal per pivot instead of a division per entry (<= 1 ulp on L; only the SIGNS of the pivots are used)
+#ifdef BWS_EXACT_DIV
             const double rk = 1.0 / akk;
+#else
+            const double rk = sx_rcp(akk);
+#endif
 #pragma unroll
             for (int i = k + 1; i < 4; ++i) a[i][k] *= rk;
         }
@@ -142,13 +146,20 @@ __device__ __forceinline__ bool value_update(bool on, bool rows, int m, double* 
         double det = QM(0, 0) * scr[S_ADJ + 0 + 4 * 0];
 #pragma unroll
         for (int i = 1; i < 4; ++i) det += QM(i, 0) * scr[S_ADJ + 0 + 4 * i];
-        // adj / det; a zero numerator (every off-diagonal entry in the rigid-body phases) would send the FP64 division
-        // through its slow path (quotient below the fast path's range check): 0 * det has the same value and sign
+        // adj / det as adj * (1/det) with the Newton-refined hardware reciprocal (model.cuh: sx_rcp, <= 2 ulp): an IEEE
+        // division is a ~127-cycle dependent sequence on the critical path of every knot.  -DBWS_EXACT_DIV restores it (a
+        // zero numerator - every off-diagonal entry in the rigid-body phases - then takes adj * det, which has the same
+        // value and sign, instead of the division's slow path).
+        const double rdet = sx_rcp(det);
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
             const int l = m + 8 * h;
             const double adj = scr[S_ADJ + l];
+#ifdef BWS_EXACT_DIV
             scr[S_INV + l] = (adj == 0.0) ? adj * det : adj / det;
+#else
+            scr[S_INV + l] = adj * rdet;
+#endif
         }
     }
 #undef QM
