@@ -182,8 +182,19 @@ def main():
     torch.cuda.set_device(local)
     dist = None
     if world > 1:
+        # stdout carries exactly one JSON line: keep NCCL's version banner (NCCL_DEBUG=VERSION/INFO write it to stdout) out of it
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO", "TRACE") and "NCCL_DEBUG_FILE" not in os.environ:
+            os.environ["NCCL_DEBUG_FILE"] = "/dev/stderr"
         import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        saved_stdout = os.dup(1)          # ... and anything else the communicator set-up prints goes to stderr as well
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+            dist.barrier()                # creates the communicator now, not inside the timed region
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_stdout, 1)
+            os.close(saved_stdout)
 
     from mhpc_minimal_env_b200.sharding import gather_result_table, shard_range
     n = args.instances
