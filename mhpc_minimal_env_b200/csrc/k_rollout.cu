@@ -18,27 +18,43 @@ namespace mhpc {
 // addresses known in advance; the trajectories and gains of a batch (GBs) do not stay in L2 between kernels, so read in
 // place each step exposes several dependent DRAM/L2 round trips (ncu: 54 % of the warp time on the long scoreboard).
 // The lanes that hold the trials of one instance stream that instance's next knot into shared memory with cp.async, one
-// step ahead of the math (double buffered, synchronised inside the lane group only, so instances with different phase
-// lengths may share a warp).
+// two steps ahead of the math (three-deep ring, synchronised inside the lane group only, so instances with different
+// phase lengths may share a warp).
 constexpr int RO_X = 0, RO_U = 14, RO_K = 18, RO_DU = 74, RO_POS = 78, RO_STAGE = 80;
 
-template <int NXP>   // 14 whole-body, 6 rigid-body
-__device__ __forceinline__ void stage_knot(const Dev& d, int kk, int i, int w, int n_lanes, double* dst) {
-    const size_t es = d.npad;
-    const double* sn = d.st_nom + st_idx(d, kk, 0, i);
-    const double* kf = d.Kfb + (size_t)kk * KDIM * es + i;
-    const double* du = d.dufb + (size_t)kk * 4 * es + i;
-    for (int t = w; t < 4 * NXP; t += n_lanes) __pipeline_memcpy_async(dst + RO_K + t, kf + (size_t)t * es, 8);
-    for (int t = w; t < NXP; t += n_lanes) __pipeline_memcpy_async(dst + RO_X + t, sn + (size_t)t * es, 8);
-    for (int t = w; t < 4; t += n_lanes) {
-        __pipeline_memcpy_async(dst + RO_U + t, sn + (size_t)(14 + t) * es, 8);
-        __pipeline_memcpy_async(dst + RO_DU + t, du + (size_t)t * es, 8);
+constexpr int RO_DEPTH = 3;   // ring of staged knots: the copy of knot k+2 is issued while knot k is computed
+
+// NL > 0: the lane-group size is a compile-time constant (the 8-trial line search), so the copy loops unroll into copies at
+// constant multiples of the element stride; NL == 0 takes it from n_lanes.  Always commits one group (possibly empty):
+// the consumer counts groups.
+template <int NXP, int NL>   // NXP: 14 whole-body, 6 rigid-body
+__device__ __forceinline__ void stage_knot(const Dev& d, bool copy, int kk, int i, int w, int n_lanes, double* dst) {
+    if (copy) {
+        const int nl = NL > 0 ? NL : n_lanes;
+        const size_t es = d.npad;
+        const double* sn = d.st_nom + st_idx(d, kk, 0, i) + (size_t)w * es;
+        const double* kf = d.Kfb + ((size_t)kk * KDIM + w) * es + i;
+        double* dw = dst + w;
+#pragma unroll
+        for (int t = 0; t < 4 * NXP; t += (NL > 0 ? NL : 1)) {
+            if (NL > 0) { if (t + w < 4 * NXP) __pipeline_memcpy_async(dw + RO_K + t, kf + (size_t)t * es, 8); }
+            else if (t % nl == 0 && t + w < 4 * NXP) __pipeline_memcpy_async(dw + RO_K + t, kf + (size_t)t * es, 8);
+        }
+#pragma unroll
+        for (int t = 0; t < NXP; t += (NL > 0 ? NL : 1)) {
+            if (NL > 0) { if (t + w < NXP) __pipeline_memcpy_async(dw + RO_X + t, sn + (size_t)t * es, 8); }
+            else if (t % nl == 0 && t + w < NXP) __pipeline_memcpy_async(dw + RO_X + t, sn + (size_t)t * es, 8);
+        }
+        for (int t = w; t < 4; t += nl) {
+            __pipeline_memcpy_async(dst + RO_U + t, d.st_nom + st_idx(d, kk, 14 + t, i), 8);
+            __pipeline_memcpy_async(dst + RO_DU + t, d.dufb + ((size_t)kk * 4 + t) * es + i, 8);
+        }
+        if (w == nl - 1) __pipeline_memcpy_async(dst + RO_POS, d.pos_ref + (size_t)kk * es + i, 8);
     }
-    if (w == n_lanes - 1) __pipeline_memcpy_async(dst + RO_POS, d.pos_ref + (size_t)kk * es + i, 8);
     __pipeline_commit();
 }
 
-template <bool STAGED>   // STAGED: the trials of an instance share a lane group that streams the knot data through shared memory
+template <bool STAGED, int NL>   // STAGED: the trials of an instance share a lane group (NL lanes, 0 = n_used) that streams the knot data through shared memory
 __global__ void __launch_bounds__(128) k_rollout(Dev d, Consts c, Opt opt, int mask_mode, int n_slots, int n_used, int trial0, EpsList eps_list) {
     extern __shared__ __align__(16) double ro_smem[];
     const int tid = blockIdx.x * blockDim.x + threadIdx.x;
@@ -47,7 +63,7 @@ __global__ void __launch_bounds__(128) k_rollout(Dev d, Consts c, Opt opt, int m
     const int w = lane % n_slots;
     const int i = (tid >> 5) * per_warp + lane / n_slots;
     const unsigned grp = (n_used == 32 ? 0xffffffffu : ((1u << n_used) - 1u)) << (lane - w);   // lanes holding the trials of my instance
-    double* stage = ro_smem + (size_t)(threadIdx.x / n_slots) * 2 * RO_STAGE;                // [2][RO_STAGE] of my instance
+    double* stage = ro_smem + (size_t)(threadIdx.x / n_slots) * RO_DEPTH * RO_STAGE;         // [RO_DEPTH][RO_STAGE] of my instance
     if (w >= n_used || i >= d.n) return;
     if (!inst_enabled(d, i, mask_mode)) return;
     if (mask_mode == MASK_LS && d.si[(size_t)SI_LS_DONE * d.npad + i]) return;
@@ -73,17 +89,18 @@ __global__ void __launch_bounds__(128) k_rollout(Dev d, Consts c, Opt opt, int m
             for (int q = 0; q < 6; ++q) par[q] = d.par[par_idx(d, p, PAR_DELTA_T + q, i)];
             if (STAGED) {
                 __syncwarp(grp);
-                if (N > 1) stage_knot<14>(d, off, i, w, n_used, stage);
+                stage_knot<14, NL>(d, 0 < N - 1, off, i, w, n_used, stage);
+                stage_knot<14, NL>(d, 1 < N - 1, off + 1, i, w, n_used, stage + RO_STAGE);
             }
             for (int k = 0; k < N - 1; ++k) {
                 const int kk = off + k;
                 const size_t b = st_idx(d, kk, 0, i);
                 double dx[14], u[4], y[4], xn[14];
-                const double* sg = stage + (k & 1) * RO_STAGE;
+                const double* sg = stage + (k % RO_DEPTH) * RO_STAGE;
                 if (STAGED) {
-                    __pipeline_wait_prior(0);
+                    __pipeline_wait_prior(1);   // everything but the newest group (knot k + 1) has landed
                     __syncwarp(grp);
-                    if (k + 1 < N - 1) stage_knot<14>(d, kk + 1, i, w, n_used, stage + ((k & 1) ^ 1) * RO_STAGE);
+                    stage_knot<14, NL>(d, k + 2 < N - 1, kk + 2, i, w, n_used, stage + ((k + 2) % RO_DEPTH) * RO_STAGE);
                 }
 #define RO_NOM(e) (STAGED ? sg[RO_X + (e)] : d.st_nom[b + (size_t)(e) * es])
 #define RO_UNOM(r) (STAGED ? sg[RO_U + (r)] : d.st_nom[b + (size_t)(14 + (r)) * es])
@@ -150,17 +167,18 @@ __global__ void __launch_bounds__(128) k_rollout(Dev d, Consts c, Opt opt, int m
             rb_foothold(c, mode, x, dt * (double)N, fh);
             if (STAGED) {
                 __syncwarp(grp);
-                if (N > 1) stage_knot<6>(d, off, i, w, n_used, stage);
+                stage_knot<6, NL>(d, 0 < N - 1, off, i, w, n_used, stage);
+                stage_knot<6, NL>(d, 1 < N - 1, off + 1, i, w, n_used, stage + RO_STAGE);
             }
             for (int k = 0; k < N - 1; ++k) {
                 const int kk = off + k;
                 const size_t b = st_idx(d, kk, 0, i);
                 double dx[6], u[4], xn[6];
-                const double* sg = stage + (k & 1) * RO_STAGE;
+                const double* sg = stage + (k % RO_DEPTH) * RO_STAGE;
                 if (STAGED) {
-                    __pipeline_wait_prior(0);
+                    __pipeline_wait_prior(1);   // everything but the newest group (knot k + 1) has landed
                     __syncwarp(grp);
-                    if (k + 1 < N - 1) stage_knot<6>(d, kk + 1, i, w, n_used, stage + ((k & 1) ^ 1) * RO_STAGE);
+                    stage_knot<6, NL>(d, k + 2 < N - 1, kk + 2, i, w, n_used, stage + ((k + 2) % RO_DEPTH) * RO_STAGE);
                 }
 #pragma unroll
                 for (int e = 0; e < 6; ++e) { act[b + e * es] = x[e]; dx[e] = x[e] - RO_NOM(e); }
@@ -213,14 +231,16 @@ void launch_rollout(const Dev& d, const Consts& c, const Opt& opt, int mask_mode
     int ns = 1;
     while (ns < n_slots) ns *= 2;
     if (ns > 32) ns = 32;
-    const int threads = std::min(128, 32 * ns);
+    const int threads = ns == 1 ? 32 : std::min(128, 16 * ns);      // at most 16 staged instances (30 KB) per block
     const int inst_per_block = threads / ns;
     const unsigned blocks = (unsigned)((d.npad + inst_per_block - 1) / inst_per_block);
-    if (n_slots > 1) {
-        const size_t smem = (size_t)inst_per_block * 2 * RO_STAGE * sizeof(double);
-        k_rollout<true><<<blocks, threads, smem, s>>>(d, c, opt, mask_mode, ns, n_slots, trial0, eps);
+    const size_t smem = (size_t)inst_per_block * RO_DEPTH * RO_STAGE * sizeof(double);
+    if (n_slots == 8) {
+        k_rollout<true, 8><<<blocks, threads, smem, s>>>(d, c, opt, mask_mode, ns, n_slots, trial0, eps);
+    } else if (n_slots > 1) {
+        k_rollout<true, 0><<<blocks, threads, smem, s>>>(d, c, opt, mask_mode, ns, n_slots, trial0, eps);
     } else {   // one trial per instance: nothing to share, every lane reads its own instance in place
-        k_rollout<false><<<blocks, threads, 0, s>>>(d, c, opt, mask_mode, ns, n_slots, trial0, eps);
+        k_rollout<false, 0><<<blocks, threads, 0, s>>>(d, c, opt, mask_mode, ns, n_slots, trial0, eps);
     }
 }
 
