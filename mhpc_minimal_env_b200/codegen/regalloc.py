@@ -116,7 +116,7 @@ def allocate(fn: SXFunction, cap: int = 104, lookahead: int = 48, window: int = 
     # output quads: a flush pseudo-instruction (negative id) right after the instruction that completes the quad
     quads: Dict[int, Dict[int, object]] = {}
     quad_stores = set()
-    if quad_of is not None and window <= 1:
+    if quad_of is not None:
         elem = {}
         for st in fn.stores:
             e = quad_of(st)
@@ -159,7 +159,7 @@ def allocate(fn: SXFunction, cap: int = 104, lookahead: int = 48, window: int = 
         return ops
 
     if window > 1:
-        perm = ilp_schedule(instrs, operands, window, slow=lambda ins: nodes[ins[0]].op in (DIV, SQRT, SIN, COS))
+        perm = ilp_schedule(instrs, operands, window, slow=lambda ins: ins[0] >= 0 and nodes[ins[0]].op in (DIV, SQRT, SIN, COS))
         instrs = [instrs[k] for k in perm]
     def_pos: Dict[int, int] = {}
     for t, ins in enumerate(instrs):
