@@ -358,6 +358,8 @@ def main():
                 "clocks": sampler.summary(),
                 "roofline": roofline, "roofline_lin_bs": roofline_lin_bs, "roofline_lin_group": roofline_lin_group,
                 "stage_ms": {k: tm[k] for k in ("total_ms", "rollout_ms", "linearize_ms", "bws_ms", "linesearch_ms", "other_ms")},
+                # the north star's unit of work: ONE HSDDP iteration over the horizon for the whole batch (10 ms control period)
+                "hsddp_iteration_ms": tm["total_ms"] / 6.0,
                 "cpu_baseline": {"value": cpu_v, "unit": UNIT, "cores": 1, "kind": _cpu_kind(),
                                  "sample": f"first {args.cpu_sample} instances of the workload, reference sources (-O3 -mavx2 -mfma, Eigen stand-in), one core; "
                                            f"host has {os.cpu_count()} cores -> x{os.cpu_count()} = {cpu_v * (os.cpu_count() or 1):.1f} solves/s if it scaled perfectly"},
