@@ -39,7 +39,14 @@ struct mhpc_batch {
     Dev d{};
     EpsList eps{};
     bool have_problems = false;
-    std::vector<mhpc_problem> problems;
+    std::vector<mhpc_problem> problems;      // as given by the caller (instance order)
+    // Instances are independent, so their place in the batch is an internal matter: a batch with mixed schedules is
+    // stored sorted by schedule (phase split, modes, knot counts), which keeps the instances that share a warp in the
+    // sweep and the rollouts (4 per warp) on nearly the same knot classes.  slot_of[instance] / user_of[slot]; every
+    // entry point speaks instance order.  Uniform batches are not permuted.
+    bool permuted = false;
+    std::vector<int> slot_of, user_of;
+    int* d_user_of = nullptr;
     std::vector<int> h_nph, h_nwb, h_nk, h_mode, h_N, h_off;   // host copy of the schedule ([P][npad] for the last three)
     std::vector<void*> allocs;
     long long bytes = 0;
@@ -150,6 +157,22 @@ static int gait_next(const mhpc_problem& p, int cur) {   // Gait.h:46-53
     return cur;
 }
 
+static inline int SL(const mhpc_batch* b, int inst) { return b->permuted ? b->slot_of[inst] : inst; }
+// n per-instance values that sit in slot order on the device -> the caller's instance order
+template <class T>
+static int pull_per_instance(mhpc_batch* b, const T* dev, T* out) {
+    if (!b->permuted) {
+        CK(cudaMemcpyAsync(out, dev, b->n * sizeof(T), cudaMemcpyDeviceToHost, b->stream));
+        CK(cudaStreamSynchronize(b->stream));
+        return 0;
+    }
+    std::vector<T> tmp(b->n);
+    CK(cudaMemcpyAsync(tmp.data(), dev, b->n * sizeof(T), cudaMemcpyDeviceToHost, b->stream));
+    CK(cudaStreamSynchronize(b->stream));
+    for (int s = 0; s < b->n; ++s) out[b->user_of[s]] = tmp[s];
+    return 0;
+}
+
 extern "C" {
 
 const char* mhpc_last_error(void) { return g_err.c_str(); }
@@ -195,6 +218,7 @@ void mhpc_batch_destroy(mhpc_batch* b) {
     free_all(b);
     if (b->stage) cudaFree(b->stage);
     if (b->rot_tmp) cudaFree(b->rot_tmp);
+    if (b->d_user_of) cudaFree(b->d_user_of);
     for (auto& e : b->evs) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
     if (b->own_stream && b->stream) cudaStreamDestroy(b->stream);
     delete b;
@@ -224,10 +248,66 @@ int mhpc_batch_synchronize(mhpc_batch* b) {
 }
 long long mhpc_batch_device_bytes(mhpc_batch* b) { return b->bytes; }
 
-int mhpc_batch_set_problems(mhpc_batch* b, const mhpc_problem* pr) {
+static int set_problems_slots(mhpc_batch* b, const mhpc_problem* pr);
+
+// schedule key of a problem: phase split, then (mode, knot count) per phase - what decides which code a knot runs
+static std::vector<int> schedule_key(const mhpc_problem& q) {
+    std::vector<int> key{q.n_wbphase, q.n_fbphase};
+    const int np = q.n_wbphase + q.n_fbphase;
+    int mode = q.cmode;
+    for (int p = 0; p < np && p < MAXP; ++p) {
+        if (p > 0) mode = gait_next(q, mode);
+        const float timing = (mode >= 1 && mode <= 4) ? q.gait_timing[mode - 1] : 0.f;
+        const double dt = p < q.n_wbphase ? (double)q.dt_wb : (double)q.dt_fb;
+        key.push_back(mode);
+        key.push_back(dt > 0 ? (int)std::round(timing / dt) : 0);
+    }
+    return key;
+}
+
+// `keep_order`: the device state already belongs to the current slots (receding-horizon shift): do not re-sort
+static int set_problems_ordered(mhpc_batch* b, const mhpc_problem* pr, bool keep_order) {
     CK(cudaSetDevice(b->device));
-    const int n = b->n, npad = (n + 31) / 32 * 32, nblk = npad / 32;
+    const int n = b->n;
+    auto same_inputs = [](const mhpc_problem& a, const mhpc_problem& c) {   // the fields schedule_key reads
+        return a.n_wbphase == c.n_wbphase && a.n_fbphase == c.n_fbphase && a.cmode == c.cmode && a.dt_wb == c.dt_wb && a.dt_fb == c.dt_fb &&
+               std::memcmp(a.gait_mode, c.gait_mode, sizeof(a.gait_mode)) == 0 && std::memcmp(a.gait_timing, c.gait_timing, sizeof(a.gait_timing)) == 0;
+    };
+    bool uniform_inputs = true;
+    for (int i = 1; i < n && uniform_inputs; ++i) uniform_inputs = same_inputs(pr[0], pr[i]);
+    if (!keep_order && uniform_inputs) {   // the common case costs one pass and no sort
+        b->permuted = false;
+        b->slot_of.clear();
+        b->user_of.clear();
+    } else if (!keep_order || (b->permuted && (int)b->slot_of.size() != n)) {
+        std::vector<std::vector<int>> keys(n);
+        for (int i = 0; i < n; ++i) keys[i] = schedule_key(pr[i]);
+        std::vector<int> order(n);
+        for (int i = 0; i < n; ++i) order[i] = i;
+        std::stable_sort(order.begin(), order.end(), [&](int a, int c) { return keys[a] < keys[c]; });
+        bool identity = true;
+        for (int s = 0; s < n; ++s) if (order[s] != s) { identity = false; break; }
+        b->user_of = order;
+        b->slot_of.assign(n, 0);
+        for (int s = 0; s < n; ++s) b->slot_of[order[s]] = s;
+        b->permuted = !identity;
+        if (b->permuted) {
+            if (b->d_user_of) cudaFree(b->d_user_of);
+            CK(cudaMalloc(&b->d_user_of, n * sizeof(int)));
+            CK(cudaMemcpy(b->d_user_of, b->user_of.data(), n * sizeof(int), cudaMemcpyHostToDevice));
+        }
+    }
     b->problems.assign(pr, pr + n);
+    if (!b->permuted) return set_problems_slots(b, pr);
+    std::vector<mhpc_problem> ps(n);
+    for (int s = 0; s < n; ++s) ps[s] = pr[b->user_of[s]];
+    return set_problems_slots(b, ps.data());
+}
+int mhpc_batch_set_problems(mhpc_batch* b, const mhpc_problem* pr) { return set_problems_ordered(b, pr, false); }
+
+// everything below works in slot order
+static int set_problems_slots(mhpc_batch* b, const mhpc_problem* pr) {
+    const int n = b->n, npad = (n + 31) / 32 * 32, nblk = npad / 32;
     int P = 1, KT = 1;
     for (int i = 0; i < n; ++i) {
         const int np = pr[i].n_wbphase + pr[i].n_fbphase;
@@ -430,7 +510,7 @@ int mhpc_batch_set_initial_condition(mhpc_batch* b, const double* x0) {
     if (need(b)) return -1;
     std::vector<double> soa((size_t)14 * b->d.npad, 0.0);
     for (int i = 0; i < b->n; ++i)
-        for (int e = 0; e < 14; ++e) { b->problems[i].x0[e] = x0[(size_t)i * 14 + e]; soa[(size_t)e * b->d.npad + i] = x0[(size_t)i * 14 + e]; }
+        for (int e = 0; e < 14; ++e) { b->problems[i].x0[e] = x0[(size_t)i * 14 + e]; soa[(size_t)e * b->d.npad + SL(b, i)] = x0[(size_t)i * 14 + e]; }
     CK(cudaMemcpyAsync(b->d.x0, soa.data(), soa.size() * sizeof(double), cudaMemcpyHostToDevice, b->stream));
     CK(cudaStreamSynchronize(b->stream));
     return 0;
@@ -460,7 +540,7 @@ int mhpc_batch_update_problem(mhpc_batch* b) {
     // (2) the gait advances one mode; schedule, knot lists and x0 are re-uploaded through the normal path
     std::vector<mhpc_problem> pr = b->problems;
     for (mhpc_problem& q : pr) q.cmode = gait_next(q, q.cmode);
-    if (mhpc_batch_set_problems(b, pr.data())) return -1;
+    if (set_problems_ordered(b, pr.data(), true)) return -1;
     // (3) every phase is re-initialised (AL/ReB parameters) and the reference regenerated from _x0
     launch_setup_refs_params(d, b->c, b->stream);
     launch_spread_last_knot(d, b->stream);
@@ -507,10 +587,7 @@ int mhpc_batch_backward_sweep(mhpc_batch* b, double reg, int* success) {
         launch_bws(b->d, b->c, b->opt, MASK_ALL, 1, b->stream);
     }
     CK(cudaGetLastError());
-    if (success) {
-        CK(cudaMemcpyAsync(success, b->d.si + (size_t)SI_BWS_OK * b->d.npad, b->n * sizeof(int), cudaMemcpyDeviceToHost, b->stream));
-        CK(cudaStreamSynchronize(b->stream));
-    }
+    if (success && pull_per_instance(b, b->d.si + (size_t)SI_BWS_OK * b->d.npad, success)) return -1;
     return 0;
 }
 static int line_search(mhpc_batch* b, int mask_ls, int mask_sel) {
@@ -535,10 +612,7 @@ int mhpc_batch_forward_iteration(mhpc_batch* b, int* trials) {
     launch_reb_from_option(b->d, b->stream);
     launch_ls_begin(b->d, MASK_ALL, b->stream);
     if (line_search(b, MASK_LS, MASK_ALL)) return -1;
-    if (trials) {
-        CK(cudaMemcpyAsync(trials, b->d.si + (size_t)SI_N_FIT * b->d.npad, b->n * sizeof(int), cudaMemcpyDeviceToHost, b->stream));
-        CK(cudaStreamSynchronize(b->stream));
-    }
+    if (trials && pull_per_instance(b, b->d.si + (size_t)SI_N_FIT * b->d.npad, trials)) return -1;
     return 0;
 }
 int mhpc_batch_update_nominal_trajectory(mhpc_batch* b) {
@@ -619,26 +693,27 @@ int mhpc_batch_get_results(mhpc_batch* b, mhpc_result* r) {
     CK(cudaMemcpyAsync(sd.data(), d.sd, sd.size() * sizeof(double), cudaMemcpyDeviceToHost, b->stream));
     CK(cudaMemcpyAsync(si.data(), d.si, si.size() * sizeof(int), cudaMemcpyDeviceToHost, b->stream));
     CK(cudaStreamSynchronize(b->stream));
-    for (int i = 0; i < b->n; ++i) {
-        r[i].cost = sd[(size_t)SD_COST * d.npad + i]; r[i].exp_cost_change = sd[(size_t)SD_DV * d.npad + i];
-        r[i].viol = sd[(size_t)SD_VIOL * d.npad + i]; r[i].status = si[(size_t)SI_STATUS * d.npad + i];
-        r[i].iter_AL = si[(size_t)SI_ITER_AL * d.npad + i]; r[i].n_records = si[(size_t)SI_N_REC * d.npad + i]; r[i].pad = 0;
+    for (int u = 0; u < b->n; ++u) {
+        const int i = SL(b, u);
+        r[u].cost = sd[(size_t)SD_COST * d.npad + i]; r[u].exp_cost_change = sd[(size_t)SD_DV * d.npad + i];
+        r[u].viol = sd[(size_t)SD_VIOL * d.npad + i]; r[u].status = si[(size_t)SI_STATUS * d.npad + i];
+        r[u].iter_AL = si[(size_t)SI_ITER_AL * d.npad + i]; r[u].n_records = si[(size_t)SI_N_REC * d.npad + i]; r[u].pad = 0;
     }
     return 0;
 }
 int mhpc_batch_get_scalars(mhpc_batch* b, double* cost, double* dv, double* viol) {
     if (need(b)) return -1;
     const Dev& d = b->d;
-    if (cost) CK(cudaMemcpyAsync(cost, d.sd + (size_t)SD_COST * d.npad, b->n * sizeof(double), cudaMemcpyDeviceToHost, b->stream));
-    if (dv) CK(cudaMemcpyAsync(dv, d.sd + (size_t)SD_DV * d.npad, b->n * sizeof(double), cudaMemcpyDeviceToHost, b->stream));
-    if (viol) CK(cudaMemcpyAsync(viol, d.sd + (size_t)SD_VIOL * d.npad, b->n * sizeof(double), cudaMemcpyDeviceToHost, b->stream));
-    CK(cudaStreamSynchronize(b->stream));
+    if (cost && pull_per_instance(b, d.sd + (size_t)SD_COST * d.npad, cost)) return -1;
+    if (dv && pull_per_instance(b, d.sd + (size_t)SD_DV * d.npad, dv)) return -1;
+    if (viol && pull_per_instance(b, d.sd + (size_t)SD_VIOL * d.npad, viol)) return -1;
     return 0;
 }
 int mhpc_batch_get_records(mhpc_batch* b, int inst, mhpc_iter_record* out, int max_records) {
     if (need(b)) return -1;
     const Dev& d = b->d;
     if (inst < 0 || inst >= b->n) return fail("get_records: bad instance");
+    inst = SL(b, inst);
     int nrec = 0;
     CK(cudaMemcpyAsync(&nrec, d.si + (size_t)SI_N_REC * d.npad + inst, sizeof(int), cudaMemcpyDeviceToHost, b->stream));
     CK(cudaStreamSynchronize(b->stream));
@@ -658,10 +733,11 @@ int mhpc_batch_get_records(mhpc_batch* b, int inst, mhpc_iter_record* out, int m
 }
 int mhpc_batch_n_phases(mhpc_batch* b, int inst) {
     if (!b || !b->have_problems || inst < 0 || inst >= b->n) return -1;
-    return b->h_nph[inst];
+    return b->h_nph[SL(b, inst)];
 }
 int mhpc_batch_get_schedule(mhpc_batch* b, int inst, int* mode, int* nk, int* is_wb) {
     if (!b || !b->have_problems || inst < 0 || inst >= b->n) return fail("get_schedule: bad arguments");
+    inst = SL(b, inst);
     const int npad = b->d.npad;
     for (int p = 0; p < b->h_nph[inst]; ++p) {
         if (mode) mode[p] = b->h_mode[(size_t)p * npad + inst];
@@ -672,6 +748,8 @@ int mhpc_batch_get_schedule(mhpc_batch* b, int inst, int* mode, int* nk, int* is
 }
 int mhpc_batch_get_phase_params(mhpc_batch* b, int inst, int phase, double* out9) {
     if (need(b)) return -1;
+    if (inst < 0 || inst >= b->n) return fail("get_phase_params: bad instance");
+    inst = SL(b, inst);
     const Dev& d = b->d;
     CK(cudaMemcpy2DAsync(out9, sizeof(double), d.par + par_idx(d, phase, 0, inst), (size_t)d.npad * sizeof(double), sizeof(double), NPAR,
                          cudaMemcpyDeviceToHost, b->stream));
@@ -689,12 +767,14 @@ static int pull_rows(mhpc_batch* b, const double* base, int rows, int inst, doub
 int mhpc_batch_get_field(mhpc_batch* b, int inst, int phase, int field, double* out) {
     if (need(b)) return -1;
     const Dev& d = b->d;
-    if (inst < 0 || inst >= b->n || phase < 0 || phase >= b->h_nph[inst]) return fail("get_field: bad instance/phase");
+    if (inst < 0 || inst >= b->n || phase < 0 || phase >= b->h_nph[SL(b, inst)]) return fail("get_field: bad instance/phase");
+    const mhpc_problem& prob = b->problems[inst];   // caller's order
+    inst = SL(b, inst);                             // slot from here on
     const int npad = d.npad;
     const bool wb = phase < b->h_nwb[inst];
     const int nx = wb ? 14 : 6;
     const int N = b->h_N[(size_t)phase * npad + inst], off = b->h_off[(size_t)phase * npad + inst], mode = b->h_mode[(size_t)phase * npad + inst];
-    const double dt = wb ? (double)b->problems[inst].dt_wb : (double)b->problems[inst].dt_fb;
+    const double dt = wb ? (double)prob.dt_wb : (double)prob.dt_fb;
     auto state_field = [&](const double* base, int e0, int dim) -> int {
         if (!out) return dim;
         std::vector<double> tmp((size_t)N * ST);
@@ -730,7 +810,7 @@ int mhpc_batch_get_field(mhpc_batch* b, int inst, int phase, int field, double* 
             if (!out) return dim;
             std::vector<double> pos(N);
             if (pull_rows(b, d.pos_ref + (size_t)off * npad, N, inst, pos.data())) return -1;
-            const double vel = b->problems[inst].vel, hgt = b->problems[inst].height;
+            const double vel = prob.vel, hgt = prob.height;
             for (int k = 0; k < N; ++k) {   // ReferenceGen.h:53-91 (the device evaluates these on the fly from pos_ref)
                 double* o = out + (size_t)k * dim;
                 for (int e = 0; e < dim; ++e) o[e] = 0;
@@ -826,9 +906,10 @@ int mhpc_batch_get_field(mhpc_batch* b, int inst, int phase, int field, double* 
 }
 
 // execution bag (MHPCLocomotion.cpp:178-194): nominal x,u,y and K,du of the leading knots, instance-major
-__global__ void k_gather_exec(Dev d, int kn, double* st_out, double* gain_out) {
+__global__ void k_gather_exec(Dev d, const int* __restrict__ user_of, int kn, double* st_out, double* gain_out) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= d.n) return;
+    const int u = user_of ? user_of[i] : i;   // output row: the caller's instance order
     const int k = blockIdx.y;   // k-th used knot of the horizon -> knot slot (phase blocks of KSTRIDE)
     int kk = -1, c = k;
     for (int p = 0; p < d.n_phases[i]; ++p) {
@@ -836,35 +917,36 @@ __global__ void k_gather_exec(Dev d, int kn, double* st_out, double* gain_out) {
         if (c < N) { kk = p * KSTRIDE + c; break; }
         c -= N;
     }
-    if (st_out) for (int e = 0; e < ST; ++e) st_out[((size_t)i * kn + k) * ST + e] = kk >= 0 ? d.st_nom[((size_t)kk * ST + e) * d.npad + i] : 0.0;
+    if (st_out) for (int e = 0; e < ST; ++e) st_out[((size_t)u * kn + k) * ST + e] = kk >= 0 ? d.st_nom[((size_t)kk * ST + e) * d.npad + i] : 0.0;
     if (gain_out) {
-        for (int e = 0; e < KDIM; ++e) gain_out[((size_t)i * kn + k) * 60 + e] = kk >= 0 ? d.Kfb[((size_t)kk * KDIM + e) * d.npad + i] : 0.0;
-        for (int e = 0; e < 4; ++e) gain_out[((size_t)i * kn + k) * 60 + 56 + e] = kk >= 0 ? d.dufb[((size_t)kk * 4 + e) * d.npad + i] : 0.0;
+        for (int e = 0; e < KDIM; ++e) gain_out[((size_t)u * kn + k) * 60 + e] = kk >= 0 ? d.Kfb[((size_t)kk * KDIM + e) * d.npad + i] : 0.0;
+        for (int e = 0; e < 4; ++e) gain_out[((size_t)u * kn + k) * 60 + 56 + e] = kk >= 0 ? d.dufb[((size_t)kk * 4 + e) * d.npad + i] : 0.0;
     }
 }
-__global__ void k_results_pack(Dev d, mhpc_result* out) {
+__global__ void k_results_pack(Dev d, const int* __restrict__ user_of, mhpc_result* out) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= d.n) return;
     mhpc_result r;
     r.cost = d.sd[(size_t)SD_COST * d.npad + i]; r.exp_cost_change = d.sd[(size_t)SD_DV * d.npad + i]; r.viol = d.sd[(size_t)SD_VIOL * d.npad + i];
     r.status = d.si[(size_t)SI_STATUS * d.npad + i]; r.iter_AL = d.si[(size_t)SI_ITER_AL * d.npad + i]; r.n_records = d.si[(size_t)SI_N_REC * d.npad + i]; r.pad = 0;
-    out[i] = r;
+    out[user_of ? user_of[i] : i] = r;
 }
-__global__ void k_results_table(Dev d, double* out) {
+__global__ void k_results_table(Dev d, const int* __restrict__ user_of, double* out) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= d.npad) return;
     const bool v = i < d.n;
-    out[0 * (size_t)d.npad + i] = v ? d.sd[(size_t)SD_COST * d.npad + i] : 0.0;
-    out[1 * (size_t)d.npad + i] = v ? d.sd[(size_t)SD_DV * d.npad + i] : 0.0;
-    out[2 * (size_t)d.npad + i] = v ? d.sd[(size_t)SD_VIOL * d.npad + i] : 0.0;
-    out[3 * (size_t)d.npad + i] = v ? (double)d.si[(size_t)SI_STATUS * d.npad + i] : -1.0;
-    out[4 * (size_t)d.npad + i] = v ? (double)d.si[(size_t)SI_ITER_AL * d.npad + i] : 0.0;
-    out[5 * (size_t)d.npad + i] = v ? (double)d.si[(size_t)SI_N_REC * d.npad + i] : 0.0;
+    const int u = (v && user_of) ? user_of[i] : i;   // padding columns stay in place
+    out[0 * (size_t)d.npad + u] = v ? d.sd[(size_t)SD_COST * d.npad + i] : 0.0;
+    out[1 * (size_t)d.npad + u] = v ? d.sd[(size_t)SD_DV * d.npad + i] : 0.0;
+    out[2 * (size_t)d.npad + u] = v ? d.sd[(size_t)SD_VIOL * d.npad + i] : 0.0;
+    out[3 * (size_t)d.npad + u] = v ? (double)d.si[(size_t)SI_STATUS * d.npad + i] : -1.0;
+    out[4 * (size_t)d.npad + u] = v ? (double)d.si[(size_t)SI_ITER_AL * d.npad + i] : 0.0;
+    out[5 * (size_t)d.npad + u] = v ? (double)d.si[(size_t)SI_N_REC * d.npad + i] : 0.0;
 }
 int mhpc_batch_results_to_device(mhpc_batch* b, double* dev_out, int capacity) {
     if (need(b)) return -1;
     if (capacity < 6 * b->d.npad) return fail("results_to_device: buffer too small (need 6*npad doubles)");
-    k_results_table<<<(b->d.npad + 127) / 128, 128, 0, b->stream>>>(b->d, dev_out);
+    k_results_table<<<(b->d.npad + 127) / 128, 128, 0, b->stream>>>(b->d, b->permuted ? b->d_user_of : nullptr, dev_out);
     CK(cudaGetLastError());
     return b->d.npad;
 }
@@ -890,8 +972,9 @@ int mhpc_batch_solve_host(mhpc_batch* b, const mhpc_problem* problems, mhpc_resu
     mhpc_result* dres = (mhpc_result*)base;
     double* dst = exec_state && kn ? (double*)(base + need_res) : nullptr;
     double* dgn = exec_gain && kn ? (double*)(base + need_res + need_st) : nullptr;
-    if (results) k_results_pack<<<(b->n + 127) / 128, 128, 0, b->stream>>>(d, dres);
-    if (kn && (dst || dgn)) { dim3 g((b->n + 127) / 128, kn); k_gather_exec<<<g, 128, 0, b->stream>>>(d, kn, dst, dgn); }
+    const int* uo = b->permuted ? b->d_user_of : nullptr;
+    if (results) k_results_pack<<<(b->n + 127) / 128, 128, 0, b->stream>>>(d, uo, dres);
+    if (kn && (dst || dgn)) { dim3 g((b->n + 127) / 128, kn); k_gather_exec<<<g, 128, 0, b->stream>>>(d, uo, kn, dst, dgn); }
     if (results) CK(cudaMemcpyAsync(results, dres, need_res, cudaMemcpyDeviceToHost, b->stream));
     if (dst) CK(cudaMemcpyAsync(exec_state, dst, need_st, cudaMemcpyDeviceToHost, b->stream));
     if (dgn) CK(cudaMemcpyAsync(exec_gain, dgn, need_gn, cudaMemcpyDeviceToHost, b->stream));

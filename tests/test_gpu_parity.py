@@ -292,6 +292,13 @@ def test_config2_1024_instances_bit_exact_counts():
     _batch_vs_oracle(1024, 2)
 
 
+@pytest.mark.parametrize("cfg", [3, 4])
+def test_full_size_sampled_instances_bit_exact_counts(cfg):
+    """BASELINE configs[2] and [3] at their full size (4096 instances: all-whole-body horizon; varied WB/RB splits and gait
+    timings): every 128th instance is solved by the CPU oracle too - integer traces bit-exact, costs to 1e-6."""
+    _batch_vs_oracle(4096, cfg, check_every=128)
+
+
 def test_full_size_properties_4096():
     """BASELINE full sizes (4096 instances, configs 2 and 4): size-independent properties.
     * batch-composition invariance: an instance's whole trace is bit-identical whether it is solved inside the 4096 batch or
