@@ -333,7 +333,7 @@ def main():
                     "traffic": ncu_traffic("r1_bws_ncu_traffic.json"), "algorithmic_bytes": BWS_BYTES_PER_INSTANCE * n,
                     "ms_per_launch": bws_ms, "us_per_knot": 1e3 * bws_ms / 712,
                     "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
-                    "note": "latency-bound: 712 sequential knots x ~4.9 us; ncu: FP64 pipe 26 %, issue slots 32 %, 1.7 warps/scheduler at 4096 instances"}
+                    "note": f"latency-bound: 712 sequential knots x {1e3 * bws_ms / 712:.1f} us; ncu (profiles/r1_ncu_summary.md): FP64 pipe 26 %, issue slots 32 %, 1.7 warps/scheduler at 4096 instances"}
         roofline_lin_bs = {"kernel": "k_lin<BS> (Dyn_BS_par + Euler A,B + cost/barrier partials, 79 back-stance knots x instances)",
                            "bound": "fp64", "achieved": bs_tflops, "peak": fp64_peak, "unit": "TFLOP/s", "frac": bs_tflops / fp64_peak,
                            "executed_tflops": exe_bs / (lin_bs_ms * 1e-3) / 1e12, "executed_frac": exe_bs / (lin_bs_ms * 1e-3) / 1e12 / fp64_peak,
