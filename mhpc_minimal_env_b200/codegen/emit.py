@@ -94,6 +94,81 @@ def _statements(fn: SXFunction, order: Optional[List[int]] = None,
     return out
 
 
+def critical_path_order(fn: SXFunction, issue: int = 2, lat_fp: int = 8, lat_rcp: int = 60, lat_trig: int = 150) -> List[int]:
+    """Topological order by list scheduling with longest-path-to-sink priority (cycles: a warp-wide FP64 instruction
+    issues every `issue` cycles per scheduler, dependent results come `lat_*` cycles later; scripts/micro/fp64_lat.cu).
+    The DAG and every operation stay the same - only the order of the straight-line statements changes, so that the
+    serial spine of the function (factorisation pivots, substitutions) is started as early as its operands exist
+    instead of where the generator happened to create it.  A rollout thread runs at ~2 warps per scheduler, where the
+    length of that spine is the step time."""
+    import heapq
+    nodes = fn.nodes
+    n = len(nodes)
+
+    def lat(i):
+        op = nodes[i].op
+        if op in (IN, CONST):
+            return 0
+        if op in (SIN, COS, SQRT):
+            return lat_trig
+        if op == DIV:
+            return lat_rcp
+        return lat_fp
+    users: List[List[int]] = [[] for _ in range(n)]
+    npred = [0] * n
+    for i, nd in enumerate(nodes):
+        for o in {nd.a, nd.b}:
+            if o >= 0:
+                users[o].append(i)
+                npred[i] += 1
+    prio = [0] * n
+    for i in reversed(range(n)):
+        best = 0
+        for u in users[i]:
+            if prio[u] > best:
+                best = prio[u]
+        prio[i] = best + lat(i)
+    ready_at = [0] * n
+    heap = [(-prio[i], i) for i in range(n) if npred[i] == 0]
+    heapq.heapify(heap)
+    waiting: List = []          # (ready cycle, -prio, node): operands issued, result not yet available
+    order: List[int] = []
+    clock = 0
+    while heap or waiting:
+        while waiting and waiting[0][0] <= clock:
+            _, pr, i = heapq.heappop(waiting)
+            heapq.heappush(heap, (pr, i))
+        if not heap:
+            clock = waiting[0][0]
+            continue
+        _, i = heapq.heappop(heap)
+        order.append(i)
+        done = clock + lat(i)
+        if nodes[i].op not in (IN, CONST):
+            clock += issue
+        for u in users[i]:
+            npred[u] -= 1
+            if done > ready_at[u]:
+                ready_at[u] = done
+            if npred[u] == 0:
+                heapq.heappush(waiting, (ready_at[u], -prio[u], u))
+    assert len(order) == n
+    return order
+
+
+def reordered(fn: SXFunction, order: List[int]) -> SXFunction:
+    """The same function with its nodes renumbered in `order` (a topological order)."""
+    from .sxdag import Node, Store
+    new_id = {old: k for k, old in enumerate(order)}
+    nodes = []
+    for old in order:
+        nd = fn.nodes[old]
+        nodes.append(Node(nd.op, new_id[nd.a] if nd.a >= 0 else -1, new_id[nd.b] if nd.b >= 0 else -1, nd.val, nd.lit, nd.arg, nd.idx))
+    out = SXFunction(name=fn.name, n_in=fn.n_in, n_out=fn.n_out, in_sizes=fn.in_sizes, nodes=nodes, out_sp=fn.out_sp)
+    out.stores = [Store(s.out, s.nz, new_id[s.node], new_id[s.node] + 1, s.row, s.col) for s in fn.stores]
+    return out
+
+
 def emit_inc(fn: SXFunction, order: Optional[List[int]] = None) -> str:
     hdr = [
         f"// GENERATED at build time by mhpc_minimal_env_b200/codegen from the CasADi SX",

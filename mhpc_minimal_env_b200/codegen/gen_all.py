@@ -23,7 +23,7 @@ import json
 import os
 import sys
 
-from .emit import emit_c, emit_inc
+from .emit import critical_path_order, emit_c, emit_inc, reordered
 from .implicit import implicit_jacobian, structured_primal
 from .regalloc import emit_c_regalloc, emit_inc_regalloc
 from .sxdag import CONST, SXFunction, parse_casadi_c, share_reciprocals
@@ -46,6 +46,8 @@ IMPLICIT_JAC = os.environ.get("MHPC_IMPLICIT_JAC", "1") == "1"
 # the primal dynamics with their symbolic Gram-Schmidt QR replaced by an LDL^T solve of the same system (rollouts)
 STRUCT_PRIMAL = os.environ.get("MHPC_STRUCT_PRIMAL", "1") == "1"
 USE_LDLT = os.environ.get("MHPC_LDLT", "1") == "1"
+CP_ORDER = os.environ.get("MHPC_CP_ORDER", "0") == "1"      # primal dynamics emitted along their critical path: neutral (ptxas -O3 re-schedules)
+JAC_CP = os.environ.get("MHPC_JAC_CP", "0") == "1"          # same for the Jacobian bodies, which ptxas -O1 keeps in the generator's order
 RA_CAP = int(os.environ.get("MHPC_RA_CAP", "104"))
 RA_LOOKAHEAD = int(os.environ.get("MHPC_RA_LOOKAHEAD", "24"))
 RA_WINDOW = int(os.environ.get("MHPC_RA_WINDOW", "0"))
@@ -185,7 +187,11 @@ def generate(ref: str = DEFAULT_REF, out: str = DEFAULT_OUT, verbose: bool = Tru
             dev[primal] = structured_primal(fns[primal], USE_LDLT)
             restated.append(primal)
     for name, fn in dev.items():
-        write(name + ".inc", emit_inc(fn))
+        # the rollout's dynamics are emitted along their critical path (same DAG, same operations; emit.critical_path_order)
+        write(name + ".inc", emit_inc(fn, critical_path_order(fn) if (CP_ORDER and name in IMPLICIT_FUNCTIONS.values()) else None))
+    if JAC_CP:
+        for name in IMPLICIT_FUNCTIONS:
+            dev[name] = reordered(dev[name], critical_path_order(dev[name]))
     ra_stats = {}
     for name in REGALLOC_FUNCTIONS:
         text, st = emit_inc_regalloc(dev[name], RA_CAP, RA_LOOKAHEAD, RA_WINDOW, RA_SMEM, RA_FAR, quad_map(name))
