@@ -329,6 +329,33 @@ def test_full_size_properties_4096():
             assert all(r["cost"] <= r["cost_prev"] or r["n_fit"] == 11 for r in recs)
 
 
+@pytest.mark.parametrize("cfg", [2, 4])
+def test_line_search_width_invariance(cfg):
+    """The Armijo search tries the step sizes in order and takes the first acceptable one (MultiPhaseDDP.cpp:132-148); how
+    many of them one launch evaluates side by side (1, 2, 4, 8 or all 10) must not change the outcome: identical integer
+    traces, regularisation values and accepted step sizes, costs equal to rounding.  (The widths run different template
+    instantiations of the rollout kernel - in-place, generic staging, 8-lane staging - in which the compiler contracts a few
+    multiply-adds differently; that shows in the 15th digit, so the costs are compared to 1e-9 rather than bit for bit.)
+    Exercises every lane-group shape of the rollout kernel (in-place single slot, generic and 8-lane staging)."""
+    import mhpc_minimal_env_b200 as m
+    specs = make_specs(96, cfg)
+    probs = [to_gpu_problem(s) for s in specs]
+    runs = {}
+    for width in (8, 1, 2, 4, 16):
+        b = m.BatchedMHPC(probs, m.default_option(), ls_width=width)
+        b.initialization()
+        b.solve()
+        runs[width] = (b.results_array().tobytes(), [b.records(i) for i in range(96)])
+        b.close()
+    ints = ("iter_AL", "iter_DDP", "n_bws", "n_fit", "reg", "eps")
+    for width in (1, 2, 4, 16):
+        for i in range(96):
+            ra, rb = runs[8][1][i], runs[width][1][i]
+            assert [[r[k] for k in ints] for r in ra] == [[r[k] for k in ints] for r in rb], (width, i)
+            for x, y in zip(ra, rb):   # 15th-digit differences, amplified over 6 iterations
+                assert abs(x["cost"] - y["cost"]) <= 1e-9 * abs(x["cost"]), (width, i, x["cost"], y["cost"])
+
+
 def test_cpp_batched_test_main_reproduces_default_run(tmp_path):
     """examples/test_main_batched.cpp (the reference's test_main.cpp with a batch dimension, through include/mhpc_b200.hpp):
     instance 0 = the reference's default ./mhpc_ctrl run."""
