@@ -47,6 +47,15 @@ struct mhpc_batch {
     bool permuted = false;
     std::vector<int> slot_of, user_of;
     int* d_user_of = nullptr;
+    // side stream for the two impact-Jacobian launches of a linearisation (32 blocks each, one long dependent chain per
+    // thread): they run underneath the stance/flight kernels instead of after them
+    cudaStream_t side = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    // second side stream: the nominal <- accepted-rollout copy (HBM-bound) runs underneath the linearisation and the
+    // latency-bound backward sweep; it is joined before the next kernel that reads the nominal or rewrites the rollouts
+    cudaStream_t side2 = nullptr;
+    cudaEvent_t ev_cfork = nullptr, ev_cjoin = nullptr;
+    bool copy_pending = false;
     std::vector<int> h_nph, h_nwb, h_nk, h_mode, h_N, h_off;   // host copy of the schedule ([P][npad] for the last three)
     std::vector<void*> allocs;
     long long bytes = 0;
@@ -219,6 +228,8 @@ void mhpc_batch_destroy(mhpc_batch* b) {
     if (b->stage) cudaFree(b->stage);
     if (b->rot_tmp) cudaFree(b->rot_tmp);
     if (b->d_user_of) cudaFree(b->d_user_of);
+    if (b->side) { cudaStreamDestroy(b->side); cudaEventDestroy(b->ev_fork); cudaEventDestroy(b->ev_join); }
+    if (b->side2) { cudaStreamDestroy(b->side2); cudaEventDestroy(b->ev_cfork); cudaEventDestroy(b->ev_cjoin); }
     for (auto& e : b->evs) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
     if (b->own_stream && b->stream) cudaStreamDestroy(b->stream);
     delete b;
@@ -467,15 +478,52 @@ static int set_problems_slots(mhpc_batch* b, const mhpc_problem* pr) {
     return 0;
 }
 
+// nominal <- accepted rollout on the second side stream (the mask is frozen first: later kernels of the main stream change
+// the flags it is made of); join_copy() before anything reads the nominal or overwrites the rollout slots
+static int fork_copy_nominal(mhpc_batch* b, int mask_mode) {
+    if (!b->side2) {
+        CK(cudaStreamCreateWithFlags(&b->side2, cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&b->ev_cfork, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&b->ev_cjoin, cudaEventDisableTiming));
+    }
+    launch_snapshot_mask(b->d, mask_mode, b->stream);
+    CK(cudaEventRecord(b->ev_cfork, b->stream));
+    CK(cudaStreamWaitEvent(b->side2, b->ev_cfork, 0));
+    launch_copy_nominal(b->d, MASK_SNAP, b->side2);
+    CK(cudaEventRecord(b->ev_cjoin, b->side2));
+    b->copy_pending = true;
+    b->launches += 2;
+    return 0;
+}
+static int join_copy(mhpc_batch* b) {
+    if (b->copy_pending) { CK(cudaStreamWaitEvent(b->stream, b->ev_cjoin, 0)); b->copy_pending = false; }
+    return 0;
+}
+
 static int linearize(mhpc_batch* b, int mask_mode) {
     Stage st(b, TB_LIN);
     const Dev& d = b->d;
     typedef void (*lin_fn)(const Dev&, const Consts&, const Opt&, int, const int*, int, cudaStream_t);
     const lin_fn fns[CLS_N] = {launch_lin_BS, launch_lin_FS, launch_lin_FL, launch_lin_IMPF, launch_lin_IMPB, launch_lin_LIGHT};
-    for (int c = 0; c < CLS_N; ++c) {
-        if (b->uniform) fns[c](d, b->c, b->opt, mask_mode, b->knot_list[c], b->knot_cnt[c], b->stream);
-        else fns[c](d, b->c, b->opt, mask_mode, (const int*)b->pair_list[c], -b->pair_cnt[c], b->stream);   // negative count = pair list
+    if (!b->side) {
+        int lo = 0, hi = 0;
+        CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        CK(cudaStreamCreateWithPriority(&b->side, cudaStreamNonBlocking, hi));
+        CK(cudaEventCreateWithFlags(&b->ev_fork, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&b->ev_join, cudaEventDisableTiming));
     }
+    auto launch_cls = [&](int c, cudaStream_t s) {
+        if (b->uniform) fns[c](d, b->c, b->opt, mask_mode, b->knot_list[c], b->knot_cnt[c], s);
+        else fns[c](d, b->c, b->opt, mask_mode, (const int*)b->pair_list[c], -b->pair_cnt[c], s);   // negative count = pair list
+    };
+    // the knot classes write disjoint records: impacts fork onto the side stream, everything else stays in order
+    CK(cudaEventRecord(b->ev_fork, b->stream));
+    CK(cudaStreamWaitEvent(b->side, b->ev_fork, 0));
+    launch_cls(CLS_IMPF, b->side);
+    launch_cls(CLS_IMPB, b->side);
+    CK(cudaEventRecord(b->ev_join, b->side));
+    for (int c : {CLS_BS, CLS_FS, CLS_FL, CLS_LIGHT}) launch_cls(c, b->stream);
+    CK(cudaStreamWaitEvent(b->stream, b->ev_join, 0));
     for (int c = 0; c < CLS_N; ++c) b->launches += b->knot_cnt[c] > 0;
     CK(cudaGetLastError());
     return 0;
@@ -591,6 +639,7 @@ int mhpc_batch_backward_sweep(mhpc_batch* b, double reg, int* success) {
     return 0;
 }
 static int line_search(mhpc_batch* b, int mask_ls, int mask_sel) {
+    if (join_copy(b)) return -1;
     Stage st(b, TB_LS);
     const Dev& d = b->d;
     for (int t0 = 0; t0 < b->eps.n; t0 += d.W) {
@@ -642,18 +691,19 @@ int mhpc_batch_solve(mhpc_batch* b, int sync_early_exit) {
     launch_solve_begin(d, s); b->launches++;
     for (int al = 1; al <= maxAL; ++al) {
         { Stage st(b, TB_OTHER); launch_al_begin(d, b->opt, s); b->launches++; }
+        if (join_copy(b)) return -1;
         { Stage st(b, TB_ROLLOUT);                                   // forward_sweep(0): rollout ...
           launch_rollout(d, b->c, b->opt, MASK_RUNNING, 1, 0, zero, s);
           launch_accept_slot0(d, MASK_RUNNING, 2, s); b->launches += 2; }
         if (linearize(b, MASK_RUNNING)) return -1;                   // ... and its derivatives
-        { Stage st(b, TB_OTHER); launch_copy_nominal(d, MASK_RUNNING, s); b->launches++; }   // update_nominal_trajectory
+        { Stage st(b, TB_OTHER); if (fork_copy_nominal(b, MASK_RUNNING)) return -1; }   // update_nominal_trajectory
         for (int it = 1; it <= maxDDP; ++it) {
             { Stage st(b, TB_OTHER); launch_ls_begin(d, MASK_DDP, s); b->launches++; }
             { Stage st(b, TB_BWS); launch_bws(d, b->c, b->opt, MASK_DDP, 0, s); b->launches++; }
             if (line_search(b, MASK_LS, MASK_DDP)) return -1;
             { Stage st(b, TB_OTHER);
-              launch_copy_nominal(d, MASK_DDP, s);
-              launch_ddp_end(d, b->opt, it, s); b->launches += 2; }
+              if (fork_copy_nominal(b, MASK_DDP)) return -1;
+              launch_ddp_end(d, b->opt, it, s); b->launches++; }
             // forward_sweep_partials_only (MultiPhaseDDP.cpp:262).  After the LAST inner iteration the reference still
             // linearises, but every derivative it writes is overwritten by the next outer iteration's forward_sweep(0)
             // (same trajectory: K (x - x_nom) = 0 exactly) or never read (end of solve): the launch is dead work and is
@@ -669,6 +719,7 @@ int mhpc_batch_solve(mhpc_batch* b, int sync_early_exit) {
             if (na == 0) break;
         }
     }
+    if (join_copy(b)) return -1;
     CK(cudaGetLastError());
     if (b->timing) {
         cudaEventRecord(t1, s);

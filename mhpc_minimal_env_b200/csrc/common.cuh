@@ -62,7 +62,7 @@ enum { PAR_SIGMA = 0, PAR_LAMBDA, PAR_DELTA_T, PAR_DELTA_J, PAR_DELTA_G, PAR_EPS
 // initialization() and later solves exactly like the members of a re-used MHPCLocomotion object; *_BASE are solve()'s locals.
 enum { SD_COST = 0, SD_COST_PREV, SD_DV, SD_VIOL, SD_REG, SD_REG_USED, SD_UPD_PENALTY, SD_EPS_ACC, SD_OPT_UPD, SD_UPD_BASE, SD_N };
 enum { SI_STATUS = 0, SI_ITER_AL, SI_ITER_DDP, SI_DDP_ACTIVE, SI_REB_ON, SI_N_BWS, SI_N_FIT, SI_ACC_SLOT, SI_LS_DONE,
-       SI_AL_PARTIALS, SI_N_REC, SI_BWS_OK, SI_OPT_REB, SI_REB_BASE, SI_N };
+       SI_AL_PARTIALS, SI_N_REC, SI_BWS_OK, SI_OPT_REB, SI_REB_BASE, SI_SNAP, SI_N };
 enum { STATUS_RUNNING = 0, STATUS_CONVERGED = 1, STATUS_MAXITER = 2, STATUS_REG_ABORT = 3 };
 constexpr int REC_I = 4, REC_D = 6;  // per-iteration record: ints {iter_AL, iter_DDP, n_bws, n_fit}, doubles {reg, eps, cost, dV, viol, cost_prev}
 

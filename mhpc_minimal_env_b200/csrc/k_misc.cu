@@ -145,6 +145,12 @@ __global__ void k_copy_nominal(Dev d, int mask_mode) {
     for (int e = 0; e < ST; ++e) dst[(size_t)e * d.npad] = v[e];
 }
 
+__global__ void k_snapshot_mask(Dev d, int mask_mode) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= d.n) return;
+    SI(SI_SNAP) = inst_enabled(d, i, mask_mode) ? 1 : 0;
+}
+
 __global__ void k_accept_slot0(Dev d, int mask_mode, int lin_mode) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= d.n || !inst_enabled(d, i, mask_mode)) return;
@@ -364,6 +370,7 @@ void launch_copy_nominal(const Dev& d, int mask_mode, cudaStream_t s) {
     dim3 grid(nb(d.n, 128), d.KT);
     k_copy_nominal<<<grid, 128, 0, s>>>(d, mask_mode);
 }
+void launch_snapshot_mask(const Dev& d, int mask_mode, cudaStream_t s) { k_snapshot_mask<<<nb(d.n, 128), 128, 0, s>>>(d, mask_mode); }
 void launch_accept_slot0(const Dev& d, int mask_mode, int lin_mode, cudaStream_t s) { k_accept_slot0<<<nb(d.n, 128), 128, 0, s>>>(d, mask_mode, lin_mode); }
 void launch_solve_begin(const Dev& d, cudaStream_t s) { k_solve_begin<<<nb(d.n, 128), 128, 0, s>>>(d); }
 void launch_al_begin(const Dev& d, const Opt& o, cudaStream_t s) { k_al_begin<<<nb(d.n, 128), 128, 0, s>>>(d, o); }

@@ -13,7 +13,7 @@ struct EpsList {  // line-search step sizes eps_t = alpha^t formed by repeated m
 };
 
 // which instances a launch touches
-enum { MASK_ALL = 0, MASK_RUNNING, MASK_DDP, MASK_LS, MASK_LIN };
+enum { MASK_ALL = 0, MASK_RUNNING, MASK_DDP, MASK_LS, MASK_LIN, MASK_SNAP };
 
 __device__ inline bool inst_enabled(const Dev& d, int i, int mask_mode) {
     switch (mask_mode) {
@@ -22,6 +22,7 @@ __device__ inline bool inst_enabled(const Dev& d, int i, int mask_mode) {
         case MASK_DDP:
         case MASK_LS: return d.si[(size_t)SI_STATUS * d.npad + i] == STATUS_RUNNING && d.si[(size_t)SI_DDP_ACTIVE * d.npad + i] != 0;
         case MASK_LIN: return d.si[(size_t)SI_STATUS * d.npad + i] == STATUS_RUNNING && d.si[(size_t)SI_AL_PARTIALS * d.npad + i] != 0;
+        case MASK_SNAP: return d.si[(size_t)SI_SNAP * d.npad + i] != 0;   // a mask frozen by launch_snapshot_mask
     }
     return false;
 }
@@ -30,6 +31,7 @@ __device__ inline bool inst_enabled(const Dev& d, int i, int mask_mode) {
 void launch_setup(const Dev& d, const Consts& c, cudaStream_t s);       // references, AL/ReB parameters, zeroed state
 void launch_warmstart(const Dev& d, const Consts& c, cudaStream_t s);   // boundingPDControl.cpp on the device -> act slot 0
 void launch_copy_nominal(const Dev& d, int mask_mode, cudaStream_t s);  // act[acc_slot] -> nom
+void launch_snapshot_mask(const Dev& d, int mask_mode, cudaStream_t s); // SI_SNAP <- inst_enabled(mask_mode), for work that runs on a side stream
 void launch_accept_slot0(const Dev& d, int mask_mode, int lin_mode, cudaStream_t s);
 void launch_solve_begin(const Dev& d, cudaStream_t s);
 void launch_al_begin(const Dev& d, const Opt& o, cudaStream_t s);
