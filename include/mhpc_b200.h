@@ -90,7 +90,9 @@ int mhpc_batch_create(int n_instances, const mhpc_hsddp_option* opt, int device,
 void mhpc_batch_destroy(mhpc_batch* b);                  /* MHPCLocomotion::~MHPCLocomotion (:383-470) */
 const char* mhpc_last_error(void);
 int mhpc_batch_set_option(mhpc_batch* b, const mhpc_hsddp_option* opt);   /* MultiPhaseDDP::set_option, MultiPhaseDDP.h:22 */
-/* Use the caller's CUDA stream (e.g. torch's current stream) for all work of this handle; NULL = own stream. */
+/* Use the caller's CUDA stream (e.g. torch's current stream) for all work of this handle; NULL = own stream.
+   (A solve forks two short pieces of work onto handle-private side streams and joins them back with events; ordering
+   against this one stream is enough.) */
 int mhpc_batch_set_stream(mhpc_batch* b, void* cuda_stream);
 
 /* ---- problem definition ------------------------------------------------------------------------- */
