@@ -356,6 +356,39 @@ def test_line_search_width_invariance(cfg):
                 assert abs(x["cost"] - y["cost"]) <= 1e-9 * abs(x["cost"]), (width, i, x["cost"], y["cost"])
 
 
+def test_instance_order_is_kept_on_every_output_path():
+    """A mixed-schedule batch is stored sorted by schedule internally (capi.cu: slot_of / user_of).  Every output path must
+    still answer in the caller's instance order: host results, scalars, records, fields, the device-side result table (the
+    multi-GPU gather) and solve_host with its execution bag - checked against the same instances solved one batch of
+    identical schedules at a time (no permutation)."""
+    import torch
+    import mhpc_minimal_env_b200 as m
+    specs = make_specs(64, 4)
+    probs = [to_gpu_problem(s) for s in specs]
+    mixed = m.BatchedMHPC(probs, m.default_option())
+    res, st, gn = mixed.solve_host(exec_knots=6)
+    table = torch.zeros(6 * 64, dtype=torch.float64, device="cuda")
+    npad = mixed.results_to_device(table.data_ptr(), table.numel())
+    table = table.cpu().numpy().reshape(6, npad)
+    host = mixed.results()
+    sc = mixed.scalars()
+    cost, dv, viol = sc["cost"], sc["exp_cost_change"], sc["viol"]
+    for i in (0, 1, 7, 20, 41, 63):
+        solo = m.BatchedMHPC([probs[i]], m.default_option())      # one instance: never permuted
+        r1, s1, g1 = solo.solve_host(exec_knots=6)
+        h1 = solo.results()[0]
+        assert (res[i].cost, res[i].status, res[i].n_records) == (r1[0].cost, r1[0].status, r1[0].n_records), i
+        assert host[i] == h1, i
+        assert (table[0, i], table[3, i], table[5, i]) == (h1["cost"], float(h1["status"]), float(h1["n_records"])), i
+        assert (cost[i], dv[i], viol[i]) == (h1["cost"], h1["exp_cost_change"], h1["viol"]), i
+        assert np.array_equal(st[i], s1[0]) and np.array_equal(gn[i], g1[0]), i
+        assert mixed.records(i) == solo.records(0), i
+        assert mixed.schedule(i) == solo.schedule(0), i
+        assert np.array_equal(mixed.field(i, 0, "X_NOM"), solo.field(0, 0, "X_NOM")), i
+        solo.close()
+    mixed.close()
+
+
 def test_cpp_batched_test_main_reproduces_default_run(tmp_path):
     """examples/test_main_batched.cpp (the reference's test_main.cpp with a batch dimension, through include/mhpc_b200.hpp):
     instance 0 = the reference's default ./mhpc_ctrl run."""
