@@ -11,7 +11,7 @@
 // cannot be built as shipped (Eigen3 is an absent, unpinned system dependency).  The
 // restatement is pinned against the reference *sources compiled here* through the
 // minimal Eigen stand-in in oracle/eigen_shim (oracle/README.md, tests/test_oracle_vs_ref.py:
-// bit-identical on 8 cases).  Real Eigen's kernel rounding is not reproduced.
+// bit-identical on 8 solve cases and 4 receding-horizon update_problem cases).  Real Eigen's kernel rounding is not reproduced.
 #pragma once
 #include <vector>
 
