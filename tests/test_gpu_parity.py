@@ -211,10 +211,10 @@ def test_fixed_iteration_budget_and_early_exit_agree():
 
 
 def _oracle_counts(args):
-    idx, cfg, optkw = args
+    idx, cfg, optkw, scale = args
     from oracle.oracle_py import OracleSolver
     out = []
-    specs = make_specs(max(idx) + 1, cfg)
+    specs = make_specs(max(idx) + 1, cfg, scale)
     for i in idx:
         o = OracleSolver(to_orc_problem(specs[i], **optkw), variant="strict")
         o.initialization()
@@ -248,20 +248,20 @@ def _oracle_cost_sensitivity(spec, optkw, rel=1e-12, trials=4):
     return sens
 
 
-def _batch_vs_oracle(n, cfg, optkw=None, check_every=1):
+def _batch_vs_oracle(n, cfg, optkw=None, check_every=1, scale=1.0):
     """BASELINE config sizes: iteration counts / regularisation / accepted step sizes bit-exact for every checked instance."""
     import multiprocessing as mp
     import os
     import mhpc_minimal_env_b200 as m
     optkw = optkw or {}
-    specs = make_specs(n, cfg)
+    specs = make_specs(n, cfg, scale)
     gpu = m.BatchedMHPC([to_gpu_problem(s) for s in specs], m.default_option(**optkw))
     gpu.initialization()
     gpu.solve()
     res = gpu.results()
     idx = list(range(0, n, check_every))
     nproc = min(os.cpu_count() or 1, 16)
-    chunks = [(idx[k::nproc], cfg, optkw) for k in range(nproc) if idx[k::nproc]]
+    chunks = [(idx[k::nproc], cfg, optkw, scale) for k in range(nproc) if idx[k::nproc]]
     with mp.get_context("fork").Pool(len(chunks)) as pool:
         outs = [x for part in pool.map(_oracle_counts, chunks) for x in part]
     bad, ill = [], []
@@ -297,6 +297,13 @@ def test_full_size_sampled_instances_bit_exact_counts(cfg):
     """BASELINE configs[2] and [3] at their full size (4096 instances: all-whole-body horizon; varied WB/RB splits and gait
     timings): every 128th instance is solved by the CPU oracle too - integer traces bit-exact, costs to 1e-6."""
     _batch_vs_oracle(4096, cfg, check_every=128)
+
+
+@pytest.mark.parametrize("cfg", [2, 4])
+def test_large_perturbations_counts_bit_exact(cfg):
+    """Initial states perturbed three times as far as in the BASELINE workload (more regularisation retries, later
+    line-search trials, aborts if any): 256 instances, integer traces bit-exact against the oracle."""
+    _batch_vs_oracle(256, cfg, scale=3.0)
 
 
 def test_full_size_properties_4096():
