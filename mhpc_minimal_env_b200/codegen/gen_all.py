@@ -41,7 +41,10 @@ FUNCTIONS = [
 REGALLOC_FUNCTIONS = ["Dyn_BS_par", "Dyn_FS_par", "Dyn_FL_par", "Imp_F_par", "Imp_B_par"]
 # dynamics Jacobians re-derived by implicit differentiation of the primal's linear solve (codegen/implicit.py); the
 # flat CasADi DAGs stay the CPU check (gen_/genra_) and MHPC_IMPLICIT_JAC=0 puts them back on the device
-IMPLICIT_FUNCTIONS = {"Dyn_BS_par": "Dyn_BS", "Dyn_FS_par": "Dyn_FS", "Dyn_FL_par": "Dyn_FL"}
+IMPLICIT_FUNCTIONS = {"Dyn_BS_par": "Dyn_BS", "Dyn_FS_par": "Dyn_FS", "Dyn_FL_par": "Dyn_FL", "Imp_F_par": "Imp_F", "Imp_B_par": "Imp_B"}
+# the impact maps' right-hand side has two structurally zero rows; their system matrix is taken from the stance dynamics of
+# the same foot (codegen/implicit.py: identify_system(donor=...))
+DONOR = {"Imp_F": "Dyn_FS", "Imp_B": "Dyn_BS"}
 IMPLICIT_JAC = os.environ.get("MHPC_IMPLICIT_JAC", "1") == "1"
 # the primal dynamics with their symbolic Gram-Schmidt QR replaced by an LDL^T solve of the same system (rollouts)
 STRUCT_PRIMAL = os.environ.get("MHPC_STRUCT_PRIMAL", "1") == "1"
@@ -70,8 +73,15 @@ def wb_record_element(st):
     return 136 + st.col * 2 + (st.row & 1)
 
 
+def imp_record_element(st):
+    """Element of a WB terminal-knot record (R_AB block = Px[7:14, 2:14]) an Imp_*_par non-zero lands in."""
+    return (st.col - 2) * 7 + (st.row - 7) if st.row >= 7 else None
+
+
 def quad_map(name):
-    return wb_record_element if (QUAD_OUT and name in IMPLICIT_FUNCTIONS) else None
+    if not (QUAD_OUT and IMPLICIT_JAC and name in IMPLICIT_FUNCTIONS):
+        return None
+    return imp_record_element if name.startswith("Imp_") else wb_record_element
 
 
 HERE = os.path.dirname(os.path.abspath(__file__))
@@ -180,11 +190,11 @@ def generate(ref: str = DEFAULT_REF, out: str = DEFAULT_OUT, verbose: bool = Tru
     restated = []
     if IMPLICIT_JAC:
         for name, primal in IMPLICIT_FUNCTIONS.items():
-            dev[name] = implicit_jacobian(fns[primal], fns[name], USE_LDLT)
+            dev[name] = implicit_jacobian(fns[primal], fns[name], USE_LDLT, donor=fns[DONOR[primal]] if primal in DONOR else None)
             restated.append(name)
     if STRUCT_PRIMAL:
         for primal in IMPLICIT_FUNCTIONS.values():
-            dev[primal] = structured_primal(fns[primal], USE_LDLT)
+            dev[primal] = structured_primal(fns[primal], USE_LDLT, donor=fns[DONOR[primal]] if primal in DONOR else None)
             restated.append(primal)
     for name, fn in dev.items():
         # the rollout's dynamics are emitted along their critical path (same DAG, same operations; emit.critical_path_order)

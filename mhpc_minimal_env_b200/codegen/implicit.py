@@ -25,8 +25,9 @@ This module rebuilds `Dyn_*_par` that way, mechanically, from the primal DAG alo
 
 The result is a different (mathematically equal) floating-point evaluation of the same Jacobian: it is checked against
 the reference's `Dyn_*_par` objects to 1e-10 of the matrix norm at random inputs (tests/test_cpu.py), within the
-1e-9 norm-relative Jacobian tolerance of SURVEY.md section 7.  The impact maps keep the CasADi operation sequence
-(two knots per horizon; their right-hand side has structural zeros, which this identification does not handle).
+1e-9 norm-relative Jacobian tolerance of SURVEY.md section 7.  The impact maps (`Imp_{F,B}`, `Imp_{F,B}_par`) have
+structural zeros in their right-hand side; their system matrix is taken from the stance dynamics of the same foot
+(identify_system(donor=...)).
 """
 from __future__ import annotations
 
@@ -179,9 +180,17 @@ def _eval_nodes(nodes: List[Node], args, override: Optional[Dict[int, float]] = 
     return v
 
 
-def identify_system(primal: SXFunction, n_points: int = 3, seed: int = 7):
-    """Returns (post, outs, beta, Kp) where `outs` are the output nodes that come out of the solve, `beta` the pre nodes
-    forming the right-hand side and Kp[i][j] = (node, sign) | None with  sum_j Kp[i][j] * value(outs[j]) = value(beta[i])."""
+def identify_system(primal: SXFunction, n_points: int = 3, seed: int = 7, donor: Optional[SXFunction] = None):
+    """Returns (post, outs, beta, Kp, nodes) where `outs` are the output nodes that come out of the solve, `beta` the pre
+    nodes forming the right-hand side (None = structurally zero row) and Kp[i][j] = (node, sign) | None with
+    sum_j Kp[i][j] * value(outs[j]) = value(beta[i]); node ids refer to `nodes` (the primal's list, extended by donor
+    nodes when the system matrix is taken from `donor`).
+
+    `donor`: a function with the SAME system matrix and a full right-hand side.  The impact maps solve
+    [M -J^T; J 0] [qd+; Lambda] = [M qd-; 0]: two rows of their right-hand side are structurally zero, so the probing
+    below only sees a 9x7 response and cannot recover the matrix; the stance dynamics of the same foot have all nine
+    right-hand-side entries, and their identified matrix (a function of q alone) is re-used after checking numerically
+    that it maps the impact outputs onto the impact right-hand side."""
     import numpy as np
     nodes = primal.nodes
     n = len(nodes)
@@ -221,7 +230,9 @@ def identify_system(primal: SXFunction, n_points: int = 3, seed: int = 7):
         if beta != b_here:
             raise RuntimeError(f"{primal.name}: right-hand-side nodes differ between sample points")
         if len(beta) != len(outs):
-            raise RuntimeError(f"{primal.name}: {len(beta)} right-hand-side nodes for {len(outs)} solved outputs")
+            if donor is None:
+                raise RuntimeError(f"{primal.name}: {len(beta)} right-hand-side nodes for {len(outs)} solved outputs")
+            return _identify_with_donor(primal, donor, post, outs, beta, n_points, seed)
         zero = {f: 0.0 for f in beta}
         zz = S(zero)
         if np.abs(zz).max() > 1e-12:
@@ -252,10 +263,72 @@ def identify_system(primal: SXFunction, n_points: int = 3, seed: int = 7):
             if hit is None:
                 raise RuntimeError(f"{primal.name}: system-matrix entry ({i},{j}) is not a node of the primal DAG")
             Kp[i][j] = hit
-    return post, outs, beta, Kp
+    return post, outs, beta, Kp, nodes
 
 
-def symmetric_form(primal: SXFunction, Kp, n_points: int = 2, seed: int = 11):
+def _identify_with_donor(primal: SXFunction, donor: SXFunction, post, outs, beta_nodes, n_points: int, seed: int):
+    import itertools
+    import numpy as np
+    dpost, douts, dbeta, dKp, dnodes = identify_system(donor)
+    if len(douts) != len(outs):
+        raise RuntimeError(f"{primal.name}: donor {donor.name} solves a system of another size")
+    # donor pre nodes the matrix depends on, appended to the primal's node list
+    need, stack = set(), [e[0] for row in dKp for e in row if e]
+    while stack:
+        q = stack.pop()
+        if q in need:
+            continue
+        need.add(q)
+        nd = dnodes[q]
+        if nd.op == IN and nd.arg != 0:
+            raise RuntimeError(f"{primal.name}: the donor matrix depends on an input the primal does not have")
+        stack.extend(o for o in (nd.a, nd.b) if o >= 0)
+    merged = list(primal.nodes)
+    remap: Dict[int, int] = {}
+    for q in sorted(need):
+        nd = dnodes[q]
+        merged.append(Node(nd.op, remap[nd.a] if nd.a >= 0 else -1, remap[nd.b] if nd.b >= 0 else -1, nd.val, nd.lit, nd.arg, nd.idx))
+        remap[q] = len(merged) - 1
+    post_m = list(post) + [False] * len(need)
+    nb = len(outs)
+    mult_cols = [j for j, o in enumerate(outs) if any(st.node == o and st.out >= 1 for st in primal.stores)]   # multiplier outputs
+    rnd = random.Random(seed)
+    samples = []
+    for _ in range(n_points):
+        args = [[rnd.uniform(-1.0, 1.0) for _ in range(sz)] for sz in primal.in_sizes]
+        samples.append(_eval_nodes(merged, args))
+    for flips in itertools.product((1, -1), repeat=len(mult_cols)):   # sign convention of the multipliers
+        colsg = [1] * nb
+        for j, f in zip(mult_cols, flips):
+            colsg[j] = f
+        Kp = [[(remap[e[0]], e[1] * colsg[j]) if e else None for j, e in enumerate(row)] for row in dKp]
+        rows = [[sum((Kp[i][j][1] * v[Kp[i][j][0]] * v[outs[j]]) for j in range(nb) if Kp[i][j]) for v in samples] for i in range(nb)]
+        beta: List[Optional[int]] = []
+        sign: List[int] = []
+        ok = True
+        for i in range(nb):
+            if all(abs(r) < 1e-9 for r in rows[i]):
+                beta.append(None)
+                sign.append(1)
+                continue
+            hit = None
+            for bnode in beta_nodes:
+                for sg in (1, -1):
+                    if all(abs(sg * v[bnode] - r) <= 1e-8 * max(1.0, abs(r)) for v, r in zip(samples, rows[i])):
+                        hit = (bnode, sg)
+            if hit is None:
+                ok = False
+                break
+            beta.append(hit[0])
+            sign.append(hit[1])
+        if ok and sorted(b for b in beta if b is not None) == sorted(beta_nodes):
+            # fold the row signs into the matrix so that  K' out = beta  holds with +beta
+            Kp = [[(e[0], e[1] * sign[i]) if e else None for e in Kp[i]] for i in range(nb)]
+            return post_m, outs, beta, Kp, merged
+    raise RuntimeError(f"{primal.name}: the system matrix of {donor.name} does not reproduce its right-hand side")
+
+
+def symmetric_form(nodes: List[Node], in_sizes: List[int], Kp, n_points: int = 2, seed: int = 11):
     """Row permutation `perm` and row signs `sg` such that  diag(sg) * Kp[perm, :]  is symmetric with its non-zero diagonal
     entries (the mass-matrix block) first - or None.  Decided numerically at random inputs."""
     import numpy as np
@@ -263,8 +336,8 @@ def symmetric_form(primal: SXFunction, Kp, n_points: int = 2, seed: int = 11):
     rnd = random.Random(seed)
     mats = []
     for _ in range(n_points):
-        args = [[rnd.uniform(-1.0, 1.0) for _ in range(sz)] for sz in primal.in_sizes]
-        v = _eval_nodes(primal.nodes, args)
+        args = [[rnd.uniform(-1.0, 1.0) for _ in range(sz)] for sz in in_sizes]
+        v = _eval_nodes(nodes, args)
         mats.append(np.array([[(Kp[i][j][1] * v[Kp[i][j][0]] if Kp[i][j] else 0.0) for j in range(nb)] for i in range(nb)]))
 
     def close(a, b):
@@ -442,13 +515,13 @@ def _copier(B: "Builder", pn: List[Node]):
     return copy
 
 
-def structured_primal(primal: SXFunction, use_ldlt: bool = True) -> SXFunction:
+def structured_primal(primal: SXFunction, use_ldlt: bool = True, donor: Optional[SXFunction] = None) -> SXFunction:
     """The primal function with its symbolic QR solve replaced by an LDL^T solve of the identified system  K z = beta
     (same value up to rounding; ~2.2x fewer operations).  Used for the rollouts on the device."""
-    post, outs, beta, Kp = identify_system(primal)
+    post, outs, beta, Kp, nodes = identify_system(primal, donor=donor)
     nb = len(beta)
     B = Builder()
-    copy = _copier(B, primal.nodes)
+    copy = _copier(B, nodes)
 
     def kentry(e):
         if e is None:
@@ -456,8 +529,8 @@ def structured_primal(primal: SXFunction, use_ldlt: bool = True) -> SXFunction:
         c = copy(e[0])
         return c if e[1] > 0 else B.neg(c)
     K = [[kentry(Kp[i][j]) for j in range(nb)] for i in range(nb)]
-    solve = make_solver(B, K, symmetric_form(primal, Kp) if use_ldlt else None)
-    z = solve([copy(b) for b in beta])
+    solve = make_solver(B, K, symmetric_form(nodes, primal.in_sizes, Kp) if use_ldlt else None)
+    z = solve([copy(b) if b is not None else None for b in beta])
     out_index = {o: k for k, o in enumerate(outs)}
     stores: List[Store] = []
     zero_id: Optional[int] = None
@@ -472,11 +545,10 @@ def structured_primal(primal: SXFunction, use_ldlt: bool = True) -> SXFunction:
     return _finish(B, primal, stores)
 
 
-def implicit_jacobian(primal: SXFunction, par: SXFunction, use_ldlt: bool = True) -> SXFunction:
+def implicit_jacobian(primal: SXFunction, par: SXFunction, use_ldlt: bool = True, donor: Optional[SXFunction] = None) -> SXFunction:
     """A drop-in replacement for `par` (same inputs, outputs, sparsity, store list) derived from `primal` by implicit
     differentiation of its linear solve.  par.out[k] must be d primal.out[k // n_in] / d in[k % n_in]."""
-    post, outs, beta, Kp = identify_system(primal)
-    pn = primal.nodes
+    post, outs, beta, Kp, pn = identify_system(primal, donor=donor)
     nb = len(beta)
     B = Builder()
 
@@ -540,9 +612,9 @@ def implicit_jacobian(primal: SXFunction, par: SXFunction, use_ldlt: bool = True
         c = copy(e[0])
         return c if e[1] > 0 else B.neg(c)
     K = [[kentry(Kp[i][j]) for j in range(nb)] for i in range(nb)]
-    solve = make_solver(B, K, symmetric_form(primal, Kp) if use_ldlt else None)
+    solve = make_solver(B, K, symmetric_form(pn, primal.in_sizes, Kp) if use_ldlt else None)
 
-    z = solve([copy(b) for b in beta])
+    z = solve([copy(b) if b is not None else None for b in beta])
     out_index = {o: k for k, o in enumerate(outs)}
 
     # ---- one solve per input direction that is asked for -----------------------------------
@@ -557,7 +629,7 @@ def implicit_jacobian(primal: SXFunction, par: SXFunction, use_ldlt: bool = True
         if d not in dz:
             rhs = []
             for i in range(nb):
-                acc = tangent(beta[i], d)
+                acc = tangent(beta[i], d) if beta[i] is not None else None
                 for j in range(nb):
                     if Kp[i][j] is None:
                         continue

@@ -70,6 +70,12 @@ template <int ROW, int COL>
 __device__ __forceinline__ void imp_par_out(double* __restrict__ rec, int j, double v) {
     if (ROW >= 7) REC_AT(R_AB(ROW - 7, COL - 2)) = v;
 }
+template <int E0, int R0, int C0, int R1, int C1, int R2, int C2, int R3, int C3>
+__device__ __forceinline__ void imp_par_out4(double* __restrict__ rec, double v0, double v1, double v2, double v3) {
+    static_assert((E0 & 3) == 0 && R_AB(R0 - 7, C0 - 2) == E0 && R_AB(R1 - 7, C1 - 2) == E0 + 1 && R_AB(R2 - 7, C2 - 2) == E0 + 2 &&
+                  R_AB(R3 - 7, C3 - 2) == E0 + 3, "codegen/gen_all.py: imp_record_element disagrees with the record layout");
+    st_quad(rec + E0, v0, v1, v2, v3);
+}
 
 // The Jacobian bodies come in the generator-allocated form (codegen/regalloc.py: a fixed file of FP64 register
 // variables + an explicit volatile local spill array with Belady eviction and software prefetch); inputs are read
@@ -93,7 +99,10 @@ __device__ __forceinline__ void dyn_par(const double* __restrict__ st, size_t es
 }
 #endif
 #undef SX_OUT
+#undef SX_OUT4
 #define SX_OUT(k, nz, row, col, v) imp_par_out<row, col>(rec, j, v)
+#define SX_OUT4(e0, k0, n0, r0, c0, v0, k1, n1, r1, c1, v1, k2, n2, r2, c2, v2, k3, n3, r3, c3, v3) \
+    imp_par_out4<e0, r0, c0, r1, c1, r2, c2, r3, c3>(rec, v0, v1, v2, v3)
 #if LIN_CLS == 3
 __device__ __forceinline__ void imp_par(const double* __restrict__ st, size_t es, double* __restrict__ rec, int j, volatile double* sx_sm) {
 #include "gen/Imp_F_par_ra.inc"
