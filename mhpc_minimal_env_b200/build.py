@@ -29,18 +29,17 @@ FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xptxas", "-v
 # resident 128-thread blocks per SM the Jacobian kernels are compiled for (register cap = 65536 / (128 * LIN_MINBLOCKS))
 LIN_MINBLOCKS = int(os.environ.get("MHPC_LIN_MINBLOCKS", "2"))
 
-LIN_EXTRA = os.environ.get("MHPC_LIN_EXTRA", "").split()
-BWS_EXTRA = os.environ.get("MHPC_BWS_EXTRA", "").split()   # dev: extra nvcc flags for the backward sweep   # dev: extra nvcc flags for the Jacobian kernel classes
-FL_OPT = os.environ.get("MHPC_LIN_FL_OPT", "O1")          # ptxas level for the flight-knot Jacobian (12 k nodes)
-FL_MINBLOCKS = int(os.environ.get("MHPC_LIN_FL_MINBLOCKS", str(LIN_MINBLOCKS)))
+LIN_EXTRA = os.environ.get("MHPC_LIN_EXTRA", "").split()   # dev: extra nvcc flags for the Jacobian kernel classes
+BWS_EXTRA = os.environ.get("MHPC_BWS_EXTRA", "").split()   # dev: extra nvcc flags for the backward sweep
+# ptxas level for the Jacobian kernels: -O1 keeps the generator's instruction order and register allocation (the bodies
+# come pre-allocated by codegen/regalloc.py); higher levels re-schedule them
+LIN_OPT = os.environ.get("MHPC_LIN_OPT", "O1")
 
 
 def _lin_flags(c):
     if c >= 5:
         return []
-    if c == 2:
-        return (["-Xptxas", "-O1"] if FL_OPT == "O1" else []) + [f"-DLIN_MINBLOCKS={FL_MINBLOCKS}"] + LIN_EXTRA
-    return ["-Xptxas", "-O1", f"-DLIN_MINBLOCKS={LIN_MINBLOCKS}"] + LIN_EXTRA
+    return ["-Xptxas", "-" + LIN_OPT, f"-DLIN_MINBLOCKS={LIN_MINBLOCKS}"] + LIN_EXTRA
 
 
 # (source, object name, extra defines)
@@ -91,7 +90,7 @@ def build(ref: str = "/root/reference", force: bool = False, verbose: bool = Tru
     srcs += [os.path.join(GEN, f) for f in os.listdir(GEN) if f.endswith(".inc")]
     srcs += [os.path.join(HERE, "..", "include", "mhpc_b200.h"), os.path.abspath(__file__)]
     stamp = os.path.join(OBJ, "stamp.txt")
-    dig = _digest(srcs) + f":mb{LIN_MINBLOCKS}:{FL_OPT}:{FL_MINBLOCKS}:{os.environ.get('MHPC_RA_CAP', '')}:{os.environ.get('MHPC_RA_LOOKAHEAD', '')}:{os.environ.get('MHPC_RA_WINDOW', '')}:{os.environ.get('MHPC_SHARE_RCP', '')}:{os.environ.get('MHPC_RA_SMEM', '')}:{os.environ.get('MHPC_RA_FAR', '')}:{os.environ.get('MHPC_LIN_EXTRA', '')}:{os.environ.get('MHPC_BWS_EXTRA', '')}"
+    dig = _digest(srcs) + f":mb{LIN_MINBLOCKS}:{LIN_OPT}:{os.environ.get('MHPC_RA_CAP', '')}:{os.environ.get('MHPC_RA_LOOKAHEAD', '')}:{os.environ.get('MHPC_RA_WINDOW', '')}:{os.environ.get('MHPC_SHARE_RCP', '')}:{os.environ.get('MHPC_RA_SMEM', '')}:{os.environ.get('MHPC_RA_FAR', '')}:{os.environ.get('MHPC_LIN_EXTRA', '')}:{os.environ.get('MHPC_BWS_EXTRA', '')}"
     if not force and os.path.exists(LIB) and os.path.exists(stamp) and open(stamp).read() == dig:
         if verbose:
             print(f"[build] up to date: {LIB}")
