@@ -682,7 +682,12 @@ int mhpc_batch_solve(mhpc_batch* b, int sync_early_exit) {
     const Dev& d = b->d;
     cudaStream_t s = b->stream;
     const int maxAL = (int)std::floor(b->opt.max_AL_iter), maxDDP = (int)std::floor(b->opt.max_DDP_iter);
-    EpsList zero{}; zero.n = 1; zero.eps[0] = 0.0;
+    // forward_sweep(0) runs as `nfs` identical trials of step size 0: a lane group of four shares the shared-memory staging
+    // of the nominal trajectory and gains, which is faster (1.25 ms) than 32 instances per warp each reading in place
+    // (1.8 ms); trial slot 0 is the one that is used, slots 1.. are scratch that the next line search overwrites
+    const int nfs = std::min(d.W, 4);
+    EpsList zero{}; zero.n = nfs;
+    for (int t = 0; t < nfs; ++t) zero.eps[t] = 0.0;
     b->launches = 0;
     for (auto& e : b->evs) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
     b->evs.clear();
@@ -693,7 +698,7 @@ int mhpc_batch_solve(mhpc_batch* b, int sync_early_exit) {
         { Stage st(b, TB_OTHER); launch_al_begin(d, b->opt, s); b->launches++; }
         if (join_copy(b)) return -1;
         { Stage st(b, TB_ROLLOUT);                                   // forward_sweep(0): rollout ...
-          launch_rollout(d, b->c, b->opt, MASK_RUNNING, 1, 0, zero, s);
+          launch_rollout(d, b->c, b->opt, MASK_RUNNING, nfs, 0, zero, s);
           launch_accept_slot0(d, MASK_RUNNING, 2, s); b->launches += 2; }
         if (linearize(b, MASK_RUNNING)) return -1;                   // ... and its derivatives
         { Stage st(b, TB_OTHER); if (fork_copy_nominal(b, MASK_RUNNING)) return -1; }   // update_nominal_trajectory

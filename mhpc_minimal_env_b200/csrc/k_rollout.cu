@@ -235,8 +235,12 @@ void launch_rollout(const Dev& d, const Consts& c, const Opt& opt, int mask_mode
     const int inst_per_block = threads / ns;
     const unsigned blocks = (unsigned)((d.npad + inst_per_block - 1) / inst_per_block);
     const size_t smem = (size_t)inst_per_block * RO_DEPTH * RO_STAGE * sizeof(double);
-    if (n_slots == 8) {
+    if (n_slots == 8) {          // the lane-group sizes of the usual line-search widths are compile-time constants
         k_rollout<true, 8><<<blocks, threads, smem, s>>>(d, c, opt, mask_mode, ns, n_slots, trial0, eps);
+    } else if (n_slots == 4) {
+        k_rollout<true, 4><<<blocks, threads, smem, s>>>(d, c, opt, mask_mode, ns, n_slots, trial0, eps);
+    } else if (n_slots == 2) {
+        k_rollout<true, 2><<<blocks, threads, smem, s>>>(d, c, opt, mask_mode, ns, n_slots, trial0, eps);
     } else if (n_slots > 1) {
         k_rollout<true, 0><<<blocks, threads, smem, s>>>(d, c, opt, mask_mode, ns, n_slots, trial0, eps);
     } else {   // one trial per instance: nothing to share, every lane reads its own instance in place

@@ -9,8 +9,10 @@ n = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
 b = m.BatchedMHPC([to_gpu_problem(s) for s in make_specs(n, 2)], m.default_option(DDP_thresh=-1.0, AL_thresh=-1.0))
 b.initialization(); b.solve(); b.synchronize()
 hist = collections.defaultdict(collections.Counter)
+hfit = collections.defaultdict(collections.Counter)
 for i in range(n):
     for k, r in enumerate(b.records(i)):
         hist[k][r["n_bws"]] += 1
+        hfit[k][r["n_fit"]] += 1
 for k in sorted(hist):
-    print("iteration", k, dict(sorted(hist[k].items())), flush=True)
+    print("iteration", k, "n_bws", dict(sorted(hist[k].items())), "n_fit", dict(sorted(hfit[k].items())), flush=True)
