@@ -20,7 +20,7 @@ for k, v in agg.most_common(20):
     L.append(f"| `{k[:60]}` | {cnt[k]} | {v:.2f} | {100*v/tot:.1f} % |")
 d = json.load(open(os.path.join(ROOT, "profiles", "r1_bench_end_of_round.json")))
 st = d["stage_ms"]; t = st["total_ms"]
-L += ["", "`k_lin grid (32, 79, 1)` (two kernels) = back/front-stance Jacobian knots `k_lin<BS>`, `k_lin<FS>`; `(32, 198, 1)` = flight knots `k_lin<FL>`; `(32, 1, 1)` (two kernels) = impact Jacobians at the two touchdowns (side stream in a real run); `(32, 362, 1)` = light knots (rigid-body + stance-terminal). `k_rollout<1, 8>` = 8-trial line-search rollouts (staged through shared memory), `k_rollout<1, 0>` = the 2-trial remainder, `k_rollout<0, 0>` = single-slot forward sweeps. `k_copy_nominal` runs on a side stream underneath `k_lin`/`k_bws` in a real run.",
+L += ["", "`k_lin grid (32, 79, 1)` (two kernels) = back/front-stance Jacobian knots `k_lin<BS>`, `k_lin<FS>`; `(32, 198, 1)` = flight knots `k_lin<FL>`; `(32, 1, 1)` (two kernels) = impact Jacobians at the two touchdowns (side stream in a real run); `(32, 362, 1)` = light knots (rigid-body + stance-terminal). `k_rollout<1, 4>` = 4-trial launches (line-search chunks and the forward sweeps, which run as four identical trials), `k_rollout<1, 2>` = the 2-trial remainder of the line search; all staged through shared memory. `k_copy_nominal` runs on a side stream underneath `k_lin`/`k_bws` in a real run.",
       f"Shares agree with the CUDA-event stage buckets bench.py reports (`stage_ms` of `profiles/r1_bench_end_of_round.json`, {t:.1f} ms per solve: backward sweep {100*st['bws_ms']/t:.0f} %, line search {100*st['linesearch_ms']/t:.0f} %, linearise {100*st['linearize_ms']/t:.0f} %, forward sweeps {100*st['rollout_ms']/t:.0f} %, rest {100*st['other_ms']/t:.0f} %)."]
 open(os.path.join(ROOT, "profiles", "r1_launches_summary.md"), "w").write("\n".join(L) + "\n")
 print("\n".join(L[4:14]))
