@@ -85,7 +85,9 @@ enum mhpc_field {
 void mhpc_default_option(mhpc_hsddp_option* o);          /* struct defaults of MHPC_CompoundTypes.h:196-212 */
 void mhpc_default_problem(mhpc_problem* p);              /* MHPC_CompoundTypes.h:242-251, Gait.h:21-26, MHPCLocomotion.cpp:37-39, test_main.cpp:23-28 */
 /* MHPCLocomotion<double>::MHPCLocomotion (MHPCLocomotion.cpp:8-43), for n instances on CUDA device `device`.
- * ls_width = number of line-search step sizes evaluated concurrently (<= 16; 0 -> 8). */
+ * ls_width = number of line-search step sizes evaluated concurrently per launch (<= 16; 0 -> 8).  The outcome does not
+ * depend on it (first acceptable step size in order, MultiPhaseDDP.cpp:132-148); 8 suits small batches, 4 is faster from
+ * a few thousand instances on (the trial rollouts then compete for the FP64 pipe; bench.py uses 4). */
 int mhpc_batch_create(int n_instances, const mhpc_hsddp_option* opt, int device, int ls_width, mhpc_batch** out);
 void mhpc_batch_destroy(mhpc_batch* b);                  /* MHPCLocomotion::~MHPCLocomotion (:383-470) */
 const char* mhpc_last_error(void);
