@@ -544,7 +544,8 @@ int mhpc_batch_initialization(mhpc_batch* b) {
     CK(cudaMemsetAsync(d.Kfb, 0, (size_t)d.KT * KDIM * d.npad * sizeof(double), b->stream));
     CK(cudaMemsetAsync(d.dufb, 0, (size_t)d.KT * 4 * d.npad * sizeof(double), b->stream));
     CK(cudaMemsetAsync(d.Gv, 0, (size_t)d.KT * 14 * d.npad * sizeof(double), b->stream));
-    CK(cudaMemsetAsync(d.lin, 0, (size_t)d.npad * d.KT * REC * sizeof(double), b->stream));
+    // (the knot records `lin` - more than half of the footprint - are not reset: every record of a used knot is written in
+    //  full by the linearisation before the sweep reads it, and no kernel or getter reads the record of an unused knot)
     launch_setup(d, b->c, b->stream);                 // build_problem: references + AL/ReB parameters
     launch_warmstart(d, b->c, b->stream);             // warmstart()
     launch_copy_nominal(d, MASK_ALL, b->stream);      // update_nominal_trajectory()
