@@ -248,14 +248,14 @@ def _oracle_cost_sensitivity(spec, optkw, rel=1e-12, trials=4):
     return sens
 
 
-def _batch_vs_oracle(n, cfg, optkw=None, check_every=1, scale=1.0):
+def _batch_vs_oracle(n, cfg, optkw=None, check_every=1, scale=1.0, ls_width=8):
     """BASELINE config sizes: iteration counts / regularisation / accepted step sizes bit-exact for every checked instance."""
     import multiprocessing as mp
     import os
     import mhpc_minimal_env_b200 as m
     optkw = optkw or {}
     specs = make_specs(n, cfg, scale)
-    gpu = m.BatchedMHPC([to_gpu_problem(s) for s in specs], m.default_option(**optkw))
+    gpu = m.BatchedMHPC([to_gpu_problem(s) for s in specs], m.default_option(**optkw), ls_width=ls_width)
     gpu.initialization()
     gpu.solve()
     res = gpu.results()
@@ -304,6 +304,13 @@ def test_large_perturbations_counts_bit_exact(cfg):
     """Initial states perturbed three times as far as in the BASELINE workload (more regularisation retries, later
     line-search trials, aborts if any): 256 instances, integer traces bit-exact against the oracle."""
     _batch_vs_oracle(256, cfg, scale=3.0)
+
+
+def test_bench_workload_sampled_against_oracle():
+    """Exactly what bench.py times (4096 instances of config 2, fixed 2x3 HSDDP iterations, four line-search trials per
+    launch): every 64th instance is solved by the CPU oracle too - integer traces bit-exact, costs to 1e-6."""
+    _, res = _batch_vs_oracle(4096, 2, optkw=dict(DDP_thresh=-1.0, AL_thresh=-1.0), check_every=64, ls_width=4)
+    assert all(r["n_records"] == 6 for r in res)
 
 
 def test_full_size_properties_4096():
