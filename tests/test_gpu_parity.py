@@ -293,10 +293,10 @@ def test_config2_1024_instances_bit_exact_counts():
 
 
 @pytest.mark.parametrize("cfg", [3, 4])
-def test_full_size_sampled_instances_bit_exact_counts(cfg):
+def test_full_size_every_instance_bit_exact_counts(cfg):
     """BASELINE configs[2] and [3] at their full size (4096 instances: all-whole-body horizon; varied WB/RB splits and gait
-    timings): every 128th instance is solved by the CPU oracle too - integer traces bit-exact, costs to 1e-6."""
-    _batch_vs_oracle(4096, cfg, check_every=128)
+    timings): EVERY instance is solved by the CPU oracle too - integer traces bit-exact, costs to 1e-6 (10-20 s each)."""
+    _batch_vs_oracle(4096, cfg, check_every=1)
 
 
 @pytest.mark.parametrize("cfg", [2, 4])
@@ -306,10 +306,10 @@ def test_large_perturbations_counts_bit_exact(cfg):
     _batch_vs_oracle(256, cfg, scale=3.0)
 
 
-def test_bench_workload_sampled_against_oracle():
+def test_bench_workload_every_instance_against_oracle():
     """Exactly what bench.py times (4096 instances of config 2, fixed 2x3 HSDDP iterations, four line-search trials per
-    launch): every 64th instance is solved by the CPU oracle too - integer traces bit-exact, costs to 1e-6."""
-    _, res = _batch_vs_oracle(4096, 2, optkw=dict(DDP_thresh=-1.0, AL_thresh=-1.0), check_every=64, ls_width=4)
+    launch): every instance is solved by the CPU oracle too - integer traces bit-exact, costs to 1e-6."""
+    _, res = _batch_vs_oracle(4096, 2, optkw=dict(DDP_thresh=-1.0, AL_thresh=-1.0), check_every=1, ls_width=4)
     assert all(r["n_records"] == 6 for r in res)
 
 
