@@ -91,6 +91,14 @@ void mhpc_default_problem(mhpc_problem* p);              /* MHPC_CompoundTypes.h
 int mhpc_batch_create(int n_instances, const mhpc_hsddp_option* opt, int device, int ls_width, mhpc_batch** out);
 void mhpc_batch_destroy(mhpc_batch* b);                  /* MHPCLocomotion::~MHPCLocomotion (:383-470) */
 const char* mhpc_last_error(void);
+/* sizes / field offsets (declaration order) of the structs above as this library was compiled, so that a binding in
+ * another language can verify its mirror: which = 0 option, 1 problem, 2 result, 3 iter_record; returns the field count */
+int mhpc_sizeof_option(void);
+int mhpc_sizeof_problem(void);
+int mhpc_sizeof_result(void);
+int mhpc_sizeof_iter_record(void);
+int mhpc_sizeof_timing(void);
+int mhpc_struct_offsets(int which, int* out, int capacity);
 int mhpc_batch_set_option(mhpc_batch* b, const mhpc_hsddp_option* opt);   /* MultiPhaseDDP::set_option, MultiPhaseDDP.h:22 */
 /* Use the caller's CUDA stream (e.g. torch's current stream) for all work of this handle; NULL = own stream.
    (A solve forks two short pieces of work onto handle-private side streams and joins them back with events; ordering
@@ -108,7 +116,10 @@ int mhpc_batch_initialization(mhpc_batch* b);
 int mhpc_batch_set_initial_condition(mhpc_batch* b, const double* x0);
 /* MHPCLocomotion::update_problem (MHPCLocomotion.cpp:107-158): the receding-horizon shift - phase buffers of each
  * model group rotate by one, the gait advances one mode, every phase is re-initialised, the reference is regenerated
- * from the current x0.  (Never called by the reference's main, but part of its class; parity is checked against it.) */
+ * from the current x0.  (Never called by the reference's main, but part of its class; parity is checked against it.)
+ * The derivative records (the reference also rotates dynpar / rcost / tcost) are NOT rotated: every solve and every
+ * forward_sweep / forward_sweep_partials_only rewrites them before a backward sweep reads them; calling
+ * mhpc_batch_backward_sweep directly after update_problem without one of those is not supported. */
 int mhpc_batch_update_problem(mhpc_batch* b);
 
 /* ---- MultiPhaseDDP<double> entry points, batched (all instances in lock step) -------------------- */
@@ -127,8 +138,9 @@ int mhpc_batch_update_AL_ReB_param(mhpc_batch* b);                       /* Mult
  * sync_early_exit != 0 lets the host poll an "any instance still running" counter once per outer iteration. */
 int mhpc_batch_solve(mhpc_batch* b, int sync_early_exit);
 /* MHPCLocomotion::solve_mhpc end to end from HOST buffers: upload problems, initialization, solve,
- * download results (+ optional execution bag: nominal x,u,y and K,du of the first `exec_phases` phases,
- * MHPCLocomotion.cpp:178-194; pass NULL / 0 to skip). */
+ * download results (+ optional execution bag, MHPCLocomotion.cpp:178-194: nominal x,u,y and K,du of the knots of the
+ * first min(exec_phases, n_wbphase) whole-body phases - the reference copies 2 - up to exec_knots knots per instance,
+ * rows beyond an instance's execution horizon are zero; pass NULL / 0 to skip). */
 int mhpc_batch_solve_host(mhpc_batch* b, const mhpc_problem* problems, mhpc_result* results,
                           int exec_phases, double* exec_state /* [n][exec_knots][22] */, double* exec_gain /* [n][exec_knots][60] */,
                           int exec_knots);
@@ -149,9 +161,18 @@ int mhpc_batch_get_phase_params(mhpc_batch* b, int instance, int phase, double* 
  * caller-provided DEVICE buffer (for an NCCL gather across ranks); returns npad. */
 int mhpc_batch_results_to_device(mhpc_batch* b, double* dev_out, int capacity_doubles);
 
-/* ---- standalone evaluation of the generated functions on the device (Jacobian parity) ------------ */
-/* name: "Dyn_BS", "Dyn_BS_par", "Imp_F_par", ... ; inputs/outputs are host arrays of n evaluations,
- * evaluation-major ([n][size]); outputs dense column-major with structural zeros written as 0. */
+/* ---- standalone evaluation of the generated functions on the device (Jacobian parity) ------------
+ * Replaces the reference's CasADi C ABI `int F(const double** arg, double** res, long long* iw, double* w, int mem)`
+ * (CasadiGen/header/Dyn_BS.h:15-30 and siblings) together with the adaptor casadi_interface (CasadiGen.cpp:4-79), batched:
+ *   "Dyn_BS" "Dyn_FS" "Dyn_FL"              (x[14], u[4])                    -> xdot[14], y[4]
+ *   "Dyn_BS_par" "Dyn_FS_par" "Dyn_FL_par"  (x[14], u[4])                    -> Ac[14x14], Bc[14x4], C[4x14], D[4x4]
+ *   "Imp_F" "Imp_B"                         (x[14])                          -> x+[14], impulse[4]
+ *   "Imp_F_par" "Imp_B_par"                 (x[14])                          -> Px[14x14]
+ *   "FBDynamics" / "FBDynamics_par"         (x[6], u[4], foothold[4], c[2])  -> xdot[6] / Ac[6x6], Bc[6x4]
+ *   "WB_FL1_terminal_constr" / "WB_FL2_..." (x[14])                          -> h[1], hx[14], hxx[14x14]
+ *   "Jacob_F" "Jacob_B"                     (x[14])                          -> J[2x7]
+ * inputs/outputs are host arrays of n evaluations, evaluation-major ([n][size]); outputs dense column-major with
+ * structural zeros written as 0 (the adaptor's scatter into pre-zeroed Eigen storage). */
 int mhpc_eval_function(const char* name, int n, int device, const double* in0, const double* in1, const double* in2,
                        const double* in3, double* out0, double* out1, double* out2, double* out3);
 
@@ -159,6 +180,12 @@ int mhpc_eval_function(const char* name, int n, int device, const double* in0, c
 typedef struct mhpc_timing { float total_ms, rollout_ms, linearize_ms, bws_ms, linesearch_ms, other_ms; int n_launches; } mhpc_timing;
 int mhpc_batch_enable_timing(mhpc_batch* b, int on);
 int mhpc_batch_get_timing(mhpc_batch* b, mhpc_timing* t);
+/* diagnostic: for every inner-iteration record r and every attempt a of its backward sweep (the regularisation ladder of
+ * MultiPhaseDDP.cpp:209-227) the backward step at which the attempt stopped: it + 1 when Quu failed the positive-definite
+ * test at backward step `it` (0 = the last knot's predecessor), -1 when the attempt passed, 0 when it was not made.
+ * out = [n][rows] ints, rows = the return value (= record slots x 24 attempts). */
+int mhpc_batch_enable_bws_trace(mhpc_batch* b, int on);
+int mhpc_batch_get_bws_trace(mhpc_batch* b, int* out);
 /* run `reps` linearisation launches back to back and return the average ms per launch (CUDA events) */
 int mhpc_batch_time_kernel(mhpc_batch* b, int which /*0 linearize group, 1 backward sweep, 2 one rollout chunk, 10+c linearisation knot class c (0 BS,1 FS,2 FL,3 IMPF,4 IMPB,5 light)*/, int reps, float* ms_per_launch);
 /* FP64 FMA peak probe on this device (TFLOP/s), used as the roofline denominator for the linearisation */

@@ -59,7 +59,8 @@ EXPORTS = [
     "mhpc_batch_get_results", "mhpc_batch_get_records", "mhpc_batch_get_scalars", "mhpc_batch_n_phases",
     "mhpc_batch_get_schedule", "mhpc_batch_get_field", "mhpc_batch_get_phase_params", "mhpc_batch_results_to_device",
     "mhpc_eval_function", "mhpc_batch_enable_timing", "mhpc_batch_get_timing", "mhpc_batch_time_kernel",
-    "mhpc_measure_fp64_peak", "mhpc_batch_device_bytes",
+    "mhpc_measure_fp64_peak", "mhpc_batch_device_bytes", "mhpc_batch_enable_bws_trace", "mhpc_batch_get_bws_trace",
+    "mhpc_sizeof_option", "mhpc_sizeof_problem", "mhpc_sizeof_result", "mhpc_sizeof_iter_record", "mhpc_sizeof_timing", "mhpc_struct_offsets",
 ]
 
 _lib = None
@@ -103,12 +104,25 @@ def load():
     L.mhpc_batch_get_phase_params.argtypes = [vp, C.c_int, C.c_int, dp]
     L.mhpc_batch_results_to_device.argtypes = [vp, vp, C.c_int]
     L.mhpc_eval_function.argtypes = [C.c_char_p, C.c_int, C.c_int] + [dp] * 8
+    L.mhpc_batch_enable_bws_trace.argtypes = [vp, C.c_int]
+    L.mhpc_batch_get_bws_trace.argtypes = [vp, ip]
     L.mhpc_batch_enable_timing.argtypes = [vp, C.c_int]
     L.mhpc_batch_get_timing.argtypes = [vp, C.POINTER(Timing)]
     L.mhpc_batch_time_kernel.argtypes = [vp, C.c_int, C.c_int, C.POINTER(C.c_float)]
     L.mhpc_measure_fp64_peak.argtypes = [C.c_int, dp]
     L.mhpc_batch_device_bytes.argtypes = [vp]
     L.mhpc_batch_device_bytes.restype = C.c_longlong
+    L.mhpc_struct_offsets.argtypes = [C.c_int, ip, C.c_int]
+    # the mirrors above must have the layout the library was compiled with
+    for which, (cls, szfn) in enumerate(((HSDDPOption, L.mhpc_sizeof_option), (Problem, L.mhpc_sizeof_problem), (Result, L.mhpc_sizeof_result),
+                                         (IterRecord, L.mhpc_sizeof_iter_record))):
+        offs = (C.c_int * 32)()
+        nf = L.mhpc_struct_offsets(which, offs, 32)
+        mine = [getattr(cls, f).offset for f, _ in cls._fields_]
+        if C.sizeof(cls) != szfn() or nf != len(mine) or list(offs[:nf]) != mine:
+            raise RuntimeError(f"ctypes mirror of {cls.__name__} does not match libmhpc_b200.so (sizeof {C.sizeof(cls)} vs {szfn()})")
+    if C.sizeof(Timing) != L.mhpc_sizeof_timing():
+        raise RuntimeError("ctypes mirror of Timing does not match libmhpc_b200.so")
     _lib = L
     return L
 
@@ -264,6 +278,15 @@ class BatchedMHPC:
     # ---- measurement ----
     def enable_timing(self, on: bool = True): self._ck(self.L.mhpc_batch_enable_timing(self.h, int(on)))
 
+    def enable_bws_trace(self, on: bool = True): self._ck(self.L.mhpc_batch_enable_bws_trace(self.h, int(on)))
+
+    def bws_trace(self, max_rec: int = 64, att: int = 24) -> np.ndarray:
+        """[n, record, attempt]: backward step + 1 at which the attempt failed, -1 passed, 0 not made."""
+        out = np.zeros((self.n, max_rec * att), dtype=np.int32)
+        rows = self._ck(self.L.mhpc_batch_get_bws_trace(self.h, out.ctypes.data_as(C.POINTER(C.c_int))))
+        assert rows == max_rec * att, rows
+        return out.reshape(self.n, max_rec, att)
+
     def timing(self) -> dict:
         t = Timing()
         self._ck(self.L.mhpc_batch_get_timing(self.h, C.byref(t)))
@@ -280,6 +303,9 @@ class BatchedMHPC:
 _EVAL_SHAPES = {
     "Dyn_BS": ([14, 4], [(14, 1), (4, 1)]), "Dyn_FS": ([14, 4], [(14, 1), (4, 1)]), "Dyn_FL": ([14, 4], [(14, 1), (4, 1)]),
     "Imp_F": ([14], [(14, 1), (4, 1)]), "Imp_B": ([14], [(14, 1), (4, 1)]),
+    "Dyn_BS_par": ([14, 4], [(14, 14), (14, 4), (4, 14), (4, 4)]), "Dyn_FS_par": ([14, 4], [(14, 14), (14, 4), (4, 14), (4, 4)]),
+    "Dyn_FL_par": ([14, 4], [(14, 14), (14, 4), (4, 14), (4, 4)]),
+    "Imp_F_par": ([14], [(14, 14)]), "Imp_B_par": ([14], [(14, 14)]),
     "FBDynamics": ([6, 4, 4, 2], [(6, 1)]), "FBDynamics_par": ([6, 4, 4, 2], [(6, 6), (6, 4)]),
     "WB_FL1_terminal_constr": ([14], [(1, 1), (1, 14), (14, 14)]), "WB_FL2_terminal_constr": ([14], [(1, 1), (1, 14), (14, 14)]),
     "Jacob_F": ([14], [(2, 7)]), "Jacob_B": ([14], [(2, 7)]),
@@ -287,7 +313,8 @@ _EVAL_SHAPES = {
 
 
 def eval_function(name: str, *args, device: int = 0):
-    """Evaluate one of the light generated functions for a batch of inputs ([n, size] arrays) on the device."""
+    """Evaluate one of the generated functions (CasADi C ABI of the reference, CasadiGen/header/*.h) for a batch of
+    inputs ([n, size] arrays) on the device; dense outputs [n, rows, cols]."""
     L = load()
     ins, outs = _EVAL_SHAPES[name]
     a = [np.ascontiguousarray(np.asarray(x, dtype=np.float64)) for x in args]

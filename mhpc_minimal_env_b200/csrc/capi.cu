@@ -3,6 +3,7 @@
 // per-instance control flow kept on the device.  No CPU arithmetic of the hot path lives here.
 #include <algorithm>
 #include <cmath>
+#include <cstddef>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -20,6 +21,7 @@ double measure_fp64_peak_tflops(int device);
 }
 using namespace mhpc;
 
+extern "C" int mhpc_batch_enable_bws_trace(mhpc_batch* b, int on);
 static thread_local std::string g_err;
 static int fail(const std::string& m) { g_err = m; return -1; }
 #define CK(call)                                                                                         \
@@ -79,6 +81,9 @@ struct mhpc_batch {
     bool keep_dead_partials = false;
     void* rot_tmp = nullptr;
     size_t rot_bytes = 0;
+    bool want_bws_trace = false;     // diagnostic: where each attempt of the backward sweep stopped
+    int* bws_trace_buf = nullptr;
+    size_t bws_trace_cap = 0;
 };
 
 static void fill_opt(Opt& o, const mhpc_hsddp_option& s) {
@@ -93,6 +98,17 @@ static void fill_eps(EpsList& e, double alpha) {   // MultiPhaseDDP.cpp:132-148
     e.n = 0;
     while (eps > std::pow(0.1, 10) && e.n < MAX_TRIALS) { e.eps[e.n++] = eps; eps *= alpha; }
     for (int i = e.n; i < MAX_TRIALS; ++i) e.eps[i] = 0;
+}
+// Options the device path cannot follow the reference on are refused instead of silently truncated: the reference's
+// line search runs `while (eps > 1e-10) ... eps *= alpha` (MultiPhaseDDP.cpp:132-148), i.e. forever for alpha >= 1 and
+// more than MAX_TRIALS step sizes for alpha above ~0.62.
+static int check_option(const mhpc_hsddp_option& o) {
+    if (!(o.alpha > 0.0 && o.alpha < 1.0)) return fail("option: alpha must be in (0, 1) (the reference's line search does not terminate otherwise, MultiPhaseDDP.cpp:132-148)");
+    int n = 0;
+    for (double eps = 1; eps > std::pow(0.1, 10); eps *= o.alpha) if (++n > MAX_TRIALS) break;
+    if (n > MAX_TRIALS) return fail("option: alpha gives more than " + std::to_string((int)MAX_TRIALS) + " line-search step sizes above 1e-10; not supported");
+    if (!(o.max_AL_iter >= 0 && o.max_DDP_iter >= 0) || o.max_AL_iter * o.max_DDP_iter > 1e6) return fail("option: bad iteration limits");
+    return 0;
 }
 static void fill_consts(Consts& c) {
     const double PI = MHPC_PI;
@@ -186,6 +202,35 @@ extern "C" {
 
 const char* mhpc_last_error(void) { return g_err.c_str(); }
 
+// layout of the ABI structs as this library was compiled (a binding checks its mirror against these)
+int mhpc_sizeof_option(void) { return (int)sizeof(mhpc_hsddp_option); }
+int mhpc_sizeof_problem(void) { return (int)sizeof(mhpc_problem); }
+int mhpc_sizeof_result(void) { return (int)sizeof(mhpc_result); }
+int mhpc_sizeof_iter_record(void) { return (int)sizeof(mhpc_iter_record); }
+int mhpc_sizeof_timing(void) { return (int)sizeof(mhpc_timing); }
+int mhpc_struct_offsets(int which, int* out, int cap) {
+#define OFF(T, f) (int)offsetof(T, f)
+    std::vector<int> v;
+    switch (which) {
+        case 0: v = {OFF(mhpc_hsddp_option, alpha), OFF(mhpc_hsddp_option, gamma), OFF(mhpc_hsddp_option, update_penalty), OFF(mhpc_hsddp_option, update_relax),
+                     OFF(mhpc_hsddp_option, update_regularization), OFF(mhpc_hsddp_option, update_ReB), OFF(mhpc_hsddp_option, max_DDP_iter),
+                     OFF(mhpc_hsddp_option, max_AL_iter), OFF(mhpc_hsddp_option, DDP_thresh), OFF(mhpc_hsddp_option, AL_thresh),
+                     OFF(mhpc_hsddp_option, AL_active), OFF(mhpc_hsddp_option, ReB_active), OFF(mhpc_hsddp_option, smooth_active)}; break;
+        case 1: v = {OFF(mhpc_problem, n_wbphase), OFF(mhpc_problem, n_fbphase), OFF(mhpc_problem, dt_wb), OFF(mhpc_problem, dt_fb), OFF(mhpc_problem, cmode),
+                     OFF(mhpc_problem, groundH), OFF(mhpc_problem, vel), OFF(mhpc_problem, height), OFF(mhpc_problem, roll), OFF(mhpc_problem, pitch),
+                     OFF(mhpc_problem, yaw), OFF(mhpc_problem, gait_mode), OFF(mhpc_problem, gait_timing), OFF(mhpc_problem, x0)}; break;
+        case 2: v = {OFF(mhpc_result, cost), OFF(mhpc_result, exp_cost_change), OFF(mhpc_result, viol), OFF(mhpc_result, status), OFF(mhpc_result, iter_AL),
+                     OFF(mhpc_result, n_records), OFF(mhpc_result, pad)}; break;
+        case 3: v = {OFF(mhpc_iter_record, iter_AL), OFF(mhpc_iter_record, iter_DDP), OFF(mhpc_iter_record, n_bws), OFF(mhpc_iter_record, n_fit),
+                     OFF(mhpc_iter_record, reg), OFF(mhpc_iter_record, eps), OFF(mhpc_iter_record, cost), OFF(mhpc_iter_record, exp_cost_change),
+                     OFF(mhpc_iter_record, viol), OFF(mhpc_iter_record, cost_prev)}; break;
+        default: return fail("mhpc_struct_offsets: which = 0 option, 1 problem, 2 result, 3 iter_record");
+    }
+#undef OFF
+    for (size_t k = 0; k < v.size() && (int)k < cap; ++k) out[k] = v[k];
+    return (int)v.size();
+}
+
 void mhpc_default_option(mhpc_hsddp_option* o) {
     o->alpha = 0.1; o->gamma = 0.01; o->update_penalty = 8; o->update_relax = 0.1; o->update_regularization = 2;
     o->update_ReB = 7; o->max_DDP_iter = 3; o->max_AL_iter = 2; o->DDP_thresh = 1e-03; o->AL_thresh = 1e-03;
@@ -205,14 +250,17 @@ void mhpc_default_problem(mhpc_problem* p) {
 
 int mhpc_batch_create(int n, const mhpc_hsddp_option* opt, int device, int ls_width, mhpc_batch** out) {
     if (n <= 0 || !opt || !out) return fail("mhpc_batch_create: bad arguments");
+    if (check_option(*opt)) return -1;
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail("mhpc_batch_create: no CUDA device (the hot path has no CPU fallback)");
     if (device < 0 || device >= ndev) return fail("mhpc_batch_create: bad device index");
     CK(cudaSetDevice(device));
+    cudaStream_t st = nullptr;
+    CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
     mhpc_batch* b = new mhpc_batch();
     b->n = n; b->device = device;
-    b->W = ls_width <= 0 ? 8 : std::min(ls_width, (int)MAX_TRIALS);
-    CK(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking));
+    b->W = ls_width <= 0 ? 8 : std::min(ls_width, (int)MAX_W);
+    b->stream = st;
     fill_opt(b->opt, *opt);
     fill_eps(b->eps, b->opt.alpha);
     fill_consts(b->c);
@@ -227,6 +275,7 @@ void mhpc_batch_destroy(mhpc_batch* b) {
     free_all(b);
     if (b->stage) cudaFree(b->stage);
     if (b->rot_tmp) cudaFree(b->rot_tmp);
+    if (b->bws_trace_buf) cudaFree(b->bws_trace_buf);
     if (b->d_user_of) cudaFree(b->d_user_of);
     if (b->side) { cudaStreamDestroy(b->side); cudaEventDestroy(b->ev_fork); cudaEventDestroy(b->ev_join); }
     if (b->side2) { cudaStreamDestroy(b->side2); cudaEventDestroy(b->ev_cfork); cudaEventDestroy(b->ev_cjoin); }
@@ -235,10 +284,22 @@ void mhpc_batch_destroy(mhpc_batch* b) {
     delete b;
 }
 int mhpc_batch_set_option(mhpc_batch* b, const mhpc_hsddp_option* opt) {
+    if (!b || !opt) return fail("set_option: bad arguments");
+    if (check_option(*opt)) return -1;
     fill_opt(b->opt, *opt);
     fill_eps(b->eps, b->opt.alpha);
     if (b->have_problems) {
         CK(cudaSetDevice(b->device));
+        // one iteration record per inner iteration: grow the record arrays with the iteration budget (never dropped silently)
+        const int need_rec = (int)std::floor(b->opt.max_AL_iter) * (int)std::floor(b->opt.max_DDP_iter);
+        if (need_rec > b->d.max_rec) {
+            CK(cudaStreamSynchronize(b->stream));
+            Dev& d = b->d;
+            d.max_rec = need_rec;
+            if (dalloc(b, &d.rec_i, (size_t)d.max_rec * REC_I * d.npad) || dalloc(b, &d.rec_d, (size_t)d.max_rec * REC_D * d.npad)) return -1;
+            CK(cudaMemsetAsync(d.si + (size_t)SI_N_REC * d.npad, 0, d.npad * sizeof(int), b->stream));
+            if (b->want_bws_trace && mhpc_batch_enable_bws_trace(b, 1)) return -1;
+        }
         launch_reset_option_state(b->d, b->opt, b->stream);
         CK(cudaGetLastError());
     }
@@ -260,6 +321,7 @@ int mhpc_batch_synchronize(mhpc_batch* b) {
 long long mhpc_batch_device_bytes(mhpc_batch* b) { return b->bytes; }
 
 static int set_problems_slots(mhpc_batch* b, const mhpc_problem* pr);
+
 
 // schedule key of a problem: phase split, then (mode, knot count) per phase - what decides which code a knot runs
 static std::vector<int> schedule_key(const mhpc_problem& q) {
@@ -475,6 +537,7 @@ static int set_problems_slots(mhpc_batch* b, const mhpc_problem* pr) {
     }
     if (upload_scalars()) return -1;
     b->have_problems = true;
+    if (b->want_bws_trace) return mhpc_batch_enable_bws_trace(b, 1);
     return 0;
 }
 
@@ -583,6 +646,7 @@ int mhpc_batch_update_problem(mhpc_batch* b) {
         const size_t bytes = (size_t)d.KT * a.elems * d.npad * sizeof(double);
         CK(cudaMemcpyAsync(tmp, a.p, bytes, cudaMemcpyDeviceToDevice, b->stream));      // rows of unused phases keep their content
         launch_rotate(d, a.p, tmp, a.elems, a.acc, b->stream);
+        CK(cudaGetLastError());   // nothing of the handle's schedule changes unless every rotation was launched
         CK(cudaMemcpyAsync(a.p, tmp, bytes, cudaMemcpyDeviceToDevice, b->stream));      // (for st_act: the accepted rollout becomes slot 0)
     }
     CK(cudaStreamSynchronize(b->stream));
@@ -807,6 +871,7 @@ int mhpc_batch_get_phase_params(mhpc_batch* b, int inst, int phase, double* out9
     if (need(b)) return -1;
     if (inst < 0 || inst >= b->n) return fail("get_phase_params: bad instance");
     inst = SL(b, inst);
+    if (phase < 0 || phase >= b->h_nph[inst]) return fail("get_phase_params: bad phase");
     const Dev& d = b->d;
     CK(cudaMemcpy2DAsync(out9, sizeof(double), d.par + par_idx(d, phase, 0, inst), (size_t)d.npad * sizeof(double), sizeof(double), NPAR,
                          cudaMemcpyDeviceToHost, b->stream));
@@ -963,13 +1028,14 @@ int mhpc_batch_get_field(mhpc_batch* b, int inst, int phase, int field, double* 
 }
 
 // execution bag (MHPCLocomotion.cpp:178-194): nominal x,u,y and K,du of the leading knots, instance-major
-__global__ void k_gather_exec(Dev d, const int* __restrict__ user_of, int kn, double* st_out, double* gain_out) {
+__global__ void k_gather_exec(Dev d, const int* __restrict__ user_of, int kn, int exec_phases, double* st_out, double* gain_out) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= d.n) return;
     const int u = user_of ? user_of[i] : i;   // output row: the caller's instance order
-    const int k = blockIdx.y;   // k-th used knot of the horizon -> knot slot (phase blocks of KSTRIDE)
+    const int k = blockIdx.y;   // k-th knot of the execution horizon -> knot slot (phase blocks of KSTRIDE)
     int kk = -1, c = k;
-    for (int p = 0; p < d.n_phases[i]; ++p) {
+    const int np_exec = min(exec_phases, d.n_wb[i]);   // whole-body phases only (ms_exec / CTG_exec are WB-typed, MHPCLocomotion.cpp:178-194)
+    for (int p = 0; p < np_exec; ++p) {
         const int N = d.ph_N[ph_idx(d, p, i)];
         if (c < N) { kk = p * KSTRIDE + c; break; }
         c -= N;
@@ -1031,7 +1097,7 @@ int mhpc_batch_solve_host(mhpc_batch* b, const mhpc_problem* problems, mhpc_resu
     double* dgn = exec_gain && kn ? (double*)(base + need_res + need_st) : nullptr;
     const int* uo = b->permuted ? b->d_user_of : nullptr;
     if (results) k_results_pack<<<(b->n + 127) / 128, 128, 0, b->stream>>>(d, uo, dres);
-    if (kn && (dst || dgn)) { dim3 g((b->n + 127) / 128, kn); k_gather_exec<<<g, 128, 0, b->stream>>>(d, uo, kn, dst, dgn); }
+    if (kn && (dst || dgn)) { dim3 g((b->n + 127) / 128, kn); k_gather_exec<<<g, 128, 0, b->stream>>>(d, uo, kn, exec_phases, dst, dgn); }
     if (results) CK(cudaMemcpyAsync(results, dres, need_res, cudaMemcpyDeviceToHost, b->stream));
     if (dst) CK(cudaMemcpyAsync(exec_state, dst, need_st, cudaMemcpyDeviceToHost, b->stream));
     if (dgn) CK(cudaMemcpyAsync(exec_gain, dgn, need_gn, cudaMemcpyDeviceToHost, b->stream));
@@ -1042,8 +1108,47 @@ int mhpc_batch_solve_host(mhpc_batch* b, const mhpc_problem* problems, mhpc_resu
 
 int mhpc_eval_function(const char* name, int n, int device, const double* in0, const double* in1, const double* in2,
                        const double* in3, double* o0, double* o1, double* o2, double* o3) {
+    if (!name || n <= 0 || !in0 || !o0) return fail("mhpc_eval_function: bad arguments");
+    {   // the five Jacobian functions (CasadiGen/header/Dyn_BS_par.h ..., adaptor CasadiGen.cpp:4-79): the bodies the
+        // linearisation kernels run, evaluated standalone: (x[14], u[4]) -> Ac 14x14, Bc 14x4, C 4x14, D 4x4; x -> Px 14x14
+        typedef void (*pe_fn)(int, size_t, const double*, double*, double*, double*, double*, cudaStream_t);
+        static const struct { const char* nm; pe_fn fn; bool dyn; } par[5] = {
+            {"Dyn_BS_par", launch_par_eval_BS, true}, {"Dyn_FS_par", launch_par_eval_FS, true}, {"Dyn_FL_par", launch_par_eval_FL, true},
+            {"Imp_F_par", launch_par_eval_IMPF, false}, {"Imp_B_par", launch_par_eval_IMPB, false}};
+        for (const auto& pf : par) {
+            if (std::strcmp(name, pf.nm)) continue;
+            if (pf.dyn && (!in1 || !o1 || !o2 || !o3)) return fail("mhpc_eval_function: Dyn_*_par takes (x, u) and returns (Ac, Bc, C, D)");
+            CK(cudaSetDevice(device));
+            const size_t es = ((size_t)n + 31) / 32 * 32;
+            std::vector<double> soa(18 * es, 0.0);
+            for (int t = 0; t < n; ++t) {
+                for (int e = 0; e < 14; ++e) soa[(size_t)e * es + t] = in0[(size_t)t * 14 + e];
+                if (pf.dyn) for (int e = 0; e < 4; ++e) soa[(size_t)(14 + e) * es + t] = in1[(size_t)t * 4 + e];
+            }
+            const size_t osz[4] = {196, pf.dyn ? 56u : 0u, pf.dyn ? 56u : 0u, pf.dyn ? 16u : 0u};
+            double* hout[4] = {o0, o1, o2, o3};
+            double *din = nullptr, *dout[4] = {nullptr, nullptr, nullptr, nullptr};
+            CK(cudaMalloc(&din, soa.size() * sizeof(double)));
+            CK(cudaMemcpy(din, soa.data(), soa.size() * sizeof(double), cudaMemcpyHostToDevice));
+            for (int q = 0; q < 4; ++q) {
+                if (!osz[q]) continue;
+                CK(cudaMalloc(&dout[q], (size_t)n * osz[q] * sizeof(double)));
+                CK(cudaMemset(dout[q], 0, (size_t)n * osz[q] * sizeof(double)));   // structural zeros (CasadiGen.cpp:58-66 writes non-zeros only)
+            }
+            pf.fn(n, es, din, dout[0], dout[1], dout[2], dout[3], 0);
+            CK(cudaGetLastError());
+            CK(cudaDeviceSynchronize());
+            for (int q = 0; q < 4; ++q) {
+                if (!osz[q]) continue;
+                CK(cudaMemcpy(hout[q], dout[q], (size_t)n * osz[q] * sizeof(double), cudaMemcpyDeviceToHost));
+                cudaFree(dout[q]);
+            }
+            cudaFree(din);
+            return 0;
+        }
+    }
     const int fn = eval_fn_id(name);
-    if (fn < 0) return fail(std::string("mhpc_eval_function: '") + name + "' is evaluated through the linearisation path (get_field A/B/C/D/PX)");
+    if (fn < 0) return fail(std::string("mhpc_eval_function: unknown function '") + name + "'");
     CK(cudaSetDevice(device));
     const int isz[11][4] = {{14, 4, 0, 0}, {14, 4, 0, 0}, {14, 4, 0, 0}, {14, 0, 0, 0}, {14, 0, 0, 0}, {6, 4, 4, 2}, {6, 4, 4, 2}, {14, 0, 0, 0}, {14, 0, 0, 0}, {14, 0, 0, 0}, {14, 0, 0, 0}};
     const int osz[11][4] = {{14, 4, 0, 0}, {14, 4, 0, 0}, {14, 4, 0, 0}, {14, 4, 0, 0}, {14, 4, 0, 0}, {6, 0, 0, 0}, {36, 24, 0, 0}, {1, 14, 196, 0}, {1, 14, 196, 0}, {14, 0, 0, 0}, {14, 0, 0, 0}};
@@ -1065,6 +1170,37 @@ int mhpc_eval_function(const char* name, int n, int device, const double* in0, c
     return 0;
 }
 
+int mhpc_batch_enable_bws_trace(mhpc_batch* b, int on) {
+    b->want_bws_trace = on != 0;
+    if (!b->have_problems) return 0;
+    CK(cudaSetDevice(b->device));
+    Dev& d = b->d;
+    if (!on) { d.bws_trace = nullptr; return 0; }
+    const size_t cnt = (size_t)d.max_rec * BWS_TRACE_ATT * d.npad;
+    if (b->bws_trace_cap < cnt) {
+        CK(cudaStreamSynchronize(b->stream));
+        if (b->bws_trace_buf) cudaFree(b->bws_trace_buf);
+        CK(cudaMalloc(&b->bws_trace_buf, cnt * sizeof(int)));
+        b->bws_trace_cap = cnt;
+    }
+    CK(cudaMemsetAsync(b->bws_trace_buf, 0, cnt * sizeof(int), b->stream));
+    d.bws_trace = b->bws_trace_buf;
+    return 0;
+}
+int mhpc_batch_get_bws_trace(mhpc_batch* b, int* out) {
+    if (need(b)) return -1;
+    const Dev& d = b->d;
+    if (!d.bws_trace) return fail("get_bws_trace: call mhpc_batch_enable_bws_trace first");
+    const size_t rows = (size_t)d.max_rec * BWS_TRACE_ATT;
+    std::vector<int> tmp(rows * d.npad);
+    CK(cudaMemcpyAsync(tmp.data(), d.bws_trace, tmp.size() * sizeof(int), cudaMemcpyDeviceToHost, b->stream));
+    CK(cudaStreamSynchronize(b->stream));
+    for (int u = 0; u < b->n; ++u) {
+        const int i = SL(b, u);
+        for (size_t r = 0; r < rows; ++r) out[(size_t)u * rows + r] = tmp[r * d.npad + i];
+    }
+    return (int)rows;
+}
 int mhpc_batch_enable_timing(mhpc_batch* b, int on) { b->timing = on != 0; return 0; }
 int mhpc_batch_get_timing(mhpc_batch* b, mhpc_timing* t) { *t = b->last; return 0; }
 

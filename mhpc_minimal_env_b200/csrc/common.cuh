@@ -21,7 +21,8 @@ constexpr int MAXP = 16;          // phases per instance (reference default 8)
 constexpr int KSTRIDE = 110;      // knot slots per phase = N_TIMESTEPS_MAX (MHPC_CPPTypes.h:9): phase p owns knots [p*110, p*110 + N_p),
                                   // exactly like the reference's per-phase arrays, so the receding-horizon buffer rotation
                                   // (MHPCLocomotion.cpp:107-158) moves whole blocks including their stale tails
-constexpr int MAX_TRIALS = 16;    // line-search step sizes (reference: 10)
+constexpr int MAX_TRIALS = 48;    // line-search step sizes: eps = alpha^t > 1e-10 (reference default alpha = 0.1: 10; alpha = 0.6: 46)
+constexpr int MAX_W = 16;         // trial rollouts evaluated side by side (slots of st_act)
 constexpr int NPAR = 9;           // per-phase AL/ReB parameters
 
 // ---- record element indices -------------------------------------------------------------
@@ -102,7 +103,24 @@ struct Dev {
     int* rec_i;      // [max_rec][REC_I][npad]
     double* rec_d;   // [max_rec][REC_D][npad]
     int* n_active;   // [1] device counter for optional host early exit
+    // optional diagnostic (mhpc_batch_enable_bws_trace): per (iteration record, attempt) the backward step at which the
+    // attempt of the backward sweep stopped: it + 1 if Quu was not positive definite at backward step `it`, -1 = passed
+    int* bws_trace;  // [max_rec][BWS_TRACE_ATT][npad] or null
+    // regularisation-ladder scheduler of the backward sweep (k_bws.cu: k_lad_plan / k_lad_resolve / k_lad_copy); null = off
+    int lad_cap;          // task capacity = lane groups (8 lanes each) that are resident at once on this GPU
+    int* lad_cnt;         // [LAD_CNT_N]
+    int* lad_unres;       // [npad] the instance has no passing rung yet in this sweep
+    int* lad_rung;        // [npad] next rung (0-based attempt index of this sweep) to test
+    int* lad_t_inst;      // [cap] task -> instance slot (-1: idle)
+    int* lad_t_rung;      // [cap] in: rung of the task; out: the rung that passed, -1 if none
+    double* lad_t_reg;    // [cap] in: regularisation of the task's rung; out: of the rung that passed
+    double* lad_t_dv;     // [cap] out: expected cost change of the passing sweep
+    int* lad_u_inst;      // [cap] compact list of the unresolved instances of this round
+    int* lad_u_copy;      // [cap] per unresolved instance: task whose scratch outputs are its result (-1: none / already in place)
+    double *lad_K, *lad_du, *lad_G;   // outputs of the speculative tasks, [KT][56 | 4 | 14][cap] (task-indexed columns)
 };
+enum { LAD_N_TASKS = 0, LAD_N_UNRES, LAD_STRIDE, LAD_S, LAD_CNT_N };
+constexpr int BWS_TRACE_ATT = 24;   // the ladder 0, 1e-3, 2e-3, ... exceeds 1000 at the 22nd attempt
 
 __host__ __device__ inline size_t st_idx(const Dev& d, int kk, int e, int i) { return ((size_t)kk * ST + e) * d.npad + i; }
 __host__ __device__ inline size_t act_idx(const Dev& d, int w, int kk, int e, int i) {

@@ -300,32 +300,55 @@ __device__ __forceinline__ double wb_terminal_row(int l, const double* buf, doub
     return buf[R_PHIX + l] + gnext;
 }
 
-__global__ void __launch_bounds__(BWS_THREADS, BWS_MINBLOCKS) k_bws(Dev d, Consts c, Opt opt, int mask_mode, int single_attempt) {
+// Work assignment.  task_mode == 0: lane group q4 of block b owns instance 4 b + q4, enters with the instance's current
+// regularisation and walks the ladder reg <- max(reg * update_regularization, 1e-3) inside the kernel (at most
+// `max_attempts` rungs when the ladder scheduler is on: what is left goes to the scheduler's rounds below).
+// task_mode == 1: lane group = one task (instance, rung, regularisation) of the list built by k_lad_plan; tasks that are
+// not the first of their instance write K, du, G into the task-indexed scratch arrays instead of the instance's own.
+__global__ void __launch_bounds__(BWS_THREADS, BWS_MINBLOCKS) k_bws(Dev d, Consts c, Opt opt, int mask_mode, int single_attempt, int task_mode,
+                                                                     int max_attempts) {
     extern __shared__ __align__(16) double smem[];
     const unsigned FULL = 0xffffffffu;
     const int tid = threadIdx.x;
     const int q4 = tid >> 3, m = tid & 7;           // instance slot in the warp, sub-lane
-    const int i = blockIdx.x * BWS_INST + q4;
     double* bufs = smem + (size_t)q4 * BWS_REGION;                     // [2 stages][REC] of my instance
     double* scr = bufs + 2 * REC;
     const size_t es = d.npad;
-    const bool valid = i < d.n;
-    const bool enabled = valid && inst_enabled(d, i, mask_mode);
+    int i = blockIdx.x * BWS_INST + q4, rung = 0, stride = 0;          // rung: 0-based attempt index of this sweep (n_bws = rung + 1)
+    bool valid, enabled, to_scratch = false;
+    double reg;
+    if (!task_mode) {
+        valid = i < d.n;
+        if (!valid) i = 0;
+        enabled = valid && inst_enabled(d, i, mask_mode);
+        reg = enabled ? d.sd[(size_t)SD_REG * es + i] : 0.0;
+    } else {
+        const int nt = d.lad_cnt[LAD_N_TASKS];
+        if (blockIdx.x * BWS_INST >= nt) return;                       // the whole warp is beyond the task list
+        const int ti = i < nt ? d.lad_t_inst[i] : -1;
+        valid = enabled = ti >= 0;
+        reg = valid ? d.lad_t_reg[i] : 0.0;
+        rung = valid ? d.lad_t_rung[i] : 0;
+        stride = d.lad_cnt[LAD_STRIDE];
+        to_scratch = (i % d.lad_cnt[LAD_S]) != 0;
+    }
+    const int task = blockIdx.x * BWS_INST + q4;
+    if (task_mode) i = valid ? d.lad_t_inst[task] : 0;
     const int np = valid ? d.n_phases[i] : 0, nwb = valid ? d.n_wb[i] : 0, nk = enabled ? d.n_knots[i] : 0;
     const double dtw = valid ? d.dt_wb[i] : 0.0, dtf = valid ? d.dt_fb[i] : 0.0;
-    double reg = enabled ? d.sd[(size_t)SD_REG * es + i] : 0.0;
-    int n_bws = 1;
     bool done = !enabled;
     int ktb = max(nk, __shfl_xor_sync(FULL, nk, 8));                   // knots this warp walks
     ktb = max(ktb, __shfl_xor_sync(FULL, ktb, 16));
-    const double* lin_i = d.lin + (size_t)(valid ? i : 0) * d.KT * REC;
+    const double* lin_i = d.lin + (size_t)i * d.KT * REC;
     const bool rowl = m < 7;                                           // this sub-lane owns WB rows m and m + 7
     // lane-constant parts of the output addresses (SoA over instances: the four instances of a warp fill one 32-byte
     // sector per element): only `kk * stride` is added per knot
-    double* const gv_lane = d.Gv + (size_t)m * es + (valid ? i : 0);
-    double* const kf_lane = d.Kfb + (size_t)(4 * m) * es + (valid ? i : 0);
-    double* const du_lane = d.dufb + (size_t)m * es + (valid ? i : 0);
-    const size_t gv_knot = 14 * es, kf_knot = (size_t)KDIM * es, du_knot = 4 * es;
+    const size_t oes = to_scratch ? (size_t)d.lad_cap : es;            // element stride and column of my outputs
+    const size_t ocol = to_scratch ? (size_t)task : (size_t)i;
+    double* const gv_lane = (to_scratch ? d.lad_G : d.Gv) + (size_t)m * oes + ocol;
+    double* const kf_lane = (to_scratch ? d.lad_K : d.Kfb) + (size_t)(4 * m) * oes + ocol;
+    double* const du_lane = (to_scratch ? d.lad_du : d.dufb) + (size_t)m * oes + ocol;
+    const size_t gv_knot = 14 * oes, kf_knot = (size_t)KDIM * oes, du_knot = 4 * oes;
 
     // per-instance schedule walker (phase p, in-phase knot k; knot slot = p*KSTRIDE + k), used both by the prefetcher
     // (one knot ahead) and by the math; it visits the nk used knots from the last one backwards
@@ -360,6 +383,7 @@ __global__ void __launch_bounds__(BWS_THREADS, BWS_MINBLOCKS) k_bws(Dev d, Const
         scr[S_G + m + 8] = 0.0;
         double dV = 0.0;
         bool failed = false;
+        int fail_it = 0;
         Walk wk, wp;
         walk_init(wk); walk_init(wp);
         int& p = wk.p; int& Nn = wk.N; int& mode = wk.mode;
@@ -430,7 +454,7 @@ __global__ void __launch_bounds__(BWS_THREADS, BWS_MINBLOCKS) k_bws(Dev d, Const
                             const double gb = wb_terminal_row(m + 7, buf, last ? 0.0 : scr[S_G + m + 7], Hb);
                             scr[S_G + m] = ga; scr[S_G + m + 7] = gb;
                             gv_lane[(size_t)kk * gv_knot] = ga;
-                            gv_lane[(size_t)kk * gv_knot + 7 * es] = gb;
+                            gv_lane[(size_t)kk * gv_knot + 7 * oes] = gb;
                         }
                     } else if (m < 6) {
                         double gv = last ? 0.0 : scr[S_G + m];
@@ -621,17 +645,17 @@ __global__ void __launch_bounds__(BWS_THREADS, BWS_MINBLOCKS) k_bws(Dev d, Const
                 const bool ok = value_update<14, true>(on, rw, m, scr, quxa, quxb, qxa, qxb, Ha, Hb, opt.quu_shift, ka, kb, du, goa, gob, dvs);
                 if (on) {   // (no hand-over needed here or after the stores: S_G is not read by value_update, and the next reader
                             //  of anything written below sits behind the __syncwarp at the top of the knot loop)
-                    if (!ok) failed = true;
+                    if (!ok) { failed = true; fail_it = it; }
                     else {
                         dV += dvs;
                         if (rowl) {
                             scr[S_G + la] = goa; scr[S_G + lb] = gob;
                             gv_lane[(size_t)kk * gv_knot] = goa;
-                            gv_lane[(size_t)kk * gv_knot + 7 * es] = gob;
+                            gv_lane[(size_t)kk * gv_knot + 7 * oes] = gob;
 #pragma unroll
                             for (int cc = 0; cc < 4; ++cc) {
-                                kf_lane[(size_t)kk * kf_knot + (size_t)cc * es] = ka[cc];
-                                kf_lane[(size_t)kk * kf_knot + (size_t)(28 + cc) * es] = kb[cc];
+                                kf_lane[(size_t)kk * kf_knot + (size_t)cc * oes] = ka[cc];
+                                kf_lane[(size_t)kk * kf_knot + (size_t)(28 + cc) * oes] = kb[cc];
                             }
                         }
                         if (m < 4) du_lane[(size_t)kk * du_knot] = du[m];
@@ -720,14 +744,14 @@ __global__ void __launch_bounds__(BWS_THREADS, BWS_MINBLOCKS) k_bws(Dev d, Const
                 __syncwarp();
                 const bool ok = value_update<6, false>(on, rw, m, scr, qux, qux, qx, qx, Ha, Hb, opt.quu_shift, ka, kb, du, gout, gdummy, dvs);
                 if (on) {
-                    if (!ok) failed = true;
+                    if (!ok) { failed = true; fail_it = it; }
                     else {
                         dV += dvs;
                         if (l < 6) {
                             scr[S_G + l] = gout;
                             gv_lane[(size_t)kk * gv_knot] = gout;
 #pragma unroll
-                            for (int cc = 0; cc < 4; ++cc) kf_lane[(size_t)kk * kf_knot + (size_t)cc * es] = ka[cc];
+                            for (int cc = 0; cc < 4; ++cc) kf_lane[(size_t)kk * kf_knot + (size_t)cc * oes] = ka[cc];
                         }
                         if (m < 4) du_lane[(size_t)kk * du_knot] = du[m];
                     }
@@ -741,15 +765,42 @@ __global__ void __launch_bounds__(BWS_THREADS, BWS_MINBLOCKS) k_bws(Dev d, Const
 
         // ---- outcome of the attempt (MultiPhaseDDP.cpp:209-241) ----
         int retry = 0;
+        if (!done && d.bws_trace && m == 0 && rung < BWS_TRACE_ATT) {
+            const int r = d.si[(size_t)SI_N_REC * es + i];
+            if (r < d.max_rec) d.bws_trace[((size_t)r * BWS_TRACE_ATT + rung) * es + i] = failed ? fail_it + 1 : -1;
+        }
         if (!done) {
-            if (single_attempt) {
-                if (m == 0) { d.si[(size_t)SI_BWS_OK * es + i] = failed ? 0 : 1; if (!failed) d.sd[(size_t)SD_DV * es + i] = dV; }
+            if (task_mode) {
+                if (!failed) {
+                    if (m == 0) { d.lad_t_rung[task] = rung; d.lad_t_reg[task] = reg; d.lad_t_dv[task] = dV; }
+                    done = true;
+                } else {
+                    // a chain of the final round goes on with every `stride`-th rung of the ladder until one passes or the
+                    // ladder runs past 1000 (a rung the reference never attempts); single-rung tasks just report
+                    bool more = stride > 0;
+                    double nr = reg;
+                    for (int k = 0; k < stride && more; ++k) { nr = fmax(nr * opt.update_regularization, 1e-03); if (nr > 1000) more = false; }
+                    if (more) { reg = nr; rung += stride; retry = 1; }
+                    else { if (m == 0) d.lad_t_rung[task] = -1; done = true; }
+                }
+            } else if (single_attempt) {
+                if (m == 0) {
+                    d.si[(size_t)SI_BWS_OK * es + i] = failed ? 0 : 1;
+                    if (!failed) d.sd[(size_t)SD_DV * es + i] = dV;
+                    if (d.lad_unres) d.lad_unres[i] = 0;
+                }
                 done = true;
             } else if (failed) {
                 reg = fmax(reg * opt.update_regularization, 1e-03);
-                ++n_bws;
+                ++rung;
                 if (reg > 1000) {
-                    if (m == 0) { d.si[(size_t)SI_STATUS * es + i] = STATUS_REG_ABORT; d.si[(size_t)SI_DDP_ACTIVE * es + i] = 0; d.si[(size_t)SI_N_BWS * es + i] = n_bws; }
+                    if (m == 0) {
+                        d.si[(size_t)SI_STATUS * es + i] = STATUS_REG_ABORT; d.si[(size_t)SI_DDP_ACTIVE * es + i] = 0; d.si[(size_t)SI_N_BWS * es + i] = rung + 1;
+                        if (d.lad_unres) d.lad_unres[i] = 0;
+                    }
+                    done = true;
+                } else if (max_attempts > 0 && rung >= max_attempts) {   // the rest of the ladder goes to the scheduler's rounds
+                    if (m == 0) { d.lad_unres[i] = 1; d.lad_rung[i] = rung; d.si[(size_t)SI_BWS_OK * es + i] = 0; }
                     done = true;
                 } else retry = 1;
             } else {
@@ -759,8 +810,9 @@ __global__ void __launch_bounds__(BWS_THREADS, BWS_MINBLOCKS) k_bws(Dev d, Const
                     double r2 = reg / 20;
                     if (r2 < 1e-06) r2 = 0;
                     d.sd[(size_t)SD_REG * es + i] = r2;
-                    d.si[(size_t)SI_N_BWS * es + i] = n_bws;
+                    d.si[(size_t)SI_N_BWS * es + i] = rung + 1;
                     d.si[(size_t)SI_BWS_OK * es + i] = 1;
+                    if (d.lad_unres) d.lad_unres[i] = 0;
                 }
                 done = true;
             }
@@ -769,9 +821,147 @@ __global__ void __launch_bounds__(BWS_THREADS, BWS_MINBLOCKS) k_bws(Dev d, Const
     }
 }
 
-void launch_bws(const Dev& d, const Consts& c, const Opt& opt, int mask_mode, int single_attempt, cudaStream_t s) {
+// ---- regularisation-ladder scheduler ---------------------------------------------------------------------------------
+// MultiPhaseDDP::solve retries a failed backward sweep with reg <- max(2 reg, 1e-3) until it passes (MultiPhaseDDP.cpp:
+// 209-227).  The ladder is deterministic, so its rungs can be tested side by side: the first rung IN LADDER ORDER that
+// passes is the reference's result whichever order the rungs were evaluated in (no monotonicity is assumed: every rung
+// below the winner is actually run and seen to fail).  A sweep stage is: one launch that walks the first rungs in the
+// kernel (all instances), then rounds of {plan, task launch, resolve, copy} over the instances that still have no passing
+// rung: the plan packs them densely and gives each S = floor(resident lane groups / unresolved instances) consecutive
+// rungs, so the SMs the finished instances left idle test the next rungs in advance.  The last round (and any round with
+// S >= 4) lets each of the S tasks of an instance walk every S-th rung to the end of the ladder, which terminates the stage
+// without a host round trip.  n_bws, the accepted reg and dV are those of the sequential ladder, bit for bit.
+__device__ __forceinline__ double ladder_reg(double reg0, int rung, double upd) {   // regularisation of attempt `rung` of a sweep entered with reg0
+    double r = reg0;
+    for (int k = 0; k < rung; ++k) r = fmax(r * upd, 1e-03);
+    return r;
+}
+
+__global__ void __launch_bounds__(1024) k_lad_plan(Dev d, Opt opt, int mask_mode, int last_round, int smax) {
+    __shared__ int s_scan[1024];
+    const int tid = threadIdx.x;
+    const int per = (d.n + 1023) / 1024;
+    const int lo = min(d.n, tid * per), hi = min(d.n, lo + per);
+    int cnt = 0;
+    for (int i = lo; i < hi; ++i) cnt += (d.lad_unres[i] != 0 && inst_enabled(d, i, mask_mode)) ? 1 : 0;
+    s_scan[tid] = cnt;
+    __syncthreads();
+    for (int off = 1; off < 1024; off <<= 1) {   // inclusive scan: the unresolved instances keep their slot order
+        const int v = tid >= off ? s_scan[tid - off] : 0;
+        __syncthreads();
+        s_scan[tid] += v;
+        __syncthreads();
+    }
+    const int total = s_scan[1023];
+    int cidx = s_scan[tid] - cnt;
+    const int S = total > 0 ? max(1, min(smax, d.lad_cap / total)) : 1;
+    if (tid == 0) {
+        d.lad_cnt[LAD_N_TASKS] = total * S;
+        d.lad_cnt[LAD_N_UNRES] = total;
+        d.lad_cnt[LAD_STRIDE] = (last_round || S >= 4) ? S : 0;
+        d.lad_cnt[LAD_S] = S;
+    }
+    for (int i = lo; i < hi; ++i) {
+        if (!(d.lad_unres[i] != 0 && inst_enabled(d, i, mask_mode))) continue;
+        d.lad_u_inst[cidx] = i;
+        d.lad_u_copy[cidx] = -1;
+        const int r0 = d.lad_rung[i];
+        double reg = ladder_reg(d.sd[(size_t)SD_REG * d.npad + i], r0, opt.update_regularization);
+        for (int sidx = 0; sidx < S; ++sidx) {
+            const int t = cidx * S + sidx;
+            const bool ok = !(reg > 1000);      // rungs past the abort threshold are never attempted (MultiPhaseDDP.cpp:221-226)
+            d.lad_t_inst[t] = ok ? i : -1;
+            d.lad_t_rung[t] = ok ? r0 + sidx : -1;
+            d.lad_t_reg[t] = reg;
+            reg = fmax(reg * opt.update_regularization, 1e-03);
+        }
+        ++cidx;
+    }
+}
+
+__global__ void k_lad_resolve(Dev d, Opt opt) {
+    const int cidx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (cidx >= d.lad_cnt[LAD_N_UNRES]) return;
+    const int S = d.lad_cnt[LAD_S], stride = d.lad_cnt[LAD_STRIDE];
+    const int i = d.lad_u_inst[cidx];
+    const size_t es = d.npad;
+    int best = -1, best_t = -1, tested = 0;
+    for (int sidx = 0; sidx < S; ++sidx) {
+        const int t = cidx * S + sidx;
+        if (d.lad_t_inst[t] < 0) continue;
+        ++tested;
+        const int r = d.lad_t_rung[t];
+        if (r >= 0 && (best < 0 || r < best)) { best = r; best_t = t; }
+    }
+    if (best >= 0) {   // the lowest passing rung: every rung below it was run and failed
+        const double reg = d.lad_t_reg[best_t];
+        d.sd[(size_t)SD_DV * es + i] = d.lad_t_dv[best_t];
+        d.sd[(size_t)SD_REG_USED * es + i] = reg;
+        double r2 = reg / 20;
+        if (r2 < 1e-06) r2 = 0;
+        d.sd[(size_t)SD_REG * es + i] = r2;
+        d.si[(size_t)SI_N_BWS * es + i] = best + 1;
+        d.si[(size_t)SI_BWS_OK * es + i] = 1;
+        d.lad_unres[i] = 0;
+        d.lad_u_copy[cidx] = (best_t % S != 0) ? best_t : -1;
+        return;
+    }
+    const double reg0 = d.sd[(size_t)SD_REG * es + i];
+    int L = d.lad_rung[i] + tested;                    // rungs 0 .. L-1 have failed
+    if (stride > 0) {                                  // the chains ran to the end of the ladder: L = the first rung past 1000
+        L = d.lad_rung[i];
+        double r = ladder_reg(reg0, L, opt.update_regularization);
+        while (!(r > 1000) && L < 64) { r = fmax(r * opt.update_regularization, 1e-03); ++L; }
+    }
+    if (ladder_reg(reg0, L, opt.update_regularization) > 1000 || stride > 0) {   // "Regularization term exceeds maximum value!"
+        d.si[(size_t)SI_STATUS * es + i] = STATUS_REG_ABORT;
+        d.si[(size_t)SI_DDP_ACTIVE * es + i] = 0;
+        d.si[(size_t)SI_N_BWS * es + i] = L + 1;
+        d.lad_unres[i] = 0;
+    } else {
+        d.lad_rung[i] = L;
+    }
+}
+
+// K, du, G of a winner that ran as a speculative task: scratch column -> the instance's own column, exactly the entries a
+// passing sweep writes (step knots: K, du, G; terminal knots: G)
+__global__ void k_lad_copy(Dev d) {
+    const int cidx = blockIdx.y * blockDim.x + threadIdx.x;
+    if (cidx >= d.lad_cnt[LAD_N_UNRES] || cidx >= d.lad_cap) return;
+    const int t = d.lad_u_copy[cidx];
+    if (t < 0) return;
+    const int i = d.lad_u_inst[cidx], kk = blockIdx.x;
+    int p, k;
+    if (!knot_to_phase(d, i, kk, p, k)) return;
+    const int nx = (p < d.n_wb[i]) ? 14 : 6;
+    const bool term = (k == d.ph_N[ph_idx(d, p, i)] - 1);
+    const size_t ces = d.lad_cap, es = d.npad;
+    for (int e = 0; e < nx; ++e) d.Gv[((size_t)kk * 14 + e) * es + i] = d.lad_G[((size_t)kk * 14 + e) * ces + t];
+    if (term) return;
+    for (int e = 0; e < 4 * nx; ++e) d.Kfb[((size_t)kk * KDIM + e) * es + i] = d.lad_K[((size_t)kk * KDIM + e) * ces + t];
+    for (int e = 0; e < 4; ++e) d.dufb[((size_t)kk * 4 + e) * es + i] = d.lad_du[((size_t)kk * 4 + e) * ces + t];
+}
+
+void launch_bws(const Dev& d, const Consts& c, const Opt& opt, int mask_mode, int single_attempt, int max_attempts, cudaStream_t s) {
     cudaFuncSetAttribute(k_bws, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BWS_SMEM);
-    k_bws<<<(d.n + BWS_INST - 1) / BWS_INST, BWS_THREADS, BWS_SMEM, s>>>(d, c, opt, mask_mode, single_attempt);
+    k_bws<<<(d.n + BWS_INST - 1) / BWS_INST, BWS_THREADS, BWS_SMEM, s>>>(d, c, opt, mask_mode, single_attempt, 0, d.lad_unres ? max_attempts : 0);
+}
+// one round of the ladder scheduler: plan -> tasks -> resolve -> copy (4 launches, no host synchronisation)
+void launch_bws_ladder_round(const Dev& d, const Consts& c, const Opt& opt, int mask_mode, int last_round, int smax, cudaStream_t s) {
+    k_lad_plan<<<1, 1024, 0, s>>>(d, opt, mask_mode, last_round, smax);
+    const int tcap = d.npad > d.lad_cap ? d.npad : d.lad_cap;
+    k_bws<<<(tcap + BWS_INST - 1) / BWS_INST, BWS_THREADS, BWS_SMEM, s>>>(d, c, opt, mask_mode, 0, 1, 0);
+    k_lad_resolve<<<(d.n + 127) / 128, 128, 0, s>>>(d, opt);
+    dim3 g(d.KT, (d.lad_cap + 127) / 128);
+    k_lad_copy<<<g, 128, 0, s>>>(d);
+}
+// lane groups of k_bws that are resident at once on this device
+int bws_resident_lane_groups(int device) {
+    int nsm = 0, per_sm = 0;
+    cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, device);
+    cudaFuncSetAttribute(k_bws, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BWS_SMEM);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_bws, BWS_THREADS, BWS_SMEM);
+    return nsm * (per_sm > 0 ? per_sm : 1) * BWS_INST;
 }
 
 }  // namespace mhpc

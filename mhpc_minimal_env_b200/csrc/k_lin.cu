@@ -114,6 +114,39 @@ __device__ __forceinline__ void imp_par(const double* __restrict__ st, size_t es
 #endif
 #undef SX_OUT
 #undef SX_OUT4
+
+// ---- standalone evaluation of the same Jacobian bodies (mhpc_eval_function "Dyn_*_par" / "Imp_*_par"): the CasADi
+// function itself - raw Ac, Bc, C, D (or Px) scattered into dense column-major outputs, the structural zeros left to
+// the caller's memset (CasadiGen.cpp:46-68) - with no Euler step and no knot record in between.
+#if LIN_CLS <= 4
+template <int K, int ROW, int COL>
+__device__ __forceinline__ void ev_out(double* o0, double* o1, double* o2, double* o3, double v) {
+    if (K == 0) o0[ROW + 14 * COL] = v;
+    else if (K == 1) o1[ROW + 14 * COL] = v;
+    else if (K == 2) o2[ROW + 4 * COL] = v;
+    else o3[ROW + 4 * COL] = v;
+}
+#define SX_OUT(k, nz, row, col, v) ev_out<k, row, col>(o0, o1, o2, o3, v)
+#define SX_OUT4(e0, k0, n0, r0, c0, v0, k1, n1, r1, c1, v1, k2, n2, r2, c2, v2, k3, n3, r3, c3, v3) \
+    do { ev_out<k0, r0, c0>(o0, o1, o2, o3, v0); ev_out<k1, r1, c1>(o0, o1, o2, o3, v1);         \
+         ev_out<k2, r2, c2>(o0, o1, o2, o3, v2); ev_out<k3, r3, c3>(o0, o1, o2, o3, v3); } while (0)
+__device__ __forceinline__ void par_eval_body(const double* __restrict__ st, size_t es, double* o0, double* o1, double* o2, double* o3,
+                                              volatile double* sx_sm) {
+#if LIN_CLS == 0
+#include "gen/Dyn_BS_par_ra.inc"
+#elif LIN_CLS == 1
+#include "gen/Dyn_FS_par_ra.inc"
+#elif LIN_CLS == 2
+#include "gen/Dyn_FL_par_ra.inc"
+#elif LIN_CLS == 3
+#include "gen/Imp_F_par_ra.inc"
+#else
+#include "gen/Imp_B_par_ra.inc"
+#endif
+}
+#undef SX_OUT
+#undef SX_OUT4
+#endif
 #undef SX_IN
 #undef SX_SMEM
 
@@ -333,6 +366,19 @@ __global__ void __launch_bounds__(LIN_THREADS, LIN_MINBLOCKS) k_lin(Dev d, Const
 #endif
 }
 
+#if LIN_CLS <= 4
+// inputs in the trajectory layout (element-major, stride es: 14 x then 4 u), one evaluation per thread
+__global__ void __launch_bounds__(LIN_THREADS, LIN_MINBLOCKS) k_par_eval(int n, size_t es, const double* __restrict__ st, double* o0, double* o1,
+                                                                         double* o2, double* o3) {
+    extern __shared__ __align__(16) double sx_smem_base[];
+    volatile double* sx_sm = sx_smem_base + threadIdx.x;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    par_eval_body(st + t, es, o0 + (size_t)t * 196, o1 ? o1 + (size_t)t * 56 : nullptr, o2 ? o2 + (size_t)t * 56 : nullptr,
+                  o3 ? o3 + (size_t)t * 16 : nullptr, sx_sm);
+}
+#endif
+
 }  // anonymous namespace
 
 #if LIN_CLS == 0
@@ -347,6 +393,23 @@ __global__ void __launch_bounds__(LIN_THREADS, LIN_MINBLOCKS) k_lin(Dev d, Const
 #define LIN_LAUNCH launch_lin_IMPB
 #else
 #define LIN_LAUNCH launch_lin_LIGHT
+#endif
+#if LIN_CLS == 0
+#define PAR_EVAL_LAUNCH launch_par_eval_BS
+#elif LIN_CLS == 1
+#define PAR_EVAL_LAUNCH launch_par_eval_FS
+#elif LIN_CLS == 2
+#define PAR_EVAL_LAUNCH launch_par_eval_FL
+#elif LIN_CLS == 3
+#define PAR_EVAL_LAUNCH launch_par_eval_IMPF
+#elif LIN_CLS == 4
+#define PAR_EVAL_LAUNCH launch_par_eval_IMPB
+#endif
+#if LIN_CLS <= 4
+void PAR_EVAL_LAUNCH(int n, size_t es, const double* st, double* o0, double* o1, double* o2, double* o3, cudaStream_t s) {
+    if (LIN_SMEM > 48 * 1024) cudaFuncSetAttribute(k_par_eval, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LIN_SMEM);
+    k_par_eval<<<(n + LIN_THREADS - 1) / LIN_THREADS, LIN_THREADS, LIN_SMEM, s>>>(n, es, st, o0, o1, o2, o3);
+}
 #endif
 
 void LIN_LAUNCH(const Dev& d, const Consts& c, const Opt& opt, int mask_mode, const int* knots, int n_knots, cudaStream_t s) {

@@ -301,9 +301,9 @@ __global__ void k_reb_from_option(Dev d) {
 // (new phase p uses the buffer of old phase p+1, the last one of each group gets the first).  One thread per
 // (knot slot, element, instance); `src`/`dst` are different allocations.  The accepted rollout becomes slot 0.
 __global__ void k_rotate(Dev d, const double* __restrict__ src, double* __restrict__ dst, int elems, int use_acc_slot) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = blockIdx.y * blockDim.x + threadIdx.x;   // rows on grid.x: KT * elems exceeds the 65535 limit of grid.y from 11 phases on
     if (i >= d.n) return;
-    const int row = blockIdx.y;            // dst knot slot * elems + e
+    const int row = blockIdx.x;            // dst knot slot * elems + e
     const int kk = row / elems, e = row - kk * elems;
     const int p = kk / KSTRIDE, k = kk - p * KSTRIDE;
     const int np = d.n_phases[i], nwb = d.n_wb[i];
@@ -385,7 +385,7 @@ void launch_al_end(const Dev& d, const Opt& o, const Consts& c, int mask_mode, i
 void launch_reset_option_state(const Dev& d, const Opt& o, cudaStream_t s) { k_reset_option_state<<<nb(d.n, 128), 128, 0, s>>>(d, o); }
 void launch_reb_from_option(const Dev& d, cudaStream_t s) { k_reb_from_option<<<nb(d.n, 128), 128, 0, s>>>(d); }
 void launch_rotate(const Dev& d, const double* src, double* dst, int elems, int use_acc_slot, cudaStream_t s) {
-    dim3 grid(nb(d.n, 128), d.KT * elems);
+    dim3 grid(d.KT * elems, nb(d.n, 128));
     k_rotate<<<grid, 128, 0, s>>>(d, src, dst, elems, use_acc_slot);
 }
 void launch_spread_last_knot(const Dev& d, cudaStream_t s) {

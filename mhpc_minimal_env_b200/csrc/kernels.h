@@ -56,8 +56,17 @@ void launch_lin_FL(const Dev&, const Consts&, const Opt&, int, const int*, int, 
 void launch_lin_IMPF(const Dev&, const Consts&, const Opt&, int, const int*, int, cudaStream_t);
 void launch_lin_IMPB(const Dev&, const Consts&, const Opt&, int, const int*, int, cudaStream_t);
 void launch_lin_LIGHT(const Dev&, const Consts&, const Opt&, int, const int*, int, cudaStream_t);
+// the same Jacobian bodies evaluated standalone (raw CasADi outputs, dense column-major); st = [18][es] element-major inputs
+void launch_par_eval_BS(int n, size_t es, const double* st, double* o0, double* o1, double* o2, double* o3, cudaStream_t s);
+void launch_par_eval_FS(int n, size_t es, const double* st, double* o0, double* o1, double* o2, double* o3, cudaStream_t s);
+void launch_par_eval_FL(int n, size_t es, const double* st, double* o0, double* o1, double* o2, double* o3, cudaStream_t s);
+void launch_par_eval_IMPF(int n, size_t es, const double* st, double* o0, double* o1, double* o2, double* o3, cudaStream_t s);
+void launch_par_eval_IMPB(int n, size_t es, const double* st, double* o0, double* o1, double* o2, double* o3, cudaStream_t s);
 // backward sweep (k_bws.cu)
-void launch_bws(const Dev& d, const Consts& c, const Opt& o, int mask_mode, int single_attempt, cudaStream_t s);
+// max_attempts > 0 (with the ladder scheduler allocated): stop walking the ladder in the kernel after that many rungs
+void launch_bws(const Dev& d, const Consts& c, const Opt& o, int mask_mode, int single_attempt, int max_attempts, cudaStream_t s);
+void launch_bws_ladder_round(const Dev& d, const Consts& c, const Opt& o, int mask_mode, int last_round, int smax, cudaStream_t s);
+int bws_resident_lane_groups(int device);
 // standalone evaluation of one generated function over a batch (Jacobian parity tests; k_eval.cu)
 int launch_eval(int fn, int n, const double* in0, const double* in1, const double* in2, const double* in3,
                 double* o0, double* o1, double* o2, double* o3, cudaStream_t s);

@@ -50,8 +50,21 @@ def to_orc_problem(spec, **opt):
     return default_problem(**kw)
 
 
+def relerr_rows(a, b, floor_frac=1e-6):
+    """Worst PER-KNOT (per-matrix) norm-relative error of a [N, dim] field: max_k |a_k - b_k|_inf / |b_k|_inf.  A knot whose
+    reference row is (numerically) empty is measured against floor_frac x the largest entry of the whole array instead, so
+    that exact zeros / cancellation rows do not divide by nothing."""
+    a = np.atleast_2d(np.asarray(a, dtype=np.float64))
+    b = np.atleast_2d(np.asarray(b, dtype=np.float64))
+    if a.size == 0:
+        return 0.0
+    glob = float(np.max(np.abs(b)))
+    den = np.maximum(np.max(np.abs(b), axis=1), max(floor_frac * glob, 1e-300))
+    return float(np.max(np.max(np.abs(a - b), axis=1) / den))
+
+
 def relerr(a, b):
-    """norm-relative error max|a-b| / max(|b|_inf, tiny)"""
+    """norm-relative error max|a-b| / max(|b|_inf, tiny) over the WHOLE array (one matrix / one vector)"""
     a = np.asarray(a, dtype=np.float64)
     b = np.asarray(b, dtype=np.float64)
     den = max(np.max(np.abs(b)) if b.size else 0.0, 1e-300)

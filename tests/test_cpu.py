@@ -205,7 +205,18 @@ def test_struct_layouts_and_defaults_match_reference():
     assert list(p.gait_mode) == [1, 2, 3, 4]
     assert np.allclose(list(p.gait_timing), [0.08, 0.1, 0.08, 0.1])
     assert abs(p.x0[0] - 0.0927) < 1e-15 and abs(p.x0[13] - 2.7346) < 1e-15
-    assert ctypes.sizeof(m.Problem) == 176 + 16 or ctypes.sizeof(m.Problem) % 8 == 0
+    # layout: the ctypes mirrors against what the compiled library reports (sizes and every field offset), and against the
+    # layout the header spells out (13 / 14 / 7 / 10 fields; doubles 8-aligned, mhpc_problem = 19 4-byte fields + pad + x0[14])
+    L = m.load()
+    for which, cls, szfn, nfields, size in ((0, m.HSDDPOption, L.mhpc_sizeof_option, 13, 10 * 8 + 3 * 4 + 4), (1, m.Problem, L.mhpc_sizeof_problem, 14, 80 + 14 * 8),
+                                            (2, m.Result, L.mhpc_sizeof_result, 7, 3 * 8 + 4 * 4), (3, m.IterRecord, L.mhpc_sizeof_iter_record, 10, 4 * 4 + 6 * 8)):
+        offs = (ctypes.c_int * 32)()
+        nf = L.mhpc_struct_offsets(which, offs, 32)
+        assert nf == nfields == len(cls._fields_)
+        assert list(offs[:nf]) == [getattr(cls, f).offset for f, _ in cls._fields_], cls.__name__
+        assert ctypes.sizeof(cls) == szfn() == size, (cls.__name__, ctypes.sizeof(cls), szfn(), size)
+    assert ctypes.sizeof(m.Timing) == L.mhpc_sizeof_timing() == 28
+    assert m.Problem.x0.offset == 80 and m.Problem.gait_mode.offset == 44 and m.Problem.gait_timing.offset == 60
 
 
 @pytest.mark.skipif(not os.path.exists(_lib_path()), reason="libmhpc_b200.so not built")

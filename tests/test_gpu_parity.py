@@ -7,7 +7,7 @@ per-iteration cost 1e-6 relative; converged trajectories and feedback gains 1e-5
 import numpy as np
 import pytest
 
-from helpers import make_specs, relerr, to_gpu_problem, to_orc_problem
+from helpers import make_specs, relerr, relerr_rows, to_gpu_problem, to_orc_problem
 
 pytestmark = pytest.mark.gpu
 
@@ -45,6 +45,31 @@ def test_generated_functions_match_reference_objects():
             ref = eval_fn(name, X[i])
             for g, r in zip(got, ref):
                 assert relerr(g[i], r) < TOL_JAC, name
+    # the five Jacobian functions through the C ABI (Dyn_*_par.h / Imp_*_par.h + casadi_interface, CasadiGen.cpp:4-79) at 64
+    # random states against the reference's own compiled objects: every matrix of every evaluation on its own norm
+    worst = {}
+    for name in ("Dyn_BS_par", "Dyn_FS_par", "Dyn_FL_par"):
+        got = m.eval_function(name, X, U)
+        for i in range(n):
+            ref = eval_fn(name, X[i], U[i])
+            for q, (g, r) in enumerate(zip(got, ref)):
+                assert g[i].shape == r.shape
+                if not r.any():
+                    assert not g[i].any(), (name, q)       # C = D = 0 in flight: structurally empty outputs stay exactly zero
+                    continue
+                assert not g[i][r == 0].any(), (name, q)   # structural zeros of the CCS pattern are exact zeros
+                e = relerr(g[i], r)
+                worst[name] = max(worst.get(name, 0.0), e)
+                assert e < TOL_JAC, (name, "output", q, "evaluation", i, e)
+    for name in ("Imp_F_par", "Imp_B_par"):
+        got = m.eval_function(name, X)
+        for i in range(n):
+            ref = eval_fn(name, X[i])
+            e = relerr(got[0][i], ref[0])
+            worst[name] = max(worst.get(name, 0.0), e)
+            assert e < TOL_JAC, (name, i, e)
+            assert np.array_equal(got[0][i][:7, :], np.hstack([np.eye(7), np.zeros((7, 7))]))   # identity block of Px, exact
+    print("worst per-matrix relative error of the Jacobian functions:", {k: "%.2e" % v for k, v in worst.items()})
     xr = rng.normal(size=(n, 6))
     fh = rng.normal(size=(n, 4))
     for ct in ([0.0, 1.0], [1.0, 0.0], [0.0, 0.0]):
@@ -57,8 +82,11 @@ def test_generated_functions_match_reference_objects():
                     assert relerr(g[i], r) < TOL_JAC, name
 
 
-def _cmp_fields(gpu, orc, inst, names, tol, tag, skip_last=False):
+def _cmp_fields(gpu, orc, inst, names, tol, tag, skip_last=False, floor_frac=1e-6):
+    """Every knot's vector / matrix of the named fields against the oracle, each on its OWN norm (helpers.relerr_rows);
+    returns the worst error seen."""
     modes, N, wb = orc.schedule()
+    worst = 0.0
     for p in range(orc.n_phases):
         for nm in names:
             if nm in ("C", "D", "LY", "LYY", "Y_REF") and not wb[p]:
@@ -68,8 +96,10 @@ def _cmp_fields(gpu, orc, inst, names, tol, tag, skip_last=False):
             if skip_last and g.ndim == 2:
                 g, o = g[:-1], o[:-1]
             assert g.shape == o.shape, (tag, p, nm, g.shape, o.shape)
-            e = relerr(g, o)
+            e = relerr_rows(g, o, floor_frac)
+            worst = max(worst, e)
             assert e < tol, (tag, "inst", inst, "phase", p, nm, e)
+    return worst
 
 
 def test_initialization_schedule_reference_warmstart():
@@ -132,7 +162,13 @@ def test_backward_sweep_and_line_search():
         assert bool(ok1[i]) == o.backward_sweep(1e-3)
         s = o.scalars()
         assert abs(sc["exp_cost_change"][i] - s["exp_cost_change"]) <= 1e-7 * abs(s["exp_cost_change"])
-        _cmp_fields(gpu, o, i, ["PX"], TOL_JAC, "impact jacobian") if False else None
+        for p in range(o.n_phases - 1):       # impact Jacobian used by impact_aware_step (MultiPhaseDDP.cpp:316-320)
+            if o.schedule()[2][p]:            # whole-body phases: modes 2 / 4 -> Imp_F_par / Imp_B_par, modes 1 / 3 -> identity
+                px_g = gpu.field(i, p, "PX").reshape(14, 14, order="F")
+                e = relerr(px_g, o.Px(p))
+                assert e < TOL_JAC, ("impact jacobian", i, p, o.schedule()[0][p], e)
+                if o.schedule()[0][p] in (1, 3):
+                    assert np.array_equal(px_g, np.eye(14))
         _cmp_fields(gpu, o, i, ["K", "DU", "G"], 1e-6, "gains", skip_last=False)
     trials = gpu.forward_iteration()
     sc = gpu.scalars()
@@ -169,8 +205,8 @@ def test_solve_default_config_matches_reference_trace():
     orcs[0].initialization()
     _check_solve(gpu, orcs)
     o = orcs[0]
-    _cmp_fields(gpu, o, 0, ["X_NOM", "U_NOM", "Y_NOM"], TOL_TRAJ, "converged trajectory")
-    _cmp_fields(gpu, o, 0, ["K", "DU"], TOL_TRAJ, "feedback gains")
+    _cmp_fields(gpu, o, 0, ["X_NOM", "U_NOM", "Y_NOM"], TOL_TRAJ, "converged trajectory", floor_frac=1e-3)
+    _cmp_fields(gpu, o, 0, ["K", "DU", "G"], TOL_TRAJ, "feedback gains", floor_frac=1e-3)
     for p in range(o.n_phases):
         g, r = gpu.phase_params(0, p), o.phase_params(p)
         assert abs(g["sigma"] - r["sigma"]) <= 1e-12 * max(1.0, abs(r["sigma"]))
@@ -197,6 +233,57 @@ def test_solve_all_wb_and_varied_splits():
         for o in orcs:
             o.initialization()
         _check_solve(gpu, orcs)
+
+
+def _oracle_final(args):
+    """worker: solve one instance with the CPU oracle and return its integer trace + final nominal trajectory and gains"""
+    i, cfg, n = args
+    from oracle.oracle_py import OracleSolver
+    o = OracleSolver(to_orc_problem(make_specs(n, cfg)[i]))
+    o.initialization()
+    o.solve()
+    fields = {nm: [o.field(p, nm) for p in range(o.n_phases)] for nm in ("X_NOM", "U_NOM", "Y_NOM", "K", "DU", "G")}
+    return i, [(r["iter_AL"], r["iter_DDP"], r["n_bws"], r["n_fit"]) for r in o.records()], fields, o.scalars()["cost"]
+
+
+@pytest.mark.parametrize("cfg", [2, 3, 4])
+def test_solved_trajectories_and_gains_64_instances(cfg):
+    """North-star tolerance "converged trajectories and feedback gains within 1e-5" on 64 instances of each of BASELINE
+    configs 2, 3 and 4 (taken evenly from a 1024-instance batch): the final nominal x, u, y, the feedback gains K, the
+    feed-forward du and the value gradient G of EVERY knot of EVERY phase after a full default solve, each knot's
+    vector / matrix on its own norm."""
+    import multiprocessing as mp
+    import os
+    import mhpc_minimal_env_b200 as m
+    n = 1024
+    pick = list(range(3, n, 16))
+    assert len(pick) == 64
+    specs = make_specs(n, cfg)
+    gpu = m.BatchedMHPC([to_gpu_problem(s) for s in specs], m.default_option())
+    gpu.initialization()
+    gpu.solve()
+    with mp.get_context("fork").Pool(min(os.cpu_count() or 1, 16)) as pool:
+        outs = pool.map(_oracle_final, [(i, cfg, n) for i in pick])
+    worst = {}
+    skipped = []
+    for i, trace, fields, cost in outs:
+        rg = gpu.records(i)
+        assert [(r["iter_AL"], r["iter_DDP"], r["n_bws"], r["n_fit"]) for r in rg] == trace, (cfg, i)
+        if np.isnan(cost):
+            skipped.append(i)      # a diverged explicit-Euler rollout is NaN in the reference too (checked by the trace tests)
+            continue
+        for nm, per_phase in fields.items():
+            for p, o in enumerate(per_phase):
+                g = gpu.field(i, p, nm)
+                assert g.shape == o.shape, (cfg, i, p, nm)
+                e = relerr_rows(g, o, 1e-3)
+                if e > worst.get(nm, (0.0,))[0]:
+                    worst[nm] = (e, i, p)
+    print("config", cfg, "worst per-knot relative error over 64 instances:", {k: ("%.2e" % v[0], "inst %d phase %d" % v[1:]) for k, v in worst.items()},
+          "NaN instances skipped:", skipped)
+    assert len(skipped) <= 2
+    for nm, (e, i, p) in worst.items():
+        assert e < TOL_TRAJ, (cfg, nm, e, "instance", i, "phase", p)
 
 
 def test_fixed_iteration_budget_and_early_exit_agree():
@@ -248,8 +335,12 @@ def _oracle_cost_sensitivity(spec, optkw, rel=1e-12, trials=4):
     return sens
 
 
-def _batch_vs_oracle(n, cfg, optkw=None, check_every=1, scale=1.0, ls_width=8):
-    """BASELINE config sizes: iteration counts / regularisation / accepted step sizes bit-exact for every checked instance."""
+def _batch_vs_oracle(n, cfg, optkw=None, check_every=1, scale=1.0, ls_width=8, tag=None):
+    """BASELINE config sizes: iteration counts / regularisation / accepted step sizes bit-exact for every checked instance;
+    per-iteration costs to 1e-6.  The instances that need the ill-conditioning exception (below) are PRINTED with their
+    error and the oracle's own sensitivity, and must be exactly the list committed in
+    tests/golden/ill_conditioned_instances.json under `tag` - the exception cannot grow silently."""
+    import json
     import multiprocessing as mp
     import os
     import mhpc_minimal_env_b200 as m
@@ -281,35 +372,40 @@ def _batch_vs_oracle(n, cfg, optkw=None, check_every=1, scale=1.0, ls_width=8):
                 if sens is None:
                     sens = _oracle_cost_sensitivity(specs[i], optkw)
                     ill.append(i)
+                print("ill-conditioned exception [%s]: instance %d iteration %d: |cost_gpu - cost_cpu| / |cost| = %.3e; the CPU oracle "
+                      "itself moves by %.3e under a 1e-12 relative change of x0" % (tag, i, k, err / abs(b[6]), sens[k] / abs(b[6])))
                 assert err <= sens[k], (i, k, a["cost"], b[6], sens[k])
     assert not bad, (len(bad), bad[:3])
+    golden = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ill_conditioned_instances.json")))
+    print("instances outside 1e-6 on some per-iteration cost [%s]: %s (committed list: %s)" % (tag, sorted(ill), golden["lists"].get(tag, [])))
+    assert sorted(ill) == golden["lists"].get(tag, []), (tag, sorted(ill))
     assert len(ill) <= max(1, n // 256), ill     # the ill-conditioned exception must stay an exception
     return gpu, res
 
 
 def test_config2_1024_instances_bit_exact_counts():
     """BASELINE configs[1]: 1024 instances with perturbed initial states, bit-exact mode/iteration check vs the CPU."""
-    _batch_vs_oracle(1024, 2)
+    _batch_vs_oracle(1024, 2, tag="config2_1024")
 
 
 @pytest.mark.parametrize("cfg", [3, 4])
 def test_full_size_every_instance_bit_exact_counts(cfg):
     """BASELINE configs[2] and [3] at their full size (4096 instances: all-whole-body horizon; varied WB/RB splits and gait
     timings): EVERY instance is solved by the CPU oracle too - integer traces bit-exact, costs to 1e-6 (10-20 s each)."""
-    _batch_vs_oracle(4096, cfg, check_every=1)
+    _batch_vs_oracle(4096, cfg, check_every=1, tag="config%d_4096" % cfg)
 
 
 @pytest.mark.parametrize("cfg", [2, 4])
 def test_large_perturbations_counts_bit_exact(cfg):
     """Initial states perturbed three times as far as in the BASELINE workload (more regularisation retries, later
     line-search trials, aborts if any): 256 instances, integer traces bit-exact against the oracle."""
-    _batch_vs_oracle(256, cfg, scale=3.0)
+    _batch_vs_oracle(256, cfg, scale=3.0, tag="config%d_256_scale3" % cfg)
 
 
 def test_bench_workload_every_instance_against_oracle():
     """Exactly what bench.py times (4096 instances of config 2, fixed 2x3 HSDDP iterations, four line-search trials per
     launch): every instance is solved by the CPU oracle too - integer traces bit-exact, costs to 1e-6."""
-    _, res = _batch_vs_oracle(4096, 2, optkw=dict(DDP_thresh=-1.0, AL_thresh=-1.0), check_every=1, ls_width=4)
+    _, res = _batch_vs_oracle(4096, 2, optkw=dict(DDP_thresh=-1.0, AL_thresh=-1.0), check_every=1, ls_width=4, tag="bench_4096_fixed2x3")
     assert all(r["n_records"] == 6 for r in res)
 
 
@@ -322,7 +418,7 @@ def test_full_size_properties_4096():
     * a sample of the batch agrees with the oracle (counts bit-exact)."""
     import mhpc_minimal_env_b200 as m
     for cfg in (2, 4):
-        gpu, res = _batch_vs_oracle(4096, cfg, check_every=128)
+        gpu, res = _batch_vs_oracle(4096, cfg, check_every=128, tag="config%d_4096_every128" % cfg)
         a1 = gpu.results_array()
         gpu.set_option(m.default_option())   # solve() leaves the option members modified, as in the reference; reset them
         gpu.initialization()
@@ -446,6 +542,7 @@ def test_odd_shapes_and_start_modes():
     gpu.initialization()
     gpu.solve()
     res = gpu.results()
+    worst_cost = worst_traj = 0.0
     for i, s in enumerate(specs):
         o = OracleSolver(to_orc_problem(s))
         o.initialization()
@@ -459,9 +556,11 @@ def test_odd_shapes_and_start_modes():
             if np.isnan(b["cost"]):      # a diverged explicit-Euler rollout is NaN in the reference too: same flow, same NaN
                 assert np.isnan(a["cost"])
                 continue
-            assert abs(a["cost"] - b["cost"]) <= 1e-5 * abs(b["cost"]), (i, variants[i], a["cost"], b["cost"])
+            worst_cost = max(worst_cost, abs(a["cost"] - b["cost"]) / abs(b["cost"]))
+            assert abs(a["cost"] - b["cost"]) <= TOL_COST * abs(b["cost"]), (i, variants[i], a["cost"], b["cost"])
         if not np.isnan(o.scalars()["cost"]):
-            _cmp_fields(gpu, o, i, ["X_NOM", "U_NOM"], 1e-4, "odd shapes trajectory")
+            worst_traj = max(worst_traj, _cmp_fields(gpu, o, i, ["X_NOM", "U_NOM", "Y_NOM", "K", "DU"], TOL_TRAJ, "odd shapes trajectory", floor_frac=1e-3))
+    print("odd shapes: worst relative cost error %.2e, worst per-knot trajectory / gain error %.2e" % (worst_cost, worst_traj))
 
 
 def test_receding_horizon_update_problem():
@@ -478,6 +577,7 @@ def test_receding_horizon_update_problem():
     for o in orcs:
         o.initialization()
         o.solve()
+    worst_cost = worst_traj = 0.0
     for tick in range(3):
         xnew = np.stack([o.field(0, "X_NOM")[12] for o in orcs])    # the state 12 knots into the first phase
         gpu.update_problem()
@@ -497,6 +597,8 @@ def test_receding_horizon_update_problem():
                 if np.isnan(b["cost"]):
                     assert np.isnan(a["cost"])
                 else:
-                    assert abs(a["cost"] - b["cost"]) <= 1e-5 * abs(b["cost"]), (tick, i, a["cost"], b["cost"])
+                    worst_cost = max(worst_cost, abs(a["cost"] - b["cost"]) / abs(b["cost"]))
+                    assert abs(a["cost"] - b["cost"]) <= TOL_COST * abs(b["cost"]), (tick, i, a["cost"], b["cost"])
             if not np.isnan(o.scalars()["cost"]):
-                _cmp_fields(gpu, o, i, ["X_NOM", "U_NOM", "Y_NOM"], 1e-4, "mpc tick %d" % tick)
+                worst_traj = max(worst_traj, _cmp_fields(gpu, o, i, ["X_NOM", "U_NOM", "Y_NOM", "K", "DU"], TOL_TRAJ, "mpc tick %d" % tick, floor_frac=1e-3))
+    print("receding horizon: worst relative cost error %.2e, worst per-knot trajectory / gain error %.2e" % (worst_cost, worst_traj))
