@@ -81,6 +81,11 @@ struct mhpc_batch {
     bool keep_dead_partials = false;
     void* rot_tmp = nullptr;
     size_t rot_bytes = 0;
+    // regularisation-ladder scheduler of the backward sweep (k_bws.cu): rounds after the first launch, rungs the first
+    // launch walks in the kernel, widest fan of rungs per instance.  MHPC_LADDER=0 puts the whole ladder back into one launch.
+    bool ladder = true;
+    bool bws16 = false;              // sixteen lanes per instance in the backward sweep (k_bws16.cu) instead of eight
+    int lad_rounds = 5, lad_first = 2, lad_smax = 16;
     bool want_bws_trace = false;     // diagnostic: where each attempt of the backward sweep stopped
     int* bws_trace_buf = nullptr;
     size_t bws_trace_cap = 0;
@@ -265,6 +270,11 @@ int mhpc_batch_create(int n, const mhpc_hsddp_option* opt, int device, int ls_wi
     fill_eps(b->eps, b->opt.alpha);
     fill_consts(b->c);
     { const char* e = getenv("MHPC_KEEP_DEAD_PARTIALS"); b->keep_dead_partials = e && e[0] == '1'; }
+    { const char* e = getenv("MHPC_LADDER"); if (e) b->ladder = e[0] != '0'; }
+    { const char* e = getenv("MHPC_BWS16"); if (e) b->bws16 = e[0] != '0'; }
+    { const char* e = getenv("MHPC_LADDER_ROUNDS"); if (e && atoi(e) > 0) b->lad_rounds = atoi(e); }
+    { const char* e = getenv("MHPC_LADDER_FIRST"); if (e && atoi(e) > 0) b->lad_first = atoi(e); }
+    { const char* e = getenv("MHPC_LADDER_SMAX"); if (e && atoi(e) > 0) b->lad_smax = atoi(e); }
     *out = b;
     return 0;
 }
@@ -453,6 +463,16 @@ static int set_problems_slots(mhpc_batch* b, const mhpc_problem* pr) {
         rc |= dalloc(b, &d.sd, (size_t)SD_N * npad); rc |= dalloc(b, &d.si, (size_t)SI_N * npad);
         rc |= dalloc(b, &d.rec_i, (size_t)d.max_rec * REC_I * npad); rc |= dalloc(b, &d.rec_d, (size_t)d.max_rec * REC_D * npad);
         rc |= dalloc(b, &d.n_active, 1);
+        if (b->ladder) {
+            d.lad_cap = b->bws16 ? bws16_resident_lane_groups(b->device) : bws_resident_lane_groups(b->device);
+            const size_t tcap = (size_t)std::max(npad, d.lad_cap);
+            rc |= dalloc(b, &d.lad_cnt, LAD_CNT_N); rc |= dalloc(b, &d.lad_unres, npad); rc |= dalloc(b, &d.lad_rung, npad);
+            rc |= dalloc(b, &d.lad_t_inst, tcap); rc |= dalloc(b, &d.lad_t_rung, tcap); rc |= dalloc(b, &d.lad_t_reg, tcap); rc |= dalloc(b, &d.lad_t_dv, tcap);
+            rc |= dalloc(b, &d.lad_u_inst, tcap); rc |= dalloc(b, &d.lad_u_copy, tcap);
+            // scratch outputs of the speculative tasks: same shape as Kfb / dufb / Gv (column = task index < npad)
+            rc |= dalloc(b, &d.lad_K, (size_t)KT * KDIM * npad); rc |= dalloc(b, &d.lad_du, (size_t)KT * 4 * npad);
+            rc |= dalloc(b, &d.lad_G, (size_t)KT * 14 * npad);
+        }
         for (int c = 0; c < CLS_N; ++c) rc |= dalloc(b, &b->knot_list[c], KT);
         if (rc) return -1;
         b->alloc_KT = KT; b->alloc_P = P;
@@ -697,7 +717,7 @@ int mhpc_batch_backward_sweep(mhpc_batch* b, double reg, int* success) {
     CK(cudaStreamSynchronize(b->stream));
     {
         Stage st(b, TB_BWS);
-        launch_bws(b->d, b->c, b->opt, MASK_ALL, 1, b->stream);
+        (b->bws16 ? launch_bws16 : launch_bws)(b->d, b->c, b->opt, MASK_ALL, 1, 0, b->stream);
     }
     CK(cudaGetLastError());
     if (success && pull_per_instance(b, b->d.si + (size_t)SI_BWS_OK * b->d.npad, success)) return -1;
@@ -769,7 +789,18 @@ int mhpc_batch_solve(mhpc_batch* b, int sync_early_exit) {
         { Stage st(b, TB_OTHER); if (fork_copy_nominal(b, MASK_RUNNING)) return -1; }   // update_nominal_trajectory
         for (int it = 1; it <= maxDDP; ++it) {
             { Stage st(b, TB_OTHER); launch_ls_begin(d, MASK_DDP, s); b->launches++; }
-            { Stage st(b, TB_BWS); launch_bws(d, b->c, b->opt, MASK_DDP, 0, s); b->launches++; }
+            { Stage st(b, TB_BWS);   // backward_sweep + regularisation retries (MultiPhaseDDP.cpp:209-227)
+              auto sweep = b->bws16 ? launch_bws16 : launch_bws;
+              if (!b->ladder) { sweep(d, b->c, b->opt, MASK_DDP, 0, 0, s); b->launches++; }
+              else {
+                  sweep(d, b->c, b->opt, MASK_DDP, 0, b->lad_first, s); b->launches++;
+                  for (int r = 1; r <= b->lad_rounds; ++r) {
+                      const int last = r == b->lad_rounds;
+                      if (!b->bws16) launch_bws_ladder_round(d, b->c, b->opt, MASK_DDP, last, b->lad_smax, s);
+                      else { launch_lad_plan(d, b->opt, MASK_DDP, last, b->lad_smax, s); launch_bws16_tasks(d, b->c, b->opt, MASK_DDP, s); launch_lad_finish(d, b->opt, s); }
+                      b->launches += 4;
+                  }
+              } }
             if (line_search(b, MASK_LS, MASK_DDP)) return -1;
             { Stage st(b, TB_OTHER);
               if (fork_copy_nominal(b, MASK_DDP)) return -1;
@@ -1219,7 +1250,7 @@ int mhpc_batch_time_kernel(mhpc_batch* b, int which, int reps, float* ms_per_lau
             const lin_fn fns[CLS_N] = {launch_lin_BS, launch_lin_FS, launch_lin_FL, launch_lin_IMPF, launch_lin_IMPB, launch_lin_LIGHT};
             fns[cls](b->d, b->c, b->opt, MASK_ALL, b->knot_list[cls], b->knot_cnt[cls], b->stream);
         } else if (which == 1) {
-            launch_bws(b->d, b->c, b->opt, MASK_ALL, 1, b->stream);
+            (b->bws16 ? launch_bws16 : launch_bws)(b->d, b->c, b->opt, MASK_ALL, 1, 0, b->stream);
         } else {
             launch_rollout(b->d, b->c, b->opt, MASK_ALL, std::min(b->d.W, b->eps.n), 0, b->eps, b->stream);
         }

@@ -117,7 +117,7 @@ struct Dev {
     double* lad_t_dv;     // [cap] out: expected cost change of the passing sweep
     int* lad_u_inst;      // [cap] compact list of the unresolved instances of this round
     int* lad_u_copy;      // [cap] per unresolved instance: task whose scratch outputs are its result (-1: none / already in place)
-    double *lad_K, *lad_du, *lad_G;   // outputs of the speculative tasks, [KT][56 | 4 | 14][cap] (task-indexed columns)
+    double *lad_K, *lad_du, *lad_G;   // outputs of the speculative tasks, shaped like Kfb / dufb / Gv (column = task index)
 };
 enum { LAD_N_TASKS = 0, LAD_N_UNRES, LAD_STRIDE, LAD_S, LAD_CNT_N };
 constexpr int BWS_TRACE_ATT = 24;   // the ladder 0, 1e-3, 2e-3, ... exceeds 1000 at the 22nd attempt

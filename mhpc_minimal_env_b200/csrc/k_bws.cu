@@ -16,297 +16,30 @@
 // operation sequence (ascending inner index) as in the reference, whichever lane computes it.
 #include <cuda_pipeline.h>
 
+#include <algorithm>
+
 #include "kernels.h"
 #include "model.cuh"
+
+#include "bws_shared.cuh"
 
 namespace mhpc {
 
 constexpr int BWS_LPI = 8;                   // lanes per instance
 constexpr int BWS_THREADS = 32;              // one warp per CTA
 constexpr int BWS_INST = BWS_THREADS / BWS_LPI;
-constexpr int MQ_LD = 15;
-// per-instance scratch (doubles)
-constexpr int S_G = 0;        // 16
-constexpr int S_MQ = 16;      // 14 x 15 : rows 7..13 of M = H*A (at rows 0..6), later Qxx for the symmetrisation
-constexpr int S_N = 226;      // 7 x 4  : rows 7..13 of H*B   (RB: 6 x 4)
-constexpr int S_QUX = 254;    // 4 x 14
-constexpr int S_QUU = 310;    // 16
-constexpr int S_QU = 326;     // 4
-// the three 4x4 work matrices of the value update live in the M/Qxx area, which is dead once Qxx has been symmetrised
-constexpr int S_ADJ = S_MQ;         // 16 adjugate of Quu
-constexpr int S_INV = S_MQ + 16;    // 16 Quu^-1
-constexpr int S_QI = S_MQ + 32;     // 16 symmetrised Quu^-1
-constexpr int SCR = 330;
-// doubles per instance in shared memory: two record stages + scratch; = 8 (mod 16) so that the two instances of a
-// half-warp sit in disjoint banks for every access pattern below
-constexpr int BWS_REGION = 2 * REC + SCR + 14;
-static_assert(BWS_REGION % 16 == 8 && SCR >= S_QU + 4, "bank layout of the per-instance shared-memory region");
 constexpr size_t BWS_SMEM = (size_t)BWS_REGION * BWS_INST * sizeof(double);
 #ifndef BWS_MINBLOCKS
 #define BWS_MINBLOCKS 7
 #endif
-
-// Eigen::LDLT<>::isPositive() restated (diagonal pivoting on the largest |a_ii|, sign of D tracked;
-// Eigen/src/Cholesky/LDLT.h); call site SinglePhase.cpp:202-205.
-__device__ __forceinline__ bool ldlt4_is_positive(const double q[4][4]) {
-    // work on a full symmetric copy of the LOWER triangle (the only part Eigen reads) so that the symmetric pivot
-    // swaps are plain row + column swaps with compile-time indices (everything stays in registers)
-    double a[4][4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int jj = 0; jj < 4; ++jj) a[i][jj] = (i >= jj) ? q[i][jj] : q[jj][i];
-    int sign = 0;  // 0 zero, 1 pos, 2 neg, 3 indefinite
-    bool result_known = false, result = true;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        int pv = k;
-        double big = fabs(a[k][k]);
-#pragma unroll
-        for (int i = k + 1; i < 4; ++i)
-            if (fabs(a[i][i]) > big) { big = fabs(a[i][i]); pv = i; }
-#pragma unroll
-        for (int pp = k + 1; pp < 4; ++pp) {
-            if (pv == pp) {
-#pragma unroll
-                for (int c = 0; c < 4; ++c) { const double t = a[k][c]; a[k][c] = a[pp][c]; a[pp][c] = t; }
-#pragma unroll
-                for (int r = 0; r < 4; ++r) { const double t = a[r][k]; a[r][k] = a[r][pp]; a[r][pp] = t; }
-            }
-        }
-        if (k > 0) {
-            double temp[3];
-#pragma unroll
-            for (int jj = 0; jj < k; ++jj) temp[jj] = a[jj][jj] * a[k][jj];
-            double sacc = a[k][0] * temp[0];
-#pragma unroll
-            for (int jj = 1; jj < k; ++jj) sacc += a[k][jj] * temp[jj];
-            a[k][k] -= sacc;
-#pragma unroll
-            for (int i = k + 1; i < 4; ++i) {
-                double t = a[i][0] * temp[0];
-#pragma unroll
-                for (int jj = 1; jj < k; ++jj) t += a[i][jj] * temp[jj];
-                a[i][k] -= t;
-            }
-        }
-        const double akk = a[k][k];
-        const bool valid = fabs(akk) > 0.0;
-        if (k == 0 && !valid && !result_known) { result_known = true; result = true; }
-        if (valid) {
-            // one reciprocal per pivot instead of a division per entry (<= 1 ulp on L; only the SIGNS of the pivots are used)
-#ifdef BWS_EXACT_DIV
-            const double rk = 1.0 / akk;
-#else
-            const double rk = sx_rcp(akk);
-#endif
-#pragma unroll
-            for (int i = k + 1; i < 4; ++i) a[i][k] *= rk;
-        }
-        if (sign == 1) { if (akk < 0) sign = 3; }
-        else if (sign == 2) { if (akk > 0) sign = 3; }
-        else if (sign == 0) { if (akk > 0) sign = 1; else if (akk < 0) sign = 2; }
-    }
-    return result_known ? result : (sign == 1 || sign == 0);
-}
-
-// value-function update shared by the WB and RB steps (MHPC_CompoundTypes.h:128-144).  Called by ALL lanes of the warp
-// (`on` = this instance takes part; `rows` = this lane owns rows).  Quu^-1 is the closed-form cofactor inverse (what a
-// fixed-size Matrix4d::inverse() computes): every lane forms TWO adjugate entries and does TWO divisions, the 16 entries
-// are shared through scratch.
-// In: Quu/Qu/Qux in scratch; per owned row (A = row m, B = row m+7 when TWO): Qux column qux[4], Qx value qx,
-// symmetrised Qxx row in H[].  Out: H[] = new H row, G entry, K column per row; du; dV of the step.
-template <int NX, bool TWO>
-__device__ __forceinline__ bool value_update(bool on, bool rows, int m, double* scr, const double quxa[4], const double quxb[4],
-                                             double qxa, double qxb, double Ha[14], double Hb[14], double quu_shift,
-                                             double ka[4], double kb[4], double du[4], double& Ga, double& Gb, double& dVstep) {
-    bool pd = true;
-#define QM(r, c) scr[S_QUU + (r) + 4 * (c)]
-    if (on) {
-        double tst[4][4];
-#pragma unroll
-        for (int r = 0; r < 4; ++r)
-#pragma unroll
-            for (int c = 0; c < 4; ++c) tst[r][c] = QM(r, c) - (r == c ? 1.0 * quu_shift : 0.0);
-        pd = ldlt4_is_positive(tst);
-        // adjugate entry r[jj][i] from the cofactor of (i, jj)
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            const int l = m + 8 * h;
-            const int i = l & 3, jj = l >> 2;
-            const int i1 = (i + 1) & 3, i2 = (i + 2) & 3, i3 = (i + 3) & 3, j1 = (jj + 1) & 3, j2 = (jj + 2) & 3, j3 = (jj + 3) & 3;
-            const double cf = QM(i1, j1) * (QM(i2, j2) * QM(i3, j3) - QM(i2, j3) * QM(i3, j2)) +
-                              QM(i2, j1) * (QM(i3, j2) * QM(i1, j3) - QM(i3, j3) * QM(i1, j2)) +
-                              QM(i3, j1) * (QM(i1, j2) * QM(i2, j3) - QM(i1, j3) * QM(i2, j2));
-            scr[S_ADJ + jj + 4 * i] = ((i + jj) & 1) ? -cf : cf;
-        }
-    }
-    __syncwarp();
-    if (on) {
-        double det = QM(0, 0) * scr[S_ADJ + 0 + 4 * 0];
-#pragma unroll
-        for (int i = 1; i < 4; ++i) det += QM(i, 0) * scr[S_ADJ + 0 + 4 * i];
-        // adj / det as adj * (1/det) with the Newton-refined hardware reciprocal (model.cuh: sx_rcp, <= 2 ulp): an IEEE
-        // division is a ~127-cycle dependent sequence on the critical path of every knot.  -DBWS_EXACT_DIV restores it (a
-        // zero numerator - every off-diagonal entry in the rigid-body phases - then takes adj * det, which has the same
-        // value and sign, instead of the division's slow path).
-        const double rdet = sx_rcp(det);
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            const int l = m + 8 * h;
-            const double adj = scr[S_ADJ + l];
-#ifdef BWS_EXACT_DIV
-            scr[S_INV + l] = (adj == 0.0) ? adj * det : adj / det;
-#else
-            scr[S_INV + l] = adj * rdet;
-#endif
-        }
-    }
-#undef QM
-    __syncwarp();
-    if (on) {
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            const int l = m + 8 * h;
-            const int r = l & 3, c = l >> 2;
-            scr[S_QI + l] = (scr[S_INV + r + 4 * c] + scr[S_INV + c + 4 * r]) / 2;
-        }
-    }
-    __syncwarp();
-    if (!on || !pd) return !on ? true : false;
-    double Qu[4], Ta[4], Tb[4];
-#pragma unroll
-    for (int c = 0; c < 4; ++c) Qu[c] = scr[S_QU + c];
-    {   // Qi(r, c) at S_QI + r + 4c; the four columns c are independent chains
-        double e4[4];
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-            const double n0 = -scr[S_QI + c + 4 * 0], p0 = scr[S_QI + 0 + 4 * c];
-            ka[c] = n0 * quxa[0]; Ta[c] = quxa[0] * p0; kb[c] = n0 * quxb[0]; Tb[c] = quxb[0] * p0; e4[c] = n0 * Qu[0];
-        }
-#pragma unroll
-        for (int cc = 1; cc < 4; ++cc) {
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                const double nn = -scr[S_QI + c + 4 * cc], pp = scr[S_QI + cc + 4 * c];
-                ka[c] += nn * quxa[cc];
-                Ta[c] += quxa[cc] * pp;
-                if (TWO) { kb[c] += nn * quxb[cc]; Tb[c] += quxb[cc] * pp; }
-                e4[c] += nn * Qu[cc];
-            }
-        }
-#pragma unroll
-        for (int c = 0; c < 4; ++c) du[c] = e4[c];
-    }
-    double ga = Ta[0] * Qu[0], gb = Tb[0] * Qu[0];
-#pragma unroll
-    for (int c = 1; c < 4; ++c) { ga += Ta[c] * Qu[c]; gb += Tb[c] * Qu[c]; }
-    Ga = qxa - ga;
-    Gb = qxb - gb;
-    if (rows) {
-#pragma unroll
-        for (int j0 = 0; j0 < NX; j0 += 7) {   // seven columns (up to fourteen chains) at a time
-            double sa[7], sb[7];
-#pragma unroll
-            for (int k = 0; k < 7; ++k) {
-                if (j0 + k < NX) { const double u0 = scr[S_QUX + j0 + k]; sa[k] = Ta[0] * u0; sb[k] = Tb[0] * u0; }
-            }
-#pragma unroll
-            for (int c = 1; c < 4; ++c) {
-#pragma unroll
-                for (int k = 0; k < 7; ++k) {
-                    if (j0 + k < NX) {
-                        const double uc = scr[S_QUX + c * 14 + j0 + k];
-                        sa[k] += Ta[c] * uc;
-                        if (TWO) sb[k] += Tb[c] * uc;
-                    }
-                }
-            }
-#pragma unroll
-            for (int k = 0; k < 7; ++k) {
-                if (j0 + k < NX) {
-                    Ha[j0 + k] = Ha[j0 + k] - sa[k];
-                    if (TWO) Hb[j0 + k] = Hb[j0 + k] - sb[k];
-                }
-            }
-        }
-    }
-    double dv = 0.0;
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {   // dV = ((-Qu^T) Quu^-1) Qu with the un-symmetrised inverse
-        double sacc = (-Qu[0]) * scr[S_INV + 0 + 4 * c];
-#pragma unroll
-        for (int cc = 1; cc < 4; ++cc) sacc += (-Qu[cc]) * scr[S_INV + cc + 4 * c];
-        dv = (c == 0) ? sacc * Qu[0] : dv + sacc * Qu[c];
-    }
-    dVstep = dv;
-    return true;
-}
-
-__device__ __forceinline__ int knot_rec_len(bool wb, bool term) {
-    return wb ? (term ? WB_TERM_LEN : WB_STEP_LEN) : (term ? RB_TERM_LEN : RB_STEP_LEN);
-}
-
-// ---- per-row pieces of the phase-boundary value reset (called once per owned row; rare: one knot per phase) ----------
-// WB index -> RB index of the projection P (MultiPhaseDDP.cpp:330-331): (x, z, pitch) and their rates
-__device__ __forceinline__ int wb_to_rb(int l) { return (l < 3) ? l : (l >= 7 && l < 10) ? l - 4 : -1; }
-
-__device__ __forceinline__ void embed_row(int l, const double* scr, double H[14]) {   // H <- row l of P^T H6 P
-    const int pl = wb_to_rb(l);
-#pragma unroll
-    for (int q = 0; q < 14; ++q) {
-        const int pq = wb_to_rb(q);
-        H[q] = (pl >= 0 && pq >= 0) ? scr[S_MQ + pl * MQ_LD + pq] : 0.0;
-    }
-}
-__device__ __forceinline__ void px_right_row(int l, const double* buf, double* scr, const double H[14]) {   // row l of H' Px
-#pragma unroll
-    for (int jc = 0; jc < 14; ++jc) {
-        double acc = (jc < 7) ? H[jc] : 0.0;
-        if (jc >= 2) {
-#pragma unroll
-            for (int s = 0; s < 7; ++s) acc += H[7 + s] * buf[R_AB(s, jc - 2)];
-        }
-        scr[S_MQ + l * MQ_LD + jc] = acc;
-    }
-}
-__device__ __forceinline__ double px_left_row(int l, const double* buf, const double* scr, double H[14]) {   // row l of Px^T (.), returns G entry
-    double pb[7];
-#pragma unroll
-    for (int s = 0; s < 7; ++s) pb[s] = (l >= 2) ? buf[R_AB(s, l - 2)] : 0.0;
-#pragma unroll
-    for (int jc = 0; jc < 14; ++jc) {
-        double acc = (l < 7) ? scr[S_MQ + l * MQ_LD + jc] : 0.0;
-        if (l >= 2) {
-#pragma unroll
-            for (int s = 0; s < 7; ++s) acc += pb[s] * scr[S_MQ + (7 + s) * MQ_LD + jc];
-        }
-        H[jc] = acc;
-    }
-    double g_new = (l < 7) ? scr[S_G + l] : 0.0;
-    if (l >= 2) {
-#pragma unroll
-        for (int s = 0; s < 7; ++s) g_new += pb[s] * scr[S_G + 7 + s];
-    }
-    return g_new;
-}
-__device__ __forceinline__ double wb_terminal_row(int l, const double* buf, double gnext, double H[14]) {   // Phixx + H, returns Phix + G
-#pragma unroll
-    for (int jc = 0; jc < 14; ++jc) {
-        double ph = (jc == l) ? buf[R_PHIXXD + l] : 0.0;
-        if (l >= 1 && l <= 6 && jc >= 1 && jc <= 6) ph = ph + buf[R_PHIXXB + (l - 1) + 6 * (jc - 1)];
-        H[jc] = ph + H[jc];
-    }
-    return buf[R_PHIX + l] + gnext;
-}
 
 // Work assignment.  task_mode == 0: lane group q4 of block b owns instance 4 b + q4, enters with the instance's current
 // regularisation and walks the ladder reg <- max(reg * update_regularization, 1e-3) inside the kernel (at most
 // `max_attempts` rungs when the ladder scheduler is on: what is left goes to the scheduler's rounds below).
 // task_mode == 1: lane group = one task (instance, rung, regularisation) of the list built by k_lad_plan; tasks that are
 // not the first of their instance write K, du, G into the task-indexed scratch arrays instead of the instance's own.
-__global__ void __launch_bounds__(BWS_THREADS, BWS_MINBLOCKS) k_bws(Dev d, Consts c, Opt opt, int mask_mode, int single_attempt, int task_mode,
-                                                                     int max_attempts) {
+template <int task_mode>
+__global__ void __launch_bounds__(BWS_THREADS, BWS_MINBLOCKS) k_bws(Dev d, Consts c, Opt opt, int mask_mode, int single_attempt, int max_attempts) {
     extern __shared__ __align__(16) double smem[];
     const unsigned FULL = 0xffffffffu;
     const int tid = threadIdx.x;
@@ -343,12 +76,12 @@ __global__ void __launch_bounds__(BWS_THREADS, BWS_MINBLOCKS) k_bws(Dev d, Const
     const bool rowl = m < 7;                                           // this sub-lane owns WB rows m and m + 7
     // lane-constant parts of the output addresses (SoA over instances: the four instances of a warp fill one 32-byte
     // sector per element): only `kk * stride` is added per knot
-    const size_t oes = to_scratch ? (size_t)d.lad_cap : es;            // element stride and column of my outputs
+    // (the scratch arrays have the element stride of the instance arrays, npad, so that only the base and the column differ)
     const size_t ocol = to_scratch ? (size_t)task : (size_t)i;
-    double* const gv_lane = (to_scratch ? d.lad_G : d.Gv) + (size_t)m * oes + ocol;
-    double* const kf_lane = (to_scratch ? d.lad_K : d.Kfb) + (size_t)(4 * m) * oes + ocol;
-    double* const du_lane = (to_scratch ? d.lad_du : d.dufb) + (size_t)m * oes + ocol;
-    const size_t gv_knot = 14 * oes, kf_knot = (size_t)KDIM * oes, du_knot = 4 * oes;
+    double* const gv_lane = (to_scratch ? d.lad_G : d.Gv) + (size_t)m * es + ocol;
+    double* const kf_lane = (to_scratch ? d.lad_K : d.Kfb) + (size_t)(4 * m) * es + ocol;
+    double* const du_lane = (to_scratch ? d.lad_du : d.dufb) + (size_t)m * es + ocol;
+    const size_t gv_knot = 14 * es, kf_knot = (size_t)KDIM * es, du_knot = 4 * es;
 
     // per-instance schedule walker (phase p, in-phase knot k; knot slot = p*KSTRIDE + k), used both by the prefetcher
     // (one knot ahead) and by the math; it visits the nk used knots from the last one backwards
@@ -454,7 +187,7 @@ __global__ void __launch_bounds__(BWS_THREADS, BWS_MINBLOCKS) k_bws(Dev d, Const
                             const double gb = wb_terminal_row(m + 7, buf, last ? 0.0 : scr[S_G + m + 7], Hb);
                             scr[S_G + m] = ga; scr[S_G + m + 7] = gb;
                             gv_lane[(size_t)kk * gv_knot] = ga;
-                            gv_lane[(size_t)kk * gv_knot + 7 * oes] = gb;
+                            gv_lane[(size_t)kk * gv_knot + 7 * es] = gb;
                         }
                     } else if (m < 6) {
                         double gv = last ? 0.0 : scr[S_G + m];
@@ -642,7 +375,7 @@ __global__ void __launch_bounds__(BWS_THREADS, BWS_MINBLOCKS) k_bws(Dev d, Const
                 }
                 double ka[4], kb[4], du[4], goa = 0.0, gob = 0.0, dvs = 0.0;
                 __syncwarp();
-                const bool ok = value_update<14, true>(on, rw, m, scr, quxa, quxb, qxa, qxb, Ha, Hb, opt.quu_shift, ka, kb, du, goa, gob, dvs);
+                const bool ok = value_update<14, true, BWS_LPI>(on, rw, m, scr, quxa, quxb, qxa, qxb, Ha, Hb, opt.quu_shift, ka, kb, du, goa, gob, dvs);
                 if (on) {   // (no hand-over needed here or after the stores: S_G is not read by value_update, and the next reader
                             //  of anything written below sits behind the __syncwarp at the top of the knot loop)
                     if (!ok) { failed = true; fail_it = it; }
@@ -651,11 +384,11 @@ __global__ void __launch_bounds__(BWS_THREADS, BWS_MINBLOCKS) k_bws(Dev d, Const
                         if (rowl) {
                             scr[S_G + la] = goa; scr[S_G + lb] = gob;
                             gv_lane[(size_t)kk * gv_knot] = goa;
-                            gv_lane[(size_t)kk * gv_knot + 7 * oes] = gob;
+                            gv_lane[(size_t)kk * gv_knot + 7 * es] = gob;
 #pragma unroll
                             for (int cc = 0; cc < 4; ++cc) {
-                                kf_lane[(size_t)kk * kf_knot + (size_t)cc * oes] = ka[cc];
-                                kf_lane[(size_t)kk * kf_knot + (size_t)(28 + cc) * oes] = kb[cc];
+                                kf_lane[(size_t)kk * kf_knot + (size_t)cc * es] = ka[cc];
+                                kf_lane[(size_t)kk * kf_knot + (size_t)(28 + cc) * es] = kb[cc];
                             }
                         }
                         if (m < 4) du_lane[(size_t)kk * du_knot] = du[m];
@@ -742,7 +475,7 @@ __global__ void __launch_bounds__(BWS_THREADS, BWS_MINBLOCKS) k_bws(Dev d, Const
                 }
                 double ka[4], kb[4], du[4], gout = 0.0, gdummy = 0.0, dvs = 0.0;
                 __syncwarp();
-                const bool ok = value_update<6, false>(on, rw, m, scr, qux, qux, qx, qx, Ha, Hb, opt.quu_shift, ka, kb, du, gout, gdummy, dvs);
+                const bool ok = value_update<6, false, BWS_LPI>(on, rw, m, scr, qux, qux, qx, qx, Ha, Hb, opt.quu_shift, ka, kb, du, gout, gdummy, dvs);
                 if (on) {
                     if (!ok) { failed = true; fail_it = it; }
                     else {
@@ -751,7 +484,7 @@ __global__ void __launch_bounds__(BWS_THREADS, BWS_MINBLOCKS) k_bws(Dev d, Const
                             scr[S_G + l] = gout;
                             gv_lane[(size_t)kk * gv_knot] = gout;
 #pragma unroll
-                            for (int cc = 0; cc < 4; ++cc) kf_lane[(size_t)kk * kf_knot + (size_t)cc * oes] = ka[cc];
+                            for (int cc = 0; cc < 4; ++cc) kf_lane[(size_t)kk * kf_knot + (size_t)cc * es] = ka[cc];
                         }
                         if (m < 4) du_lane[(size_t)kk * du_knot] = du[m];
                     }
@@ -854,11 +587,11 @@ __global__ void __launch_bounds__(1024) k_lad_plan(Dev d, Opt opt, int mask_mode
     }
     const int total = s_scan[1023];
     int cidx = s_scan[tid] - cnt;
-    const int S = total > 0 ? max(1, min(smax, d.lad_cap / total)) : 1;
+    const int S = total > 0 ? max(1, min(smax, min(d.lad_cap, d.npad) / total)) : 1;   // speculative tasks need a scratch column < npad
     if (tid == 0) {
         d.lad_cnt[LAD_N_TASKS] = total * S;
         d.lad_cnt[LAD_N_UNRES] = total;
-        d.lad_cnt[LAD_STRIDE] = (last_round || S >= 4) ? S : 0;
+        d.lad_cnt[LAD_STRIDE] = last_round ? S : 0;
         d.lad_cnt[LAD_S] = S;
     }
     for (int i = lo; i < hi; ++i) {
@@ -927,7 +660,7 @@ __global__ void k_lad_resolve(Dev d, Opt opt) {
 // passing sweep writes (step knots: K, du, G; terminal knots: G)
 __global__ void k_lad_copy(Dev d) {
     const int cidx = blockIdx.y * blockDim.x + threadIdx.x;
-    if (cidx >= d.lad_cnt[LAD_N_UNRES] || cidx >= d.lad_cap) return;
+    if (cidx >= d.lad_cnt[LAD_N_UNRES]) return;
     const int t = d.lad_u_copy[cidx];
     if (t < 0) return;
     const int i = d.lad_u_inst[cidx], kk = blockIdx.x;
@@ -935,7 +668,7 @@ __global__ void k_lad_copy(Dev d) {
     if (!knot_to_phase(d, i, kk, p, k)) return;
     const int nx = (p < d.n_wb[i]) ? 14 : 6;
     const bool term = (k == d.ph_N[ph_idx(d, p, i)] - 1);
-    const size_t ces = d.lad_cap, es = d.npad;
+    const size_t ces = d.npad, es = d.npad;
     for (int e = 0; e < nx; ++e) d.Gv[((size_t)kk * 14 + e) * es + i] = d.lad_G[((size_t)kk * 14 + e) * ces + t];
     if (term) return;
     for (int e = 0; e < 4 * nx; ++e) d.Kfb[((size_t)kk * KDIM + e) * es + i] = d.lad_K[((size_t)kk * KDIM + e) * ces + t];
@@ -943,24 +676,31 @@ __global__ void k_lad_copy(Dev d) {
 }
 
 void launch_bws(const Dev& d, const Consts& c, const Opt& opt, int mask_mode, int single_attempt, int max_attempts, cudaStream_t s) {
-    cudaFuncSetAttribute(k_bws, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BWS_SMEM);
-    k_bws<<<(d.n + BWS_INST - 1) / BWS_INST, BWS_THREADS, BWS_SMEM, s>>>(d, c, opt, mask_mode, single_attempt, 0, d.lad_unres ? max_attempts : 0);
+    cudaFuncSetAttribute(k_bws<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BWS_SMEM);
+    k_bws<0><<<(d.n + BWS_INST - 1) / BWS_INST, BWS_THREADS, BWS_SMEM, s>>>(d, c, opt, mask_mode, single_attempt, d.lad_unres ? max_attempts : 0);
 }
 // one round of the ladder scheduler: plan -> tasks -> resolve -> copy (4 launches, no host synchronisation)
-void launch_bws_ladder_round(const Dev& d, const Consts& c, const Opt& opt, int mask_mode, int last_round, int smax, cudaStream_t s) {
+void launch_lad_plan(const Dev& d, const Opt& opt, int mask_mode, int last_round, int smax, cudaStream_t s) {
     k_lad_plan<<<1, 1024, 0, s>>>(d, opt, mask_mode, last_round, smax);
-    const int tcap = d.npad > d.lad_cap ? d.npad : d.lad_cap;
-    k_bws<<<(tcap + BWS_INST - 1) / BWS_INST, BWS_THREADS, BWS_SMEM, s>>>(d, c, opt, mask_mode, 0, 1, 0);
+}
+void launch_lad_finish(const Dev& d, const Opt& opt, cudaStream_t s) {
     k_lad_resolve<<<(d.n + 127) / 128, 128, 0, s>>>(d, opt);
-    dim3 g(d.KT, (d.lad_cap + 127) / 128);
+    dim3 g(d.KT, (std::min(d.lad_cap, d.npad) / 2 + 127) / 128);   // a winner is copied only when S >= 2, i.e. unresolved <= min(cap, npad) / 2
     k_lad_copy<<<g, 128, 0, s>>>(d);
+}
+void launch_bws_ladder_round(const Dev& d, const Consts& c, const Opt& opt, int mask_mode, int last_round, int smax, cudaStream_t s) {
+    cudaFuncSetAttribute(k_bws<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BWS_SMEM);
+    launch_lad_plan(d, opt, mask_mode, last_round, smax, s);
+    const int tcap = d.npad > d.lad_cap ? d.npad : d.lad_cap;
+    k_bws<1><<<(tcap + BWS_INST - 1) / BWS_INST, BWS_THREADS, BWS_SMEM, s>>>(d, c, opt, mask_mode, 0, 0);
+    launch_lad_finish(d, opt, s);
 }
 // lane groups of k_bws that are resident at once on this device
 int bws_resident_lane_groups(int device) {
     int nsm = 0, per_sm = 0;
     cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, device);
-    cudaFuncSetAttribute(k_bws, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BWS_SMEM);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_bws, BWS_THREADS, BWS_SMEM);
+    cudaFuncSetAttribute(k_bws<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BWS_SMEM);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_bws<1>, BWS_THREADS, BWS_SMEM);
     return nsm * (per_sm > 0 ? per_sm : 1) * BWS_INST;
 }
 

@@ -67,6 +67,12 @@ void launch_par_eval_IMPB(int n, size_t es, const double* st, double* o0, double
 void launch_bws(const Dev& d, const Consts& c, const Opt& o, int mask_mode, int single_attempt, int max_attempts, cudaStream_t s);
 void launch_bws_ladder_round(const Dev& d, const Consts& c, const Opt& o, int mask_mode, int last_round, int smax, cudaStream_t s);
 int bws_resident_lane_groups(int device);
+// the same sweep with sixteen lanes per instance (k_bws16.cu)
+void launch_bws16(const Dev& d, const Consts& c, const Opt& o, int mask_mode, int single_attempt, int max_attempts, cudaStream_t s);
+void launch_bws16_tasks(const Dev& d, const Consts& c, const Opt& o, int mask_mode, cudaStream_t s);
+int bws16_resident_lane_groups(int device);
+void launch_lad_plan(const Dev& d, const Opt& o, int mask_mode, int last_round, int smax, cudaStream_t s);
+void launch_lad_finish(const Dev& d, const Opt& o, cudaStream_t s);
 // standalone evaluation of one generated function over a batch (Jacobian parity tests; k_eval.cu)
 int launch_eval(int fn, int n, const double* in0, const double* in1, const double* in2, const double* in3,
                 double* o0, double* o1, double* o2, double* o3, cudaStream_t s);

@@ -466,6 +466,39 @@ def test_line_search_width_invariance(cfg):
                 assert abs(x["cost"] - y["cost"]) <= 1e-9 * abs(x["cost"]), (width, i, x["cost"], y["cost"])
 
 
+@pytest.mark.parametrize("cfg,rounds,first", [(2, 4, 2), (4, 4, 2), (4, 1, 1), (3, 2, 3), (4, 3, 2)])
+def test_regularisation_ladder_scheduler_equals_sequential_retries(cfg, rounds, first, monkeypatch):
+    """The backward sweep's regularisation retries (MultiPhaseDDP.cpp:209-227) run as scheduled rounds of side-by-side
+    rungs (k_bws.cu, "ladder scheduler").  Whatever the schedule - number of rounds, rungs walked inside the first launch,
+    widest fan - the outcome must be that of the sequential ladder in ONE launch (MHPC_LADDER=0), bit for bit: n_bws, reg,
+    dV, every per-iteration cost, and the final K, du, G, x, u of every knot (the winner of a speculative rung is copied
+    from scratch into place).  Fixed 2x3 budget so that the second outer iteration's retry storm (up to 14 rungs on
+    config 4) is always exercised; 1024 instances so that the rounds run with different fan widths."""
+    import mhpc_minimal_env_b200 as m
+    n = 1024
+    probs = [to_gpu_problem(s) for s in make_specs(n, cfg)]
+    opt = dict(DDP_thresh=-1.0, AL_thresh=-1.0)
+    runs = []
+    for ladder in ("0", "1"):
+        monkeypatch.setenv("MHPC_LADDER", ladder)
+        monkeypatch.setenv("MHPC_LADDER_ROUNDS", str(rounds))
+        monkeypatch.setenv("MHPC_LADDER_FIRST", str(first))
+        monkeypatch.setenv("MHPC_LADDER_SMAX", "16" if rounds != 3 else "3")
+        b = m.BatchedMHPC(probs, m.default_option(**opt), ls_width=4)
+        b.initialization()
+        b.solve()
+        recs = [b.records(i) for i in range(n)]
+        pick = [i for i in range(n) if max(r["n_bws"] for r in recs[i]) >= 3][:24] + [0, 1, n - 1]
+        fields = {(i, p, nm): b.field(i, p, nm).tobytes() for i in pick for p in range(len(b.schedule(i)[0])) for nm in ("K", "DU", "G", "X_NOM", "U_NOM")}
+        runs.append((b.results_array().tobytes(), recs, fields, pick))
+        b.close()
+    assert max(r["n_bws"] for rr in runs[0][1] for r in rr) >= 5      # the retry storm is there
+    assert runs[0][3] == runs[1][3]
+    assert runs[0][1] == runs[1][1]                                   # every record of every instance: ints and doubles identical
+    assert runs[0][0] == runs[1][0]
+    assert runs[0][2] == runs[1][2]
+
+
 def test_instance_order_is_kept_on_every_output_path():
     """A mixed-schedule batch is stored sorted by schedule internally (capi.cu: slot_of / user_of).  Every output path must
     still answer in the caller's instance order: host results, scalars, records, fields, the device-side result table (the
