@@ -44,7 +44,7 @@ def _lin_flags(c):
 
 # (source, object name, extra defines)
 UNITS = [("capi.cu", "capi.o", []), ("k_misc.cu", "k_misc.o", []), ("k_rollout.cu", "k_rollout.o", []),
-         ("k_bws.cu", "k_bws.o", BWS_EXTRA), ("k_bws16.cu", "k_bws16.o", BWS_EXTRA), ("k_eval.cu", "k_eval.o", [])] + \
+         ("k_bws.cu", "k_bws.o", BWS_EXTRA), ("k_bws16.cu", "k_bws16.o", BWS_EXTRA), ("k_bwsT.cu", "k_bwsT.o", BWS_EXTRA), ("k_eval.cu", "k_eval.o", [])] + \
         [("k_lin.cu", f"k_lin_{c}.o", [f"-DLIN_CLS={c}"] + _lin_flags(c)) for c in range(6)]
 # ptxas -O3 degenerates on the 26k-node Jacobian bodies (32 registers, ~100 KB of spill stores per thread);
 # at -O1 it keeps the generator's instruction order and allocates 255 registers (~24 KB of spill stores).

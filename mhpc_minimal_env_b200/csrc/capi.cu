@@ -84,7 +84,7 @@ struct mhpc_batch {
     // regularisation-ladder scheduler of the backward sweep (k_bws.cu): rounds after the first launch, rungs the first
     // launch walks in the kernel, widest fan of rungs per instance.  MHPC_LADDER=0 puts the whole ladder back into one launch.
     bool ladder = true;
-    bool bws16 = false;              // sixteen lanes per instance in the backward sweep (k_bws16.cu) instead of eight
+    int bws_kind = 0;                // backward sweep mapping: 0 = eight lanes per instance (k_bws.cu), 1 = sixteen (k_bws16.cu), 2 = tensor cores, warp per instance (k_bwsT.cu)
     int lad_rounds = 5, lad_first = 2, lad_smax = 16;
     bool want_bws_trace = false;     // diagnostic: where each attempt of the backward sweep stopped
     int* bws_trace_buf = nullptr;
@@ -271,7 +271,7 @@ int mhpc_batch_create(int n, const mhpc_hsddp_option* opt, int device, int ls_wi
     fill_consts(b->c);
     { const char* e = getenv("MHPC_KEEP_DEAD_PARTIALS"); b->keep_dead_partials = e && e[0] == '1'; }
     { const char* e = getenv("MHPC_LADDER"); if (e) b->ladder = e[0] != '0'; }
-    { const char* e = getenv("MHPC_BWS16"); if (e) b->bws16 = e[0] != '0'; }
+    { const char* e = getenv("MHPC_BWS"); if (e) b->bws_kind = (e[0] == 'T' || e[0] == 't') ? 2 : (!strcmp(e, "16") ? 1 : 0); }
     { const char* e = getenv("MHPC_LADDER_ROUNDS"); if (e && atoi(e) > 0) b->lad_rounds = atoi(e); }
     { const char* e = getenv("MHPC_LADDER_FIRST"); if (e && atoi(e) > 0) b->lad_first = atoi(e); }
     { const char* e = getenv("MHPC_LADDER_SMAX"); if (e && atoi(e) > 0) b->lad_smax = atoi(e); }
@@ -464,7 +464,7 @@ static int set_problems_slots(mhpc_batch* b, const mhpc_problem* pr) {
         rc |= dalloc(b, &d.rec_i, (size_t)d.max_rec * REC_I * npad); rc |= dalloc(b, &d.rec_d, (size_t)d.max_rec * REC_D * npad);
         rc |= dalloc(b, &d.n_active, 1);
         if (b->ladder) {
-            d.lad_cap = b->bws16 ? bws16_resident_lane_groups(b->device) : bws_resident_lane_groups(b->device);
+            d.lad_cap = b->bws_kind == 2 ? bwsT_resident_warps(b->device) : b->bws_kind == 1 ? bws16_resident_lane_groups(b->device) : bws_resident_lane_groups(b->device);
             const size_t tcap = (size_t)std::max(npad, d.lad_cap);
             rc |= dalloc(b, &d.lad_cnt, LAD_CNT_N); rc |= dalloc(b, &d.lad_unres, npad); rc |= dalloc(b, &d.lad_rung, npad);
             rc |= dalloc(b, &d.lad_t_inst, tcap); rc |= dalloc(b, &d.lad_t_rung, tcap); rc |= dalloc(b, &d.lad_t_reg, tcap); rc |= dalloc(b, &d.lad_t_dv, tcap);
@@ -717,7 +717,7 @@ int mhpc_batch_backward_sweep(mhpc_batch* b, double reg, int* success) {
     CK(cudaStreamSynchronize(b->stream));
     {
         Stage st(b, TB_BWS);
-        (b->bws16 ? launch_bws16 : launch_bws)(b->d, b->c, b->opt, MASK_ALL, 1, 0, b->stream);
+        (b->bws_kind == 2 ? launch_bwsT : b->bws_kind == 1 ? launch_bws16 : launch_bws)(b->d, b->c, b->opt, MASK_ALL, 1, 0, b->stream);
     }
     CK(cudaGetLastError());
     if (success && pull_per_instance(b, b->d.si + (size_t)SI_BWS_OK * b->d.npad, success)) return -1;
@@ -790,14 +790,18 @@ int mhpc_batch_solve(mhpc_batch* b, int sync_early_exit) {
         for (int it = 1; it <= maxDDP; ++it) {
             { Stage st(b, TB_OTHER); launch_ls_begin(d, MASK_DDP, s); b->launches++; }
             { Stage st(b, TB_BWS);   // backward_sweep + regularisation retries (MultiPhaseDDP.cpp:209-227)
-              auto sweep = b->bws16 ? launch_bws16 : launch_bws;
+              auto sweep = b->bws_kind == 2 ? launch_bwsT : b->bws_kind == 1 ? launch_bws16 : launch_bws;
               if (!b->ladder) { sweep(d, b->c, b->opt, MASK_DDP, 0, 0, s); b->launches++; }
               else {
                   sweep(d, b->c, b->opt, MASK_DDP, 0, b->lad_first, s); b->launches++;
                   for (int r = 1; r <= b->lad_rounds; ++r) {
                       const int last = r == b->lad_rounds;
-                      if (!b->bws16) launch_bws_ladder_round(d, b->c, b->opt, MASK_DDP, last, b->lad_smax, s);
-                      else { launch_lad_plan(d, b->opt, MASK_DDP, last, b->lad_smax, s); launch_bws16_tasks(d, b->c, b->opt, MASK_DDP, s); launch_lad_finish(d, b->opt, s); }
+                      if (b->bws_kind == 0) launch_bws_ladder_round(d, b->c, b->opt, MASK_DDP, last, b->lad_smax, s);
+                      else {
+                          launch_lad_plan(d, b->opt, MASK_DDP, last, b->lad_smax, s);
+                          if (b->bws_kind == 2) launch_bwsT_tasks(d, b->c, b->opt, MASK_DDP, s); else launch_bws16_tasks(d, b->c, b->opt, MASK_DDP, s);
+                          launch_lad_finish(d, b->opt, s);
+                      }
                       b->launches += 4;
                   }
               } }
@@ -1250,7 +1254,7 @@ int mhpc_batch_time_kernel(mhpc_batch* b, int which, int reps, float* ms_per_lau
             const lin_fn fns[CLS_N] = {launch_lin_BS, launch_lin_FS, launch_lin_FL, launch_lin_IMPF, launch_lin_IMPB, launch_lin_LIGHT};
             fns[cls](b->d, b->c, b->opt, MASK_ALL, b->knot_list[cls], b->knot_cnt[cls], b->stream);
         } else if (which == 1) {
-            (b->bws16 ? launch_bws16 : launch_bws)(b->d, b->c, b->opt, MASK_ALL, 1, 0, b->stream);
+            (b->bws_kind == 2 ? launch_bwsT : b->bws_kind == 1 ? launch_bws16 : launch_bws)(b->d, b->c, b->opt, MASK_ALL, 1, 0, b->stream);
         } else {
             launch_rollout(b->d, b->c, b->opt, MASK_ALL, std::min(b->d.W, b->eps.n), 0, b->eps, b->stream);
         }

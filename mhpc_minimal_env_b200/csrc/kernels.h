@@ -71,6 +71,10 @@ int bws_resident_lane_groups(int device);
 void launch_bws16(const Dev& d, const Consts& c, const Opt& o, int mask_mode, int single_attempt, int max_attempts, cudaStream_t s);
 void launch_bws16_tasks(const Dev& d, const Consts& c, const Opt& o, int mask_mode, cudaStream_t s);
 int bws16_resident_lane_groups(int device);
+// ... and on the FP64 tensor cores, one warp per instance (k_bwsT.cu)
+void launch_bwsT(const Dev& d, const Consts& c, const Opt& o, int mask_mode, int single_attempt, int max_attempts, cudaStream_t s);
+void launch_bwsT_tasks(const Dev& d, const Consts& c, const Opt& o, int mask_mode, cudaStream_t s);
+int bwsT_resident_warps(int device);
 void launch_lad_plan(const Dev& d, const Opt& o, int mask_mode, int last_round, int smax, cudaStream_t s);
 void launch_lad_finish(const Dev& d, const Opt& o, cudaStream_t s);
 // standalone evaluation of one generated function over a batch (Jacobian parity tests; k_eval.cu)

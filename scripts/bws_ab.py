@@ -10,8 +10,9 @@ n = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
 cfg = int(sys.argv[2]) if len(sys.argv) > 2 else 2
 probs = [to_gpu_problem(s) for s in make_specs(n, cfg)]
 out = {}
-for v in ("0", "1"):
-    os.environ["MHPC_BWS16"] = v
+kinds = (sys.argv[3].split(",") if len(sys.argv) > 3 else ["8", "T"])
+for v in kinds:
+    os.environ["MHPC_BWS"] = v
     b = m.BatchedMHPC(probs, m.default_option(DDP_thresh=-1.0, AL_thresh=-1.0), ls_width=4)
     b.initialization(); b.forward_sweep(0.0); b.update_nominal_trajectory()
     ok = b.backward_sweep(1.0)
@@ -26,10 +27,17 @@ for v in ("0", "1"):
     tm = b.timing()
     recs = [b.records(i) for i in range(0, n, max(1, n // 256))]
     out[v] = (f, sc, recs, b.results_array().tobytes())
-    print("BWS16=" + v, "success", int(ok.sum()), "full sweep ms %.3f" % t, "solve: total %.2f bws %.2f ls %.2f lin %.2f" % (tm["total_ms"], tm["bws_ms"], tm["linesearch_ms"], tm["linearize_ms"]), flush=True)
+    print("BWS=" + v, "success", int(ok.sum()), "full sweep ms %.3f" % t, "solve: total %.2f bws %.2f ls %.2f lin %.2f" % (tm["total_ms"], tm["bws_ms"], tm["linesearch_ms"], tm["linearize_ms"]), flush=True)
     b.close()
-f0, f1 = out["0"][0], out["1"][0]
+A, B = kinds[0], kinds[1]
+f0, f1 = out[A][0], out[B][0]
 nd = sum(0 if np.array_equal(f0[k], f1[k]) else 1 for k in f0)
 worst = max(float(np.max(np.abs(f0[k] - f1[k]) / (np.max(np.abs(f0[k])) + 1e-300))) for k in f0)
 print("fields differing bitwise:", nd, "of", len(f0), "worst rel diff %.2e" % worst)
-print("dV identical:", np.array_equal(out["0"][1], out["1"][1]), "records identical:", out["0"][2] == out["1"][2], "results identical:", out["0"][3] == out["1"][3])
+ints = lambda rr: [[(r["iter_AL"], r["iter_DDP"], r["n_bws"], r["n_fit"], r["reg"], r["eps"]) for r in x] for x in rr]
+dv0, dv1 = out[A][1], out[B][1]
+print("dV worst rel diff %.2e" % float(np.max(np.abs(dv0 - dv1) / np.abs(dv0))), "integer traces identical:", ints(out[A][2]) == ints(out[B][2]),
+      "worst rel cost diff %.2e" % max(abs(a["cost"] - b["cost"]) / abs(a["cost"]) for x, y in zip(out[A][2], out[B][2]) for a, b in zip(x, y)))
+for k in f0:
+    e = float(np.max(np.abs(f0[k] - f1[k]) / (np.max(np.abs(f0[k])) + 1e-300)))
+    if e > 1e-9: print("  field", k, "rel diff %.2e" % e)
