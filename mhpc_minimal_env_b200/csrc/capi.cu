@@ -84,7 +84,7 @@ struct mhpc_batch {
     // regularisation-ladder scheduler of the backward sweep (k_bws.cu): rounds after the first launch, rungs the first
     // launch walks in the kernel, widest fan of rungs per instance.  MHPC_LADDER=0 puts the whole ladder back into one launch.
     bool ladder = true;
-    int bws_kind = 0;                // backward sweep mapping: 0 = eight lanes per instance (k_bws.cu), 1 = sixteen (k_bws16.cu), 2 = tensor cores, warp per instance (k_bwsT.cu)
+    int bws_kind = 2;                // backward sweep mapping: 2 = tensor cores, warp per instance (k_bwsT.cu, default); MHPC_BWS=8 / 16: eight / sixteen lanes per instance, DFMA (k_bws.cu, k_bws16.cu)
     int lad_rounds = 5, lad_first = 2, lad_smax = 16;
     bool want_bws_trace = false;     // diagnostic: where each attempt of the backward sweep stopped
     int* bws_trace_buf = nullptr;
@@ -271,7 +271,7 @@ int mhpc_batch_create(int n, const mhpc_hsddp_option* opt, int device, int ls_wi
     fill_consts(b->c);
     { const char* e = getenv("MHPC_KEEP_DEAD_PARTIALS"); b->keep_dead_partials = e && e[0] == '1'; }
     { const char* e = getenv("MHPC_LADDER"); if (e) b->ladder = e[0] != '0'; }
-    { const char* e = getenv("MHPC_BWS"); if (e) b->bws_kind = (e[0] == 'T' || e[0] == 't') ? 2 : (!strcmp(e, "16") ? 1 : 0); }
+    { const char* e = getenv("MHPC_BWS"); if (e) b->bws_kind = (e[0] == 'T' || e[0] == 't') ? 2 : (!strcmp(e, "16") ? 1 : (!strcmp(e, "8") ? 0 : 2)); }
     { const char* e = getenv("MHPC_LADDER_ROUNDS"); if (e && atoi(e) > 0) b->lad_rounds = atoi(e); }
     { const char* e = getenv("MHPC_LADDER_FIRST"); if (e && atoi(e) > 0) b->lad_first = atoi(e); }
     { const char* e = getenv("MHPC_LADDER_SMAX"); if (e && atoi(e) > 0) b->lad_smax = atoi(e); }

@@ -445,7 +445,8 @@ def test_line_search_width_invariance(cfg):
     many of them one launch evaluates side by side (1, 2, 4, 8 or all 10) must not change the outcome: identical integer
     traces, regularisation values and accepted step sizes, costs equal to rounding.  (The widths run different template
     instantiations of the rollout kernel - in-place, generic staging, 8-lane staging - in which the compiler contracts a few
-    multiply-adds differently; that shows in the 15th digit, so the costs are compared to 1e-9 rather than bit for bit.)
+    multiply-adds differently; that shows in the 15th digit and is amplified over the six iterations, so the costs are compared to 1e-8 (measured worst
+    case 1.0e-9) rather than bit for bit.)
     Exercises every lane-group shape of the rollout kernel (in-place single slot, generic and 8-lane staging)."""
     import mhpc_minimal_env_b200 as m
     specs = make_specs(96, cfg)
@@ -463,7 +464,7 @@ def test_line_search_width_invariance(cfg):
             ra, rb = runs[8][1][i], runs[width][1][i]
             assert [[r[k] for k in ints] for r in ra] == [[r[k] for k in ints] for r in rb], (width, i)
             for x, y in zip(ra, rb):   # 15th-digit differences, amplified over 6 iterations
-                assert abs(x["cost"] - y["cost"]) <= 1e-9 * abs(x["cost"]), (width, i, x["cost"], y["cost"])
+                assert abs(x["cost"] - y["cost"]) <= 1e-8 * abs(x["cost"]), (width, i, x["cost"], y["cost"])
 
 
 @pytest.mark.parametrize("cfg,rounds,first", [(2, 4, 2), (4, 4, 2), (4, 1, 1), (3, 2, 3), (4, 3, 2)])
@@ -497,6 +498,41 @@ def test_regularisation_ladder_scheduler_equals_sequential_retries(cfg, rounds, 
     assert runs[0][1] == runs[1][1]                                   # every record of every instance: ints and doubles identical
     assert runs[0][0] == runs[1][0]
     assert runs[0][2] == runs[1][2]
+
+
+@pytest.mark.parametrize("cfg", [2, 3, 4])
+def test_backward_sweep_mappings_agree(cfg, monkeypatch):
+    """The three lane mappings of the backward sweep - tensor cores with a warp per instance (k_bwsT.cu, the default), eight
+    and sixteen lanes per instance on the FP64 cores (k_bws.cu, k_bws16.cu) - are the same algorithm with different
+    accumulation orders: after ONE sweep K, du, G agree to 1e-9 of each knot's norm (measured: 3e-11) and dV to 1e-12, and whole fixed-budget
+    solves of 512 instances give identical integer traces (iteration counts, attempts, regularisation, step sizes)."""
+    import mhpc_minimal_env_b200 as m
+    n = 512
+    probs = [to_gpu_problem(s) for s in make_specs(n, cfg)]
+    out = {}
+    for kind in ("T", "8", "16"):
+        monkeypatch.setenv("MHPC_BWS", kind)
+        b = m.BatchedMHPC(probs, m.default_option(DDP_thresh=-1.0, AL_thresh=-1.0), ls_width=4)
+        b.initialization(); b.forward_sweep(0.0); b.update_nominal_trajectory()
+        ok = b.backward_sweep(1e-3)
+        dv = b.scalars()["exp_cost_change"].copy()
+        pick = [0, 1, 2, 3, n // 2, n - 1]
+        f = {(i, p, nm): b.field(i, p, nm) for i in pick for p in range(len(b.schedule(i)[0])) for nm in ("K", "DU", "G")}
+        b.initialization(); b.solve()
+        recs = [b.records(i) for i in range(n)]
+        out[kind] = (ok.copy(), dv, f, recs)
+        b.close()
+    ints = lambda rr: [[(r["iter_AL"], r["iter_DDP"], r["n_bws"], r["n_fit"], r["reg"], r["eps"]) for r in x] for x in rr]
+    for kind in ("8", "16"):
+        assert np.array_equal(out["T"][0], out[kind][0])
+        okm = out["T"][0]
+        assert np.max(np.abs(out["T"][1][okm] - out[kind][1][okm]) / np.abs(out[kind][1][okm])) < 1e-12
+        for key, a in out["T"][2].items():
+            if okm[key[0]]:
+                assert relerr_rows(a, out[kind][2][key], 1e-3) < 1e-9, (kind, key)
+        assert ints(out["T"][3]) == ints(out[kind][3]), kind
+        worst = max(abs(x["cost"] - y["cost"]) / abs(y["cost"]) for a, bb in zip(out["T"][3], out[kind][3]) for x, y in zip(a, bb) if not np.isnan(y["cost"]))
+        assert worst < 1e-7, (kind, worst)
 
 
 def test_instance_order_is_kept_on_every_output_path():
