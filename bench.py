@@ -160,7 +160,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--instances", type=int, default=4096, help="instances per GPU")
-    ap.add_argument("--exec-knots", type=int, default=10, help="knots of the execution bag returned by the e2e call")
+    # execution bag of the e2e call: the reference copies the first two whole-body phases (MHPCLocomotion.cpp:178-194),
+    # N0 + N1 = 80 + 100 knots of the default gait; --exec-knots 10 gives the lighter figure reported as e2e_first10
+    ap.add_argument("--exec-knots", type=int, default=180, help="knots of the execution bag returned by the e2e call")
     ap.add_argument("--cpu-sample", type=int, default=256)
     ap.add_argument("--ref-sample", type=int, default=256)
     # line-search trials evaluated side by side per launch.  At 4096 instances the accepted step size is among the first
@@ -254,36 +256,40 @@ def main():
     # ---- end-to-end through the host-facing call, host buffers, copies inside the timed region ----
     import ctypes as C
     from mhpc_minimal_env_b200.capi import Problem, Result
-    ek = args.exec_knots
+    L = m.load()
+    dp = C.POINTER(C.c_double)
     pin_p = torch.empty(n * C.sizeof(Problem), dtype=torch.uint8).pin_memory()
     C.memmove(pin_p.data_ptr(), C.addressof(batch._problems), n * C.sizeof(Problem))
     pin_r = torch.empty(n * C.sizeof(Result), dtype=torch.uint8).pin_memory()
-    pin_s = torch.empty(n * ek * 22, dtype=torch.float64).pin_memory()
-    pin_g = torch.empty(n * ek * 60, dtype=torch.float64).pin_memory()
-    L = m.load()
-    dp = C.POINTER(C.c_double)
 
-    def e2e_step():
-        rc = L.mhpc_batch_solve_host(batch.h, C.cast(pin_p.data_ptr(), C.POINTER(Problem)), C.cast(pin_r.data_ptr(), C.POINTER(Result)),
-                                     2, C.cast(pin_s.data_ptr(), dp), C.cast(pin_g.data_ptr(), dp), ek)
-        if rc < 0:
-            raise RuntimeError(L.mhpc_last_error().decode())
+    def measure_e2e(ek):
+        pin_s = torch.empty(n * ek * 22, dtype=torch.float64).pin_memory()
+        pin_g = torch.empty(n * ek * 60, dtype=torch.float64).pin_memory()
 
-    e2e_step()
-    barrier()
-    t0 = time.perf_counter()
-    e2e_steps = max(2, min(args.steps, 5))
-    for _ in range(e2e_steps):
+        def e2e_step():
+            rc = L.mhpc_batch_solve_host(batch.h, C.cast(pin_p.data_ptr(), C.POINTER(Problem)), C.cast(pin_r.data_ptr(), C.POINTER(Result)),
+                                         2, C.cast(pin_s.data_ptr(), dp), C.cast(pin_g.data_ptr(), dp), ek)
+            if rc < 0:
+                raise RuntimeError(L.mhpc_last_error().decode())
+
         e2e_step()
-    torch.cuda.synchronize()
-    t_e2e = torch.tensor([(time.perf_counter() - t0) / e2e_steps], device="cuda", dtype=torch.float64)
-    if dist is not None:
-        dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
+        barrier()
+        t0 = time.perf_counter()
+        e2e_steps = max(2, min(args.steps, 5))
+        for _ in range(e2e_steps):
+            e2e_step()
+        torch.cuda.synchronize()
+        t_e2e = torch.tensor([(time.perf_counter() - t0) / e2e_steps], device="cuda", dtype=torch.float64)
+        if dist is not None:
+            dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
+        return n * world / float(t_e2e.item()), n * C.sizeof(Result) + n * ek * (22 + 60) * 8
+
+    ek = args.exec_knots
+    e2e_value, d2h = measure_e2e(ek)
+    e2e10_value, d2h10 = measure_e2e(10) if ek != 10 else (e2e_value, d2h)
     sampler.stop_flag = True
     sampler.join(timeout=2)
-    e2e_value = n * world / float(t_e2e.item())
     h2d = n * C.sizeof(Problem)
-    d2h = n * C.sizeof(Result) + n * ek * (22 + 60) * 8
 
     line = None
     if rank == 0:
@@ -292,6 +298,7 @@ def main():
         step()
         batch.synchronize()
         tm = batch.timing()
+        itm = batch.iteration_timing()
         batch.enable_timing(False)
         lin_ms = batch.time_kernel(0, 5)
         lin_bs_ms = batch.time_kernel(10, 5)      # the single dominant kernel: k_lin<BS> (back-stance Jacobian knots)
@@ -330,25 +337,35 @@ def main():
             except Exception:
                 pass
             return None
-        # the dominant kernel of a step is the backward sweep (stage_ms below); it moves its algorithmic bytes once (ncu
-        # traffic <= algorithmic) and is bound by the 712 dependent Riccati steps, not by bandwidth
-        roofline = {"kernel": "k_bws (impact-aware Riccati sweep over 712 knots, one attempt, all instances)", "bound": "hbm",
+        # the dominant kernel of a step is the backward sweep (stage_ms below): k_bwsT, one warp per instance on the FP64 tensor
+        # cores; algorithmic bytes = knot records in + K, du, G out
+        roofline = {"kernel": "k_bwsT (impact-aware Riccati sweep over 712 knots on the FP64 tensor cores, one attempt, all instances)", "bound": "hbm",
                     "achieved": bws_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": bws_gbs / hbm_peak,
-                    "traffic": ncu_traffic("r1_bws_ncu_traffic.json"), "algorithmic_bytes": BWS_BYTES_PER_INSTANCE * n,
+                    "traffic": ncu_traffic("r2_bwsT_ncu_traffic.json"), "algorithmic_bytes": BWS_BYTES_PER_INSTANCE * n,
                     "ms_per_launch": bws_ms, "us_per_knot": 1e3 * bws_ms / 712,
                     "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
-                    "note": f"latency-bound: 712 sequential knots x {1e3 * bws_ms / 712:.1f} us; ncu (profiles/r1_ncu_summary.md): FP64 pipe 26 %, issue slots 32 %, 1.7 warps/scheduler at 4096 instances"}
+                    "note": "712 dependent knots per instance; ncu (profiles/r2_ncu_summary.md): shared-memory data pipe 64 %, issue slots 43 %, "
+                            "FP64 tensor pipe 36 % of peak; DMMA and DFMA have the same FP64 peak on B200 (profiles/r2_dmma_microbench.txt)"}
+        # FP64 kernels: frac = flops the device form EXECUTES / measured DFMA peak.  (The Jacobians are re-derived by implicit
+        # differentiation, ~5x fewer operations than the reference's flat CasADi DAGs; the reference formulation's flop count of
+        # SURVEY.md 8(d) over the same time is kept under reference_formulation_* for comparison with the CPU path only.)
         roofline_lin_bs = {"kernel": "k_lin<BS> (Dyn_BS_par + Euler A,B + cost/barrier partials, 79 back-stance knots x instances)",
-                           "bound": "fp64", "achieved": bs_tflops, "peak": fp64_peak, "unit": "TFLOP/s", "frac": bs_tflops / fp64_peak,
-                           "executed_tflops": exe_bs / (lin_bs_ms * 1e-3) / 1e12, "executed_frac": exe_bs / (lin_bs_ms * 1e-3) / 1e12 / fp64_peak,
+                           "bound": "fp64", "achieved": exe_bs / (lin_bs_ms * 1e-3) / 1e12, "peak": fp64_peak, "unit": "TFLOP/s",
+                           "frac": exe_bs / (lin_bs_ms * 1e-3) / 1e12 / fp64_peak,
+                           "reference_formulation_tflops": bs_tflops, "reference_formulation_frac": bs_tflops / fp64_peak,
                            "traffic": ncu_traffic("r1_lin_bs_ncu_traffic.json"), "algorithmic_bytes": 1352.0 * n_bs_knots * n,
                            "hbm_frac_algorithmic": 1352.0 * n_bs_knots * n / (lin_bs_ms * 1e-3) / 1e9 / hbm_peak, "ms_per_launch": lin_bs_ms,
-                           "peak_source": "FP64 FMA probe measured live on this GPU (MEASURED_PEAKS.json has no FP64 entry)",
-                           "note": "achieved counts the reference formulation's flops (SURVEY.md 8(d)); executed_* counts what the re-derived Jacobian runs"}
+                           "peak_source": "FP64 FMA probe measured live on this GPU (MEASURED_PEAKS.json has no FP64 entry)"}
         roofline_lin_group = {"kernel": "linearisation launch group (k_lin<BS,FS,FL,IMPF,IMPB,light>)", "bound": "fp64",
-                              "achieved": lin_tflops, "peak": fp64_peak, "unit": "TFLOP/s", "frac": lin_tflops / fp64_peak,
-                              "executed_tflops": exe_lin / (lin_ms * 1e-3) / 1e12, "executed_frac": exe_lin / (lin_ms * 1e-3) / 1e12 / fp64_peak,
+                              "achieved": exe_lin / (lin_ms * 1e-3) / 1e12, "peak": fp64_peak, "unit": "TFLOP/s",
+                              "frac": exe_lin / (lin_ms * 1e-3) / 1e12 / fp64_peak,
+                              "reference_formulation_tflops": lin_tflops, "reference_formulation_frac": lin_tflops / fp64_peak,
                               "ms_per_launch": lin_ms, "us_per_horizon_linearize": 1e3 * lin_ms / n}
+        strong = None
+        try:
+            strong = json.load(open(os.path.join(ROOT, "profiles", "r2_strong_scaling.json")))
+        except Exception:
+            pass
         cpu_v = cpu_baseline_single(args.cpu_sample)
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
@@ -357,13 +374,19 @@ def main():
                            "ls_width": args.ls_width, "l2": "working set (>10 GB/GPU) far exceeds the 126 MB L2; no explicit flush",
                            "sharding": "by instance, contiguous blocks per rank, one final NCCL all_gather of the result table"},
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                        "note": f"mhpc_batch_solve_host: pinned host problems in, results + first {ek} knots of x,u,y,K,du out"},
+                        "note": f"mhpc_batch_solve_host: pinned host problems in; results + the execution bag of the reference (x,u,y,K,du of the first two "
+                                f"whole-body phases, {ek} knots per instance, MHPCLocomotion.cpp:178-194) out"},
+                "e2e_first10": {"value": e2e10_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h10,
+                                "note": "the same call returning only the first 10 knots of the execution bag (what one 10 ms control period consumes)"},
                 "gpu_launches": int(tm["n_launches"] + 3) * args.steps,
                 "clocks": sampler.summary(),
                 "roofline": roofline, "roofline_lin_bs": roofline_lin_bs, "roofline_lin_group": roofline_lin_group,
                 "stage_ms": {k: tm[k] for k in ("total_ms", "rollout_ms", "linearize_ms", "bws_ms", "linesearch_ms", "other_ms")},
                 # the north star's unit of work: ONE HSDDP iteration over the horizon for the whole batch (10 ms control period)
                 "hsddp_iteration_ms": tm["total_ms"] / 6.0,
+                "hsddp_iteration_ms_max": max((r["total_ms"] for r in itm), default=None),
+                "iteration_ms": [{k: (round(v, 3) if isinstance(v, float) else v) for k, v in r.items()} for r in itm],
+                "strong_scaling": strong,
                 "cpu_baseline": {"value": cpu_v, "unit": UNIT, "cores": 1, "kind": _cpu_kind(),
                                  "sample": f"first {args.cpu_sample} instances of the workload, reference sources (-O3 -mavx2 -mfma, Eigen stand-in), one core; "
                                            f"host has {os.cpu_count()} cores -> x{os.cpu_count()} = {cpu_v * (os.cpu_count() or 1):.1f} solves/s if it scaled perfectly"},

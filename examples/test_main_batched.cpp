@@ -9,6 +9,7 @@
 
 int main(int argn, char* argv[]) {
     const int n = argn > 1 ? std::atoi(argv[1]) : 4;
+    const bool fixed_budget = argn > 2 && std::atoi(argv[2]) != 0;   // run all max_AL_iter x max_DDP_iter iterations
 
     // Choose HSDDP options
     HSDDP_OPTION<double> option;
@@ -16,6 +17,7 @@ int main(int argn, char* argv[]) {
     option.AL_active = 1;
     option.max_AL_iter = 2;
     option.max_DDP_iter = 3;
+    if (fixed_budget) { option.DDP_thresh = -1; option.AL_thresh = -1; }
 
     // Instantiate MHPCLocomotion
     USRCMD usrcmd;
@@ -29,8 +31,12 @@ int main(int argn, char* argv[]) {
     Gait gait;
     BatchedMHPCLocomotion<double> locomotion(n, &mhpcparams, &gait, option);
     for (int i = 1; i < n; ++i) locomotion.problem(i).x0[7] += 0.01 * i;
+    locomotion.enable_timing();
     locomotion.initialization();
     locomotion.solve_mhpc();
+    for (const TIME_PER_ITERATION& t : locomotion.time_ddp(0))   // the reference's TIME_BENCHMARK table (help.cpp:3-13)
+        std::printf("time_ddp  iter %d  n_bws %d  time_bws %.3f ms  n_fit %d  time_fit %.3f ms  time_partial %.3f ms\n", t.DDP_iter, t.n_bws, t.time_bws, t.n_fit,
+                    t.time_fit, t.time_partial);
     locomotion.print_debugInfo(0);
     for (int i = 0; i < n; ++i) {
         std::printf("instance %d: cost %.12f  exp. cost change %.6e  terminal constraint violation %.3e\n", i,

@@ -171,15 +171,28 @@ int mhpc_batch_results_to_device(mhpc_batch* b, double* dev_out, int capacity_do
  *   "FBDynamics" / "FBDynamics_par"         (x[6], u[4], foothold[4], c[2])  -> xdot[6] / Ac[6x6], Bc[6x4]
  *   "WB_FL1_terminal_constr" / "WB_FL2_..." (x[14])                          -> h[1], hx[14], hxx[14x14]
  *   "Jacob_F" "Jacob_B"                     (x[14])                          -> J[2x7]
+ *   "Link0Jacobian" .. "Link4Jacobian"      (x[14], p[2])                    -> J[2x7], Jdot[2x7]   (dormant in the reference:
+ *                                            included by CasadiGen.h:22-26, never called)
  * inputs/outputs are host arrays of n evaluations, evaluation-major ([n][size]); outputs dense column-major with
  * structural zeros written as 0 (the adaptor's scatter into pre-zeroed Eigen storage). */
 int mhpc_eval_function(const char* name, int n, int device, const double* in0, const double* in1, const double* in2,
                        const double* in3, double* out0, double* out1, double* out2, double* out3);
 
+/* Control-smoothness penalty (HSDDP_OPTION::smooth_active, AL_REB_PARAMETER::eps_smooth = 1; MHPC_CompoundTypes.h:211,224): dormant in
+ * the reference - update_running_cost_with_smooth is an empty body that nothing calls (SinglePhase.cpp:252-254).  Accepted, stored,
+ * without effect on any result, exactly as there. */
+int mhpc_batch_set_eps_smooth(mhpc_batch* b, double eps_smooth);
+double mhpc_batch_get_eps_smooth(mhpc_batch* b);
+
 /* ---- timing of the last solve (TIME_PER_ITERATION buckets, MHPC_CompoundTypes.h:253-262), ms, CUDA events */
 typedef struct mhpc_timing { float total_ms, rollout_ms, linearize_ms, bws_ms, linesearch_ms, other_ms; int n_launches; } mhpc_timing;
 int mhpc_batch_enable_timing(mhpc_batch* b, int on);
 int mhpc_batch_get_timing(mhpc_batch* b, mhpc_timing* t);
+/* the same per inner iteration: TIME_PER_ITERATION::{time_bws, time_fit, time_partial} (MHPC_CompoundTypes.h:253-262, filled by
+ * MultiPhaseDDP.cpp:206-208,228-235,242-253,259-267 under TIME_BENCHMARK) for the whole batch, ms; the full forward sweep of an
+ * outer iteration (MultiPhaseDDP.cpp:184-192) is reported with its first inner iteration.  Returns the number of records. */
+typedef struct mhpc_iter_timing { int iter_AL, iter_DDP; float time_fwd_ms, time_bws_ms, time_fit_ms, time_partial_ms, total_ms; } mhpc_iter_timing;
+int mhpc_batch_get_iteration_timing(mhpc_batch* b, mhpc_iter_timing* out, int max_records);
 /* diagnostic: for every inner-iteration record r and every attempt a of its backward sweep (the regularisation ladder of
  * MultiPhaseDDP.cpp:209-227) the backward step at which the attempt stopped: it + 1 when Quu failed the positive-definite
  * test at backward step `it` (0 = the last knot's predecessor), -1 when the attempt passed, 0 when it was not made.

@@ -11,7 +11,9 @@
 #ifndef MHPC_B200_HPP
 #define MHPC_B200_HPP
 #include <cassert>
+#include <algorithm>
 #include <fstream>
+#include <sstream>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -155,10 +157,27 @@ public:
         r.resize(n);
         return r;
     }
-    std::vector<TIME_PER_ITERATION> time_ddp(int i) {   // the integer half of the reference's TIME_BENCHMARK record
+    // MultiPhaseDDP.cpp:163-170,206-253 (TIME_BENCHMARK): one record per executed inner iteration of instance i.  n_bws / n_fit
+    // are the instance's own counts; the times are those of the batch (CUDA events, ms; call enable_timing() before the
+    // solve), booked as the reference books them: time_partial of an iteration is the time of the sweep that produced the
+    // derivatives it used - the full forward sweep for the first inner iteration of an outer iteration, the partials-only
+    // sweep of the previous inner iteration otherwise.
+    void enable_timing(bool on = true) { ck(mhpc_batch_enable_timing(_h, on ? 1 : 0)); }
+    std::vector<TIME_PER_ITERATION> time_ddp(int i) {
         std::vector<TIME_PER_ITERATION> out;
+        std::vector<mhpc_iter_timing> tm(256);
+        const int nt = mhpc_batch_get_iteration_timing(_h, tm.data(), 256);
         int abs_it = 1;
-        for (const mhpc_iter_record& r : records(i)) { TIME_PER_ITERATION t; t.DDP_iter = abs_it++; t.n_bws = r.n_bws; t.n_fit = r.n_fit; out.push_back(t); }
+        for (const mhpc_iter_record& r : records(i)) {
+            TIME_PER_ITERATION t;
+            t.DDP_iter = abs_it++; t.n_bws = r.n_bws; t.n_fit = r.n_fit;
+            for (int k = 0; k < nt; ++k) {
+                if (tm[k].iter_AL != r.iter_AL) continue;
+                if (tm[k].iter_DDP == r.iter_DDP) { t.time_bws = tm[k].time_bws_ms; t.time_fit = tm[k].time_fit_ms; if (r.iter_DDP == 1) t.time_partial = tm[k].time_fwd_ms; }
+                if (r.iter_DDP > 1 && tm[k].iter_DDP == r.iter_DDP - 1) t.time_partial = tm[k].time_partial_ms;
+            }
+            out.push_back(t);
+        }
         return out;
     }
     // [N_knots x dim] row-major copy of a per-knot field of one phase (matrices column-major inside a row)
@@ -176,17 +195,35 @@ public:
         if (knots_out) *knots_out = per_phase ? 1 : N[phase];
         return out;
     }
-    // print_debugInfo (MHPCLocomotion.cpp:293-380): nominal state / control / value gradient / terminal gradient of one
-    // instance, one knot per line, written as <prefix>state.txt, control.txt, gradient.txt, cost.txt
-    void print_debugInfo(int i, const std::string& prefix = "") {
+    // print_debugInfo (MHPCLocomotion.cpp:293-380) of instance i, file for file and row for row:
+    //   state.txt     nominal x of every knot, whole-body phases then rigid-body phases
+    //   control.txt   nominal u;  gradient.txt  value gradient G
+    //   cost.txt      per phase the running-cost gradients lx of knots 0..N-2, then the terminal gradient Phix
+    // in Eigen's default stream format (6 significant digits, coefficients right-aligned to the longest one of the row).
+    // The reference sizes the rigid-body loops of control / gradient / cost with N_TIMESTEPS[i + 2] instead of
+    // N_TIMESTEPS[i + n_wbphase] (:330,350,371); the row counts follow it (rows past a phase's own knots are the zeros of
+    // memory_reset).  lx and Phix are those of forward_sweep_partials_only() at the final nominal trajectory, which is what
+    // the reference's arrays hold when the inner loop ran to max_DDP_iter; it is re-run here because solve() skips that
+    // last, otherwise dead, sweep.  (When the reference's inner loop stops on DDP_thresh instead, its arrays keep the
+    // derivatives of the previous linearisation point plus what the line-search trials added to Phix - SURVEY A.2-1; that
+    // left-over is not reproduced.)
+    void print_debugInfo(int i, const std::string& prefix = "", int precision = 6) {
+        ck(mhpc_batch_forward_sweep_partials_only(_h));
         std::ofstream state(prefix + "state.txt"), control(prefix + "control.txt"), gradient(prefix + "gradient.txt"), cost(prefix + "cost.txt");
+        for (std::ofstream* f : {&state, &control, &gradient, &cost}) f->precision(precision);
         const int np = mhpc_batch_n_phases(_h, i);
+        ck(np);
+        std::vector<int> mode(np), N(np), wb(np);
+        ck(mhpc_batch_get_schedule(_h, i, mode.data(), N.data(), wb.data()));
+        int nwb = 0;
+        for (int p = 0; p < np; ++p) nwb += wb[p];
         for (int p = 0; p < np; ++p) {
-            dump(state, i, p, MHPC_F_X_NOM);
-            dump(control, i, p, MHPC_F_U_NOM);
-            dump(gradient, i, p, MHPC_F_G);
-            dump(cost, i, p, MHPC_F_LX);
-            dump(cost, i, p, MHPC_F_PHIX);
+            const int rows_ref = wb[p] ? N[p] : N[std::min(p - nwb + 2, np - 1)];   // the reference's loop bound
+            dump(state, i, p, MHPC_F_X_NOM, N[p]);
+            dump(control, i, p, MHPC_F_U_NOM, rows_ref);
+            dump(gradient, i, p, MHPC_F_G, rows_ref);
+            dump(cost, i, p, MHPC_F_LX, rows_ref - 1);
+            dump(cost, i, p, MHPC_F_PHIX, 1);
         }
     }
     mhpc_batch* handle() { return _h; }
@@ -210,11 +247,23 @@ private:
         _actual_cost.resize(_n_instances); _exp_cost_change.resize(_n_instances); _tconstr_violation.resize(_n_instances);
         ck(mhpc_batch_get_scalars(_h, _actual_cost.data(), _exp_cost_change.data(), _tconstr_violation.data()));
     }
-    void dump(std::ofstream& os, int i, int p, mhpc_field f) {
+    // `rows` rows of a field in Eigen's default IOFormat; rows the phase does not have are zeros
+    void dump(std::ofstream& os, int i, int p, mhpc_field f, int rows) {
         int dim = 0, kn = 0;
         std::vector<double> v = field(i, p, f, &dim, &kn);
-        os.precision(17);
-        for (int k = 0; k < kn; ++k) { for (int e = 0; e < dim; ++e) os << (e ? " " : "") << v[(size_t)k * dim + e]; os << "\n"; }
+        for (int k = 0; k < rows; ++k) {
+            std::vector<std::string> txt(dim);
+            size_t width = 0;
+            for (int e = 0; e < dim; ++e) {
+                std::ostringstream ss;
+                ss.copyfmt(os);
+                ss << (k < kn ? v[(size_t)k * dim + e] : 0.0);
+                txt[e] = ss.str();
+                width = std::max(width, txt[e].size());
+            }
+            for (int e = 0; e < dim; ++e) os << (e ? " " : "") << std::string(width - txt[e].size(), ' ') << txt[e];
+            os << "\n";
+        }
     }
     mhpc_batch* _h = nullptr;
     std::vector<mhpc_problem> _problems;

@@ -51,7 +51,7 @@ UNITS = [("capi.cu", "capi.o", []), ("k_misc.cu", "k_misc.o", []), ("k_rollout.c
 
 GEN_FILES = ["Dyn_BS", "Dyn_FS", "Dyn_FL", "Dyn_BS_par", "Dyn_FS_par", "Dyn_FL_par", "Imp_F", "Imp_B", "Imp_F_par",
              "Imp_B_par", "FBDynamics", "FBDynamics_par", "WB_FL1_terminal_constr", "WB_FL2_terminal_constr",
-             "Jacob_F", "Jacob_B"]
+             "Jacob_F", "Jacob_B", "Link0Jacobian", "Link1Jacobian", "Link2Jacobian", "Link3Jacobian", "Link4Jacobian"]
 
 
 def _digest(paths):

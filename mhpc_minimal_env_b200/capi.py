@@ -11,7 +11,7 @@ from typing import List, Optional, Sequence
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libmhpc_b200.so")
+LIB_PATH = os.environ.get("MHPC_B200_LIB") or os.path.join(HERE, "libmhpc_b200.so")   # (the override is for timing build variants)
 
 FIELDS = ["X_ACT", "U_ACT", "Y_ACT", "X_NOM", "U_NOM", "Y_NOM", "X_REF", "U_REF", "Y_REF",
           "A", "B", "C", "D", "LX", "LU", "LY", "LXX", "LUU", "LYY", "K", "DU", "G", "H_UNUSED", "PHIX", "PHIXX", "PX"]
@@ -50,6 +50,11 @@ class Timing(C.Structure):
                 ("linesearch_ms", C.c_float), ("other_ms", C.c_float), ("n_launches", C.c_int)]
 
 
+class IterTiming(C.Structure):
+    _fields_ = [("iter_AL", C.c_int), ("iter_DDP", C.c_int), ("time_fwd_ms", C.c_float), ("time_bws_ms", C.c_float),
+                ("time_fit_ms", C.c_float), ("time_partial_ms", C.c_float), ("total_ms", C.c_float)]
+
+
 EXPORTS = [
     "mhpc_default_option", "mhpc_default_problem", "mhpc_batch_create", "mhpc_batch_destroy", "mhpc_last_error",
     "mhpc_batch_set_option", "mhpc_batch_set_stream", "mhpc_batch_set_problems", "mhpc_batch_initialization", "mhpc_batch_set_initial_condition", "mhpc_batch_update_problem",
@@ -60,6 +65,7 @@ EXPORTS = [
     "mhpc_batch_get_schedule", "mhpc_batch_get_field", "mhpc_batch_get_phase_params", "mhpc_batch_results_to_device",
     "mhpc_eval_function", "mhpc_batch_enable_timing", "mhpc_batch_get_timing", "mhpc_batch_time_kernel",
     "mhpc_measure_fp64_peak", "mhpc_batch_device_bytes", "mhpc_batch_enable_bws_trace", "mhpc_batch_get_bws_trace",
+    "mhpc_batch_get_iteration_timing", "mhpc_batch_set_eps_smooth", "mhpc_batch_get_eps_smooth",
     "mhpc_sizeof_option", "mhpc_sizeof_problem", "mhpc_sizeof_result", "mhpc_sizeof_iter_record", "mhpc_sizeof_timing", "mhpc_struct_offsets",
 ]
 
@@ -108,6 +114,10 @@ def load():
     L.mhpc_batch_get_bws_trace.argtypes = [vp, ip]
     L.mhpc_batch_enable_timing.argtypes = [vp, C.c_int]
     L.mhpc_batch_get_timing.argtypes = [vp, C.POINTER(Timing)]
+    L.mhpc_batch_set_eps_smooth.argtypes = [vp, C.c_double]
+    L.mhpc_batch_get_eps_smooth.argtypes = [vp]
+    L.mhpc_batch_get_eps_smooth.restype = C.c_double
+    L.mhpc_batch_get_iteration_timing.argtypes = [vp, C.POINTER(IterTiming), C.c_int]
     L.mhpc_batch_time_kernel.argtypes = [vp, C.c_int, C.c_int, C.POINTER(C.c_float)]
     L.mhpc_measure_fp64_peak.argtypes = [C.c_int, dp]
     L.mhpc_batch_device_bytes.argtypes = [vp]
@@ -292,6 +302,14 @@ class BatchedMHPC:
         self._ck(self.L.mhpc_batch_get_timing(self.h, C.byref(t)))
         return {k: getattr(t, k) for k, _ in Timing._fields_}
 
+    def set_eps_smooth(self, v: float): self._ck(self.L.mhpc_batch_set_eps_smooth(self.h, float(v)))
+    def eps_smooth(self) -> float: return float(self.L.mhpc_batch_get_eps_smooth(self.h))
+
+    def iteration_timing(self) -> List[dict]:
+        buf = (IterTiming * 256)()
+        n = self._ck(self.L.mhpc_batch_get_iteration_timing(self.h, buf, 256))
+        return [{k: getattr(r, k) for k, _ in IterTiming._fields_} for r in buf[:n]]
+
     def time_kernel(self, which: int, reps: int) -> float:
         ms = C.c_float()
         self._ck(self.L.mhpc_batch_time_kernel(self.h, which, reps, C.byref(ms)))
@@ -309,6 +327,8 @@ _EVAL_SHAPES = {
     "FBDynamics": ([6, 4, 4, 2], [(6, 1)]), "FBDynamics_par": ([6, 4, 4, 2], [(6, 6), (6, 4)]),
     "WB_FL1_terminal_constr": ([14], [(1, 1), (1, 14), (14, 14)]), "WB_FL2_terminal_constr": ([14], [(1, 1), (1, 14), (14, 14)]),
     "Jacob_F": ([14], [(2, 7)]), "Jacob_B": ([14], [(2, 7)]),
+    "Link0Jacobian": ([14, 2], [(2, 7), (2, 7)]), "Link1Jacobian": ([14, 2], [(2, 7), (2, 7)]), "Link2Jacobian": ([14, 2], [(2, 7), (2, 7)]),
+    "Link3Jacobian": ([14, 2], [(2, 7), (2, 7)]), "Link4Jacobian": ([14, 2], [(2, 7), (2, 7)]),
 }
 
 

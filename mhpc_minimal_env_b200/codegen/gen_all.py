@@ -35,6 +35,9 @@ FUNCTIONS = [
     "FBDynamics", "FBDynamics_par",
     "WB_FL1_terminal_constr", "WB_FL2_terminal_constr",
     "Jacob_F", "Jacob_B",
+    # link-point Jacobians: included by the reference (CasadiGen.h:22-26) but never called (PlanarQuadruped.h:72 is an empty
+    # stub); generated for completeness and reachable through mhpc_eval_function only
+    "Link0Jacobian", "Link1Jacobian", "Link2Jacobian", "Link3Jacobian", "Link4Jacobian",
 ]
 
 # the large Jacobian bodies additionally get a generator-side register allocation (codegen/regalloc.py)

@@ -72,7 +72,9 @@ struct mhpc_batch {
     int alloc_KT = 0, alloc_P = 0;
     // timing
     bool timing = false;
-    struct Ev { cudaEvent_t a, b; int bucket; };
+    struct Ev { cudaEvent_t a, b; int bucket; int iter; };   // iter: inner iteration the stage belongs to (al * 1000 + it), -1: none
+    int cur_iter = -1;
+    std::vector<mhpc_iter_timing> iter_times;
     std::vector<Ev> evs;
     mhpc_timing last{};
     int launches = 0;
@@ -85,7 +87,8 @@ struct mhpc_batch {
     // launch walks in the kernel, widest fan of rungs per instance.  MHPC_LADDER=0 puts the whole ladder back into one launch.
     bool ladder = true;
     int bws_kind = 2;                // backward sweep mapping: 2 = tensor cores, warp per instance (k_bwsT.cu, default); MHPC_BWS=8 / 16: eight / sixteen lanes per instance, DFMA (k_bws.cu, k_bws16.cu)
-    int lad_rounds = 5, lad_first = 2, lad_smax = 16;
+    int lad_rounds = 6, lad_first = 2, lad_smax = 16;
+    double eps_smooth = 1.0;         // AL_REB_PARAMETER::eps_smooth (MHPC_CompoundTypes.h:224): stored, never read - as in the reference
     bool want_bws_trace = false;     // diagnostic: where each attempt of the backward sweep stopped
     int* bws_trace_buf = nullptr;
     size_t bws_trace_cap = 0;
@@ -179,7 +182,7 @@ struct Stage {
     Stage(mhpc_batch* b_, int bucket_) : b(b_), bucket(bucket_), on(b_->timing) {
         if (on) { cudaEventCreate(&a); cudaEventCreate(&e); cudaEventRecord(a, b->stream); }
     }
-    ~Stage() { if (on) { cudaEventRecord(e, b->stream); b->evs.push_back({a, e, bucket}); } }
+    ~Stage() { if (on) { cudaEventRecord(e, b->stream); b->evs.push_back({a, e, bucket, b->cur_iter}); } }
 };
 
 static int gait_next(const mhpc_problem& p, int cur) {   // Gait.h:46-53
@@ -463,6 +466,8 @@ static int set_problems_slots(mhpc_batch* b, const mhpc_problem* pr) {
         rc |= dalloc(b, &d.sd, (size_t)SD_N * npad); rc |= dalloc(b, &d.si, (size_t)SI_N * npad);
         rc |= dalloc(b, &d.rec_i, (size_t)d.max_rec * REC_I * npad); rc |= dalloc(b, &d.rec_d, (size_t)d.max_rec * REC_D * npad);
         rc |= dalloc(b, &d.n_active, 1);
+        // the tensor-core sweep addresses its outputs with 32-bit element offsets
+        if (b->bws_kind == 2 && (double)KT * KDIM * npad >= 4294967296.0) b->bws_kind = 0;
         if (b->ladder) {
             d.lad_cap = b->bws_kind == 2 ? bwsT_resident_warps(b->device) : b->bws_kind == 1 ? bws16_resident_lane_groups(b->device) : bws_resident_lane_groups(b->device);
             const size_t tcap = (size_t)std::max(npad, d.lad_cap);
@@ -780,6 +785,7 @@ int mhpc_batch_solve(mhpc_batch* b, int sync_early_exit) {
     if (b->timing) { cudaEventCreate(&t0); cudaEventCreate(&t1); cudaEventRecord(t0, s); }
     launch_solve_begin(d, s); b->launches++;
     for (int al = 1; al <= maxAL; ++al) {
+        b->cur_iter = al * 1000 + 1;   // the full forward sweep of an outer iteration is booked on its first inner iteration
         { Stage st(b, TB_OTHER); launch_al_begin(d, b->opt, s); b->launches++; }
         if (join_copy(b)) return -1;
         { Stage st(b, TB_ROLLOUT);                                   // forward_sweep(0): rollout ...
@@ -788,6 +794,7 @@ int mhpc_batch_solve(mhpc_batch* b, int sync_early_exit) {
         if (linearize(b, MASK_RUNNING)) return -1;                   // ... and its derivatives
         { Stage st(b, TB_OTHER); if (fork_copy_nominal(b, MASK_RUNNING)) return -1; }   // update_nominal_trajectory
         for (int it = 1; it <= maxDDP; ++it) {
+            b->cur_iter = al * 1000 + it;
             { Stage st(b, TB_OTHER); launch_ls_begin(d, MASK_DDP, s); b->launches++; }
             { Stage st(b, TB_BWS);   // backward_sweep + regularisation retries (MultiPhaseDDP.cpp:209-227)
               auto sweep = b->bws_kind == 2 ? launch_bwsT : b->bws_kind == 1 ? launch_bws16 : launch_bws;
@@ -836,6 +843,24 @@ int mhpc_batch_solve(mhpc_batch* b, int sync_early_exit) {
         t.rollout_ms = acc[TB_ROLLOUT]; t.linearize_ms = acc[TB_LIN]; t.bws_ms = acc[TB_BWS]; t.linesearch_ms = acc[TB_LS]; t.other_ms = acc[TB_OTHER];
         t.n_launches = b->launches;
         b->last = t;
+        // TIME_PER_ITERATION buckets (MHPC_CompoundTypes.h:253-262; MultiPhaseDDP.cpp:163-170,184-192,206-208,228-235,242-253,259-267):
+        // per inner iteration the backward sweep with its retries, the line search and the partials; the full forward sweep of
+        // the outer iteration goes to its first inner iteration
+        b->iter_times.clear();
+        for (auto& e : b->evs) {
+            if (e.iter < 0) continue;
+            mhpc_iter_timing* it = nullptr;
+            for (auto& x : b->iter_times) if (x.iter_AL == e.iter / 1000 && x.iter_DDP == e.iter % 1000) it = &x;
+            if (!it) { b->iter_times.push_back(mhpc_iter_timing{e.iter / 1000, e.iter % 1000, 0, 0, 0, 0, 0}); it = &b->iter_times.back(); }
+            float ms = 0;
+            cudaEventElapsedTime(&ms, e.a, e.b);
+            if (e.bucket == TB_ROLLOUT) it->time_fwd_ms += ms;
+            else if (e.bucket == TB_BWS) it->time_bws_ms += ms;
+            else if (e.bucket == TB_LS) it->time_fit_ms += ms;
+            else if (e.bucket == TB_LIN) { if (e.iter % 1000 == 1 && it->time_fwd_ms > 0 && it->time_bws_ms == 0) it->time_fwd_ms += ms; else it->time_partial_ms += ms; }
+            it->total_ms += ms;
+        }
+        b->cur_iter = -1;
         cudaEventDestroy(t0); cudaEventDestroy(t1);
     }
     return 0;
@@ -1185,8 +1210,10 @@ int mhpc_eval_function(const char* name, int n, int device, const double* in0, c
     const int fn = eval_fn_id(name);
     if (fn < 0) return fail(std::string("mhpc_eval_function: unknown function '") + name + "'");
     CK(cudaSetDevice(device));
-    const int isz[11][4] = {{14, 4, 0, 0}, {14, 4, 0, 0}, {14, 4, 0, 0}, {14, 0, 0, 0}, {14, 0, 0, 0}, {6, 4, 4, 2}, {6, 4, 4, 2}, {14, 0, 0, 0}, {14, 0, 0, 0}, {14, 0, 0, 0}, {14, 0, 0, 0}};
-    const int osz[11][4] = {{14, 4, 0, 0}, {14, 4, 0, 0}, {14, 4, 0, 0}, {14, 4, 0, 0}, {14, 4, 0, 0}, {6, 0, 0, 0}, {36, 24, 0, 0}, {1, 14, 196, 0}, {1, 14, 196, 0}, {14, 0, 0, 0}, {14, 0, 0, 0}};
+    const int isz[16][4] = {{14, 4, 0, 0}, {14, 4, 0, 0}, {14, 4, 0, 0}, {14, 0, 0, 0}, {14, 0, 0, 0}, {6, 4, 4, 2}, {6, 4, 4, 2}, {14, 0, 0, 0}, {14, 0, 0, 0}, {14, 0, 0, 0}, {14, 0, 0, 0},
+                            {14, 2, 0, 0}, {14, 2, 0, 0}, {14, 2, 0, 0}, {14, 2, 0, 0}, {14, 2, 0, 0}};
+    const int osz[16][4] = {{14, 4, 0, 0}, {14, 4, 0, 0}, {14, 4, 0, 0}, {14, 4, 0, 0}, {14, 4, 0, 0}, {6, 0, 0, 0}, {36, 24, 0, 0}, {1, 14, 196, 0}, {1, 14, 196, 0}, {14, 0, 0, 0}, {14, 0, 0, 0},
+                            {14, 14, 0, 0}, {14, 14, 0, 0}, {14, 14, 0, 0}, {14, 14, 0, 0}, {14, 14, 0, 0}};
     const double* hin[4] = {in0, in1, in2, in3};
     double* hout[4] = {o0, o1, o2, o3};
     double* din[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -1236,8 +1263,18 @@ int mhpc_batch_get_bws_trace(mhpc_batch* b, int* out) {
     }
     return (int)rows;
 }
+// Control-smoothness penalty: the reference carries the switch (HSDDP_OPTION::smooth_active, MHPC_CompoundTypes.h:211) and the
+// weight (AL_REB_PARAMETER::eps_smooth, :224), but SinglePhase::update_running_cost_with_smooth is an empty body that nothing
+// calls (SinglePhase.cpp:252-254).  Both values are accepted and kept; like there, they change no result.
+int mhpc_batch_set_eps_smooth(mhpc_batch* b, double eps_smooth) { if (!b) return fail("null handle"); b->eps_smooth = eps_smooth; return 0; }
+double mhpc_batch_get_eps_smooth(mhpc_batch* b) { return b ? b->eps_smooth : 0.0; }
 int mhpc_batch_enable_timing(mhpc_batch* b, int on) { b->timing = on != 0; return 0; }
 int mhpc_batch_get_timing(mhpc_batch* b, mhpc_timing* t) { *t = b->last; return 0; }
+int mhpc_batch_get_iteration_timing(mhpc_batch* b, mhpc_iter_timing* out, int max_records) {
+    const int n = std::min((int)b->iter_times.size(), max_records);
+    for (int k = 0; k < n; ++k) out[k] = b->iter_times[k];
+    return n;
+}
 
 int mhpc_batch_time_kernel(mhpc_batch* b, int which, int reps, float* ms_per_launch) {
     if (need(b)) return -1;

@@ -51,9 +51,23 @@ constexpr int BT_THREADS = 32;
 constexpr int ZSLOT = REC - 1;        // element 175 of a record stage: 0.0 (k_lin writes it as the pad of the last quad of a WB step
                                       // record; no other record kind reaches it; both stages are cleared at kernel start)
 static_assert(WB_STEP_LEN == REC - 1 && WB_TERM_LEN < REC - 1 && RB_STEP_LEN < REC - 1, "the zero slot must be outside every record but the WB step pad");
-constexpr int BT_SCR = 2 * REC;       // scratch behind the two record stages
-constexpr int BT_BAR = 2 * REC + SCR + 14;          // two 8-byte mbarriers (one per stage)
-constexpr int BT_NPH = BT_BAR + 2;                  // knot counts per phase (ints)
+#ifndef BT_AHEAD
+#define BT_AHEAD 2        // knots in flight ahead of the one being computed (1..3); measured 2.31 / 2.25 / 2.27 ms per sweep
+#endif
+#ifndef BT_SYM_MASK
+#define BT_SYM_MASK 0     // Qxx is symmetrised on the knots k with (k & mask) == 0 (every knot, like the reference; mask 3 is not faster)
+#endif
+#ifndef BT_OFF32
+#define BT_OFF32 0          // 32-bit output offsets: slower (2.55 ms), kept for the record
+#endif
+#ifndef BT_CT_SELECT
+#define BT_CT_SELECT 1      // right factor of the output-cost products by selects instead of three more loads
+#endif
+constexpr int BT_NST = BT_AHEAD == 1 ? 2 : 4;       // record stages (a power of two > BT_AHEAD)
+constexpr int BT_NSH = BT_AHEAD == 1 ? 1 : 2;       // log2(BT_NST)
+constexpr int BT_SCR = BT_NST * REC;  // scratch behind the record stages
+constexpr int BT_BAR = BT_NST * REC + SCR + 14;     // one 8-byte mbarrier per stage
+constexpr int BT_NPH = BT_BAR + BT_NST;             // knot counts per phase (ints)
 constexpr size_t BT_SMEM = (size_t)(BT_NPH + MAXP / 2 + 2) * sizeof(double);
 #ifndef BT_MINBLOCKS
 #define BT_MINBLOCKS 16
@@ -161,32 +175,48 @@ __global__ void __launch_bounds__(BT_THREADS, BT_MINBLOCKS) k_bwsT(Dev d, Consts
     double* const dUout = (to_scratch ? d.lad_du : d.dufb) + ocol;
     const unsigned bar_a = smem_u32(smem + BT_BAR), buf_a = smem_u32(bufs);   // shared-window addresses of barrier 0 / stage 0
     if (lane < np) sN[lane] = d.ph_N[ph_idx(d, lane, i)];
-    if (lane < 2) {
+    if (lane < BT_NST) {
         bufs[lane * REC + ZSLOT] = 0.0;
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_a + 8u * lane));
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncwarp();
-    int total_knots = 0;
-    for (int q = 0; q < np; ++q) total_knots += sN[q];
 
-    // ---- record stream: one bulk copy per knot into stage (cnt & 1), issued one knot ahead by lane 0; the barrier of a stage
-    // completes once per use, so its parity is bit 1 of the running knot counter ----
+    // ---- record stream: one bulk copy per knot into stage (cnt % BT_NST), issued BT_AHEAD knots ahead by lane 0 from a cursor
+    // over the knot sequence (phases last to first; in a phase the boundary knot, then the step knots downwards: one
+    // descending run of records).  The barrier of a stage completes once per use, so its parity is the bit of the running
+    // knot counter above the stage index. ----
     unsigned cnt = 0;                               // knots consumed since the kernel started (all attempts)
-    auto fetch = [&](unsigned knot_cnt, const double* src, unsigned bytes) {
-        if (lane == 0) {
-            const unsigned bar = bar_a + 8u * (knot_cnt & 1u), dst = buf_a + (unsigned)(REC * 8) * (knot_cnt & 1u);
-            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+    unsigned fcnt = 0;                              // knots fetched
+    const double* c_src = lin_i;                    // cursor of the next fetch: record, knots left in its phase, phase
+    int c_left = 0, c_p = -1;
+    unsigned c_bytes = 0;
+    auto cursor_phase = [&](int p) {                // put the cursor on the boundary knot of phase p (p < 0: end of the stream)
+        c_p = p;
+        if (p >= 0) {
+            c_left = sN[p];
+            c_src = lin_i + (size_t)(p * KSTRIDE + c_left - 1) * REC;
+            c_bytes = (p < nwb) ? WB_TERM_LEN * 8u : RB_TERM_LEN * 8u;
+        } else c_left = 0;
+    };
+    auto fetch_next = [&]() {                       // issue the copy of the cursor knot, if any, and advance
+        if (c_left > 0) {
+            if (lane == 0) {
+                const unsigned st = fcnt & (BT_NST - 1), bar = bar_a + 8u * st, dst = buf_a + (unsigned)(REC * 8) * st;
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(c_bytes) : "memory");
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(c_src), "r"(c_bytes), "r"(bar) : "memory");
+            }
+            ++fcnt;
+            c_src -= REC;
+            c_bytes = (c_p < nwb) ? (unsigned)REC * 8u : RB_STEP_LEN * 8u;
+            if (--c_left == 0) cursor_phase(c_p - 1);
         }
     };
     auto landed = [&](unsigned knot_cnt) {
-        const unsigned bar = bar_a + 8u * (knot_cnt & 1u), parity = (knot_cnt >> 1) & 1u;
+        const unsigned bar = bar_a + 8u * (knot_cnt & (BT_NST - 1)), parity = (knot_cnt >> BT_NSH) & 1u;
         asm volatile("{\n .reg .pred p;\n WAIT_%=:\n mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n @p bra DONE_%=;\n bra WAIT_%=;\n DONE_%=:\n}" ::"r"(bar), "r"(parity) : "memory");
     };
-    auto term_bytes = [&](int p) -> unsigned { return (p < nwb) ? WB_TERM_LEN * 8u : RB_TERM_LEN * 8u; };
-    auto term_src = [&](int p) -> const double* { return lin_i + (size_t)(p * KSTRIDE + sN[p] - 1) * REC; };
 
     // ---- lane constants shared by all kinds of step knots ----
     const bool gf = g < 7, gev = !(g & 1), hom = g == 7, k1ok = n1 < 7;
@@ -199,9 +229,15 @@ __global__ void __launch_bounds__(BT_THREADS, BT_MINBLOCKS) k_bwsT(Dev d, Consts
     const bool rep_r = qr < 3, rep_c = qc < 3;
     const int oCof = S_QP + qr + 7 * qc;                                  // cofactor of (i, jj) = (g/2, t): elements QP[oCof + a + 7 b], a, b = 1..3
     const double sgn = ((qr + qc) & 1) ? -1.0 : 1.0;
+#if BT_OFF32
+    // output element offsets of this lane (32-bit: the host checks KT * 56 * npad < 2^32)
+    const unsigned ues = (unsigned)es;
+    const unsigned oK = (unsigned)(4 * (gf ? g : 0) + t) * ues, oG = hom ? (unsigned)(7 + n0) * ues : (unsigned)(gf ? g : 0) * ues, oU4 = (unsigned)t * ues;
+#else
     double* const pK1 = Kout + (size_t)(4 * (gf ? g : 0) + t) * es;
     double* const pG = hom ? Gout + (size_t)(7 + n0) * es : Gout + (size_t)(gf ? g : 0) * es;
     double* const pdU = dUout + (size_t)t * es;
+#endif
 
     while (true) {
         // ---- one attempt -----------------------------------------------------------------
@@ -210,7 +246,9 @@ __global__ void __launch_bounds__(BT_THREADS, BT_MINBLOCKS) k_bwsT(Dev d, Consts
         bool failed = false;
         int fail_it = 0, it = 0;
         __syncwarp();
-        if (np > 0) fetch(cnt, term_src(np - 1), term_bytes(np - 1));
+        fcnt = cnt;
+        cursor_phase(np - 1);
+        for (int q = 0; q < BT_AHEAD; ++q) fetch_next();
 
         // the step knots k = N-2 .. 0 of phase p; KIND 0 = whole-body stance, 1 = whole-body flight, 2 = rigid body
         auto run_steps = [&](auto KIND, int p, int N, int mode) {
@@ -266,15 +304,17 @@ __global__ void __launch_bounds__(BT_THREADS, BT_MINBLOCKS) k_bwsT(Dev d, Consts
                 oYt = (t == 0) ? oZt0 : (t == 1) ? oZt1 : ZSLOT; oYb = (t == 0) ? oZb0 : (t == 1) ? oZb1 : ZSLOT; oYu = (t == 0) ? oZu0 : (t == 1) ? oZu1 : ZSLOT;
                 zt2 = hom ? 1.0 : 0.0; cYt = (hom && t == 2) ? 1.0 : 0.0;
             }
-            const unsigned step_bytes = WB ? (unsigned)REC * 8u : RB_STEP_LEN * 8u;
-            const double* src = lin_i + (size_t)(p * KSTRIDE + N - 2) * REC;     // record of the current knot
-            size_t koff = (size_t)(p * KSTRIDE + N - 2) * es;                    // (knot slot) x (instance stride) of the current knot
-            for (int k = N - 2; k >= 0; --k, ++it, ++cnt, koff -= es, src -= REC) {
-                const double* buf = bufs + (cnt & 1u) * REC;
+#if BT_OFF32
+            unsigned koff = (unsigned)(p * KSTRIDE + N - 2) * (unsigned)es;       // (knot slot) x (instance stride) of the current knot
+            for (int k = N - 2; k >= 0; --k, ++it, ++cnt, koff -= (unsigned)es) {
+#else
+            size_t koff = (size_t)(p * KSTRIDE + N - 2) * es;
+            for (int k = N - 2; k >= 0; --k, ++it, ++cnt, koff -= es) {
+#endif
+                const double* buf = bufs + (cnt & (BT_NST - 1)) * REC;
                 landed(cnt);
-                __syncwarp();                        // everyone is done with the other stage (and with the scratch of the previous knot)
-                if (k > 0) fetch(cnt + 1, src - REC, step_bytes);
-                else if (p > 0) fetch(cnt + 1, term_src(p - 1), term_bytes(p - 1));
+                __syncwarp();                        // everyone is done with the stage of the previous knot (and with its scratch)
+                fetch_next();                        // ... which the copy of knot cnt + BT_AHEAD may now overwrite
                 Tile u1 = tzero(), u2 = tzero(), quu = tzero(), q11, q12 = tzero(), q22 = tzero();
                 if (WB) {
                     Tile eT, fT, bT;
@@ -299,10 +339,16 @@ __global__ void __launch_bounds__(BT_THREADS, BT_MINBLOCKS) k_bwsT(Dev d, Consts
                     mm_xyT(quu, w, bT);
                     if (kind == 0) {                 // one k-step each
                         const double lc0 = buf[oL0], lc1 = buf[oL1], lc2 = buf[oL2];
-                        const double xt = (buf[oZt0] * lc0 + buf[oZt1] * lc1) + zt2 * lc2;   // (Z^' L^)[g][t]: top / bottom / input tiles
-                        const double xb = buf[oZb0] * lc0 + buf[oZb1] * lc1;
-                        const double xu = buf[oZu0] * lc0 + buf[oZu1] * lc1;
+                        const double zt0 = buf[oZt0], zt1 = buf[oZt1], zb0 = buf[oZb0], zb1 = buf[oZb1], zu0 = buf[oZu0], zu1 = buf[oZu1];
+                        const double xt = (zt0 * lc0 + zt1 * lc1) + zt2 * lc2;               // (Z^' L^)[g][t]: top / bottom / input tiles
+                        const double xb = zb0 * lc0 + zb1 * lc1;
+                        const double xu = zu0 * lc0 + zu1 * lc1;
+#if BT_CT_SELECT
+                        const double yt = (t == 0) ? zt0 : (t == 1) ? zt1 : cYt;             // Z^[t][g]
+                        const double yb = (t == 0) ? zb0 : (t == 1) ? zb1 : 0.0, yu = (t == 0) ? zu0 : (t == 1) ? zu1 : 0.0;
+#else
                         const double yt = buf[oYt] + cYt, yb = buf[oYb], yu = buf[oYu];      // Z^[t][g]
+#endif
                         dmma(q11.c0, q11.c1, xt, yt);
                         dmma(q12.c0, q12.c1, xt, yb);
                         dmma(q22.c0, q22.c1, xb, yb);
@@ -332,8 +378,11 @@ __global__ void __launch_bounds__(BT_THREADS, BT_MINBLOCKS) k_bwsT(Dev d, Consts
                 if (lane == 31) q11.c1 = 0.0;                            // [hom][hom]: the constant term is not carried
                 // Qxx = (Qxx + Qxx')/2 on the diagonal tiles (the off-diagonal block is one tile used for both halves);
                 // Quu = (Quu + Quu')/2 -> doubly periodic table
-                *reinterpret_cast<double2*>(scr + sOwn) = make_double2(q11.c0, q11.c1);
-                if (WB) *reinterpret_cast<double2*>(scr + sOwn + 80) = make_double2(q22.c0, q22.c1);
+                const bool do_sym = BT_SYM_MASK == 0 || ((k & BT_SYM_MASK) == 0);   // rounding-level asymmetry only
+                if (do_sym) {
+                    *reinterpret_cast<double2*>(scr + sOwn) = make_double2(q11.c0, q11.c1);
+                    if (WB) *reinterpret_cast<double2*>(scr + sOwn + 80) = make_double2(q22.c0, q22.c1);
+                }
                 const double qv = (quu.c0 + __shfl_sync(FULL, quu.c0, src_T)) / 2;   // Quu(g/2, t), symmetrised
                 if (gev) {
                     scr[oQP] = qv;
@@ -342,8 +391,10 @@ __global__ void __launch_bounds__(BT_THREADS, BT_MINBLOCKS) k_bwsT(Dev d, Consts
                     if (rep_r && rep_c) scr[oQP + 32] = qv;
                 }
                 __syncwarp();
-                q11.c0 = (q11.c0 + scr[sT0]) / 2; q11.c1 = (q11.c1 + scr[sT1]) / 2;
-                if (WB) { q22.c0 = (q22.c0 + scr[sT0 + 80]) / 2; q22.c1 = (q22.c1 + scr[sT1 + 80]) / 2; }
+                if (do_sym) {
+                    q11.c0 = (q11.c0 + scr[sT0]) / 2; q11.c1 = (q11.c1 + scr[sT1]) / 2;
+                    if (WB) { q22.c0 = (q22.c0 + scr[sT0 + 80]) / 2; q22.c1 = (q22.c1 + scr[sT1 + 80]) / 2; }
+                }
                 // ---- 4x4 part: positive-definite test, my entry of the cofactor inverse ----
                 int pd = pd_by_minors(scr + S_QP, opt.quu_shift);
                 if (pd < 0) {
@@ -380,6 +431,27 @@ __global__ void __launch_bounds__(BT_THREADS, BT_MINBLOCKS) k_bwsT(Dev d, Consts
                 if (lane == 31) q11.c1 = 0.0;
                 T11 = q11; T12 = q12; T22 = q22;
                 // K (4 x nx column-major), du, G of this knot
+#if BT_OFF32
+                const unsigned kK = koff * KDIM + oK, kG = koff * 14 + oG;
+                if (WB) {
+                    if (gf) {
+                        Kout[kK] = kt1.c0;
+                        Kout[kK + 28 * ues] = kt2.c0;
+                        if (t == 3) Gout[kG] = T11.c1;
+                    } else {
+                        dUout[koff * 4 + oU4] = kt1.c0;
+                        Gout[kG] = T12.c0;
+                        if (k1ok) Gout[kG + ues] = T12.c1;
+                    }
+                } else {
+                    if (g6) {
+                        Kout[kK] = kt1.c0;
+                        if (t == 3) Gout[kG] = T11.c1;
+                    } else if (hom) {
+                        dUout[koff * 4 + oU4] = kt1.c0;
+                    }
+                }
+#else
                 if (WB) {
                     if (gf) {
                         pK1[koff * KDIM] = kt1.c0;
@@ -398,6 +470,7 @@ __global__ void __launch_bounds__(BT_THREADS, BT_MINBLOCKS) k_bwsT(Dev d, Consts
                         pdU[koff * 4] = kt1.c0;
                     }
                 }
+#endif
             }
         };
 
@@ -407,11 +480,10 @@ __global__ void __launch_bounds__(BT_THREADS, BT_MINBLOCKS) k_bwsT(Dev d, Consts
             const int mode = d.ph_mode[ph_idx(d, p, i)];
             // ============ phase boundary (last knot of the phase): tiles -> rows, the row code of k_bws.cu, rows -> tiles ============
             {
-                const double* buf = bufs + (cnt & 1u) * REC;
+                const double* buf = bufs + (cnt & (BT_NST - 1)) * REC;
                 landed(cnt);
                 __syncwarp();
-                if (N > 1) fetch(cnt + 1, lin_i + (size_t)(p * KSTRIDE + N - 2) * REC, wb ? (unsigned)REC * 8u : RB_STEP_LEN * 8u);
-                else if (p > 0) fetch(cnt + 1, term_src(p - 1), term_bytes(p - 1));
+                fetch_next();
                 const int kk = p * KSTRIDE + N - 1;
                 const bool last = (p == np - 1);
                 const bool next_rb = !last && (p + 1 >= nwb);
@@ -542,9 +614,9 @@ __global__ void __launch_bounds__(BT_THREADS, BT_MINBLOCKS) k_bwsT(Dev d, Consts
         // after a failure the copy issued for the knot behind the failing one is still in flight: wait for it, so that the
         // next attempt starts with idle stages and barriers
         __syncwarp();
-        if (failed) {   // the failing knot used counter value cnt; the knot behind it (if any) was fetched as cnt + 1: wait, then skip both
-            if (it + 1 < total_knots) { landed(cnt + 1); cnt += 2; }
-            else cnt += 1;
+        if (failed) {   // the failing knot used counter value cnt; the knots behind it that are in flight: wait for them, skip them
+            for (unsigned q = cnt + 1; q < fcnt; ++q) landed(q);
+            cnt = fcnt;
         }
         __syncwarp();
         double dV = dVp;                                                 // sum of the four lanes of row "hom"

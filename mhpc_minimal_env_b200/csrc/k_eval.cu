@@ -8,7 +8,7 @@
 
 namespace mhpc {
 
-enum { EV_DYN_BS = 0, EV_DYN_FS, EV_DYN_FL, EV_IMP_F, EV_IMP_B, EV_FB, EV_FB_PAR, EV_TC1, EV_TC2, EV_JF, EV_JB };
+enum { EV_DYN_BS = 0, EV_DYN_FS, EV_DYN_FL, EV_IMP_F, EV_IMP_B, EV_FB, EV_FB_PAR, EV_TC1, EV_TC2, EV_JF, EV_JB, EV_LINK0, EV_LINK1, EV_LINK2, EV_LINK3, EV_LINK4 };
 
 __global__ void k_eval(int fn, int n, const double* in0, const double* in1, const double* in2, const double* in3,
                        double* o0, double* o1, double* o2, double* o3) {
@@ -55,6 +55,12 @@ __global__ void k_eval(int fn, int n, const double* in0, const double* in1, cons
         o0[t] = h;
         for (int e = 0; e < 14; ++e) o1[(size_t)t * 14 + e] = hx[e];
         for (int e = 0; e < 196; ++e) o2[(size_t)t * 196 + e] = hxx[e];
+    } else if (fn >= EV_LINK0) {
+        double x[14], pt[2], J[14], Jd[14];
+        for (int e = 0; e < 14; ++e) { x[e] = in0[(size_t)t * 14 + e]; J[e] = 0.0; Jd[e] = 0.0; }
+        pt[0] = in1[(size_t)t * 2]; pt[1] = in1[(size_t)t * 2 + 1];
+        link_jacobian(fn - EV_LINK0, x, pt, J, Jd);
+        for (int e = 0; e < 14; ++e) { o0[(size_t)t * 14 + e] = J[e]; o1[(size_t)t * 14 + e] = Jd[e]; }
     } else {
         double x[14], J[14];
         for (int e = 0; e < 14; ++e) { x[e] = in0[(size_t)t * 14 + e]; J[e] = 0.0; }
@@ -65,8 +71,9 @@ __global__ void k_eval(int fn, int n, const double* in0, const double* in1, cons
 
 int eval_fn_id(const char* name) {
     const char* names[] = {"Dyn_BS", "Dyn_FS", "Dyn_FL", "Imp_F", "Imp_B", "FBDynamics", "FBDynamics_par",
-                           "WB_FL1_terminal_constr", "WB_FL2_terminal_constr", "Jacob_F", "Jacob_B"};
-    for (int i = 0; i < 11; ++i)
+                           "WB_FL1_terminal_constr", "WB_FL2_terminal_constr", "Jacob_F", "Jacob_B",
+                           "Link0Jacobian", "Link1Jacobian", "Link2Jacobian", "Link3Jacobian", "Link4Jacobian"};
+    for (int i = 0; i < 16; ++i)
         if (!strcmp(name, names[i])) return i;
     return -1;
 }

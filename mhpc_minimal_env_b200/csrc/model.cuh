@@ -97,6 +97,24 @@ static __device__ __forceinline__ void jacob_b(const double* x, double* J) {
 }
 #undef SX_OUT
 #undef SX_IN
+// ---- link-point Jacobians J, Jdot (2x7) of a point p (2) on link 0..4: dormant in the reference (CasadiGen.h:22-26) ----
+#define SX_IN(i, j) ((i) == 0 ? x[j] : pt[j])
+#define SX_OUT(k, nz, row, col, v) do { if ((k) == 0) J[(row) + 2 * (col)] = (v); else Jd[(row) + 2 * (col)] = (v); } while (0)
+static __device__ __forceinline__ void link_jacobian(int link, const double* x, const double* pt, double* J, double* Jd) {
+    if (link == 0) {
+#include "gen/Link0Jacobian.inc"
+    } else if (link == 1) {
+#include "gen/Link1Jacobian.inc"
+    } else if (link == 2) {
+#include "gen/Link2Jacobian.inc"
+    } else if (link == 3) {
+#include "gen/Link3Jacobian.inc"
+    } else {
+#include "gen/Link4Jacobian.inc"
+    }
+}
+#undef SX_OUT
+#undef SX_IN
 // ---- rigid-body model: xdot(6) from x, u, foothold(4), contact(2) -------------------------
 #define SX_IN(i, j) ((i) == 0 ? x[j] : (i) == 1 ? u[j] : (i) == 2 ? fh[j] : ct[j])
 #define SX_OUT(k, nz, row, col, v) do { xdot[row] = (v); } while (0)

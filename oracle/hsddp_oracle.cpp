@@ -24,6 +24,7 @@ ORC_DECL(Imp_F) ORC_DECL(Imp_B) ORC_DECL(Imp_F_par) ORC_DECL(Imp_B_par)
 ORC_DECL(FBDynamics) ORC_DECL(FBDynamics_par)
 ORC_DECL(WB_FL1_terminal_constr) ORC_DECL(WB_FL2_terminal_constr)
 ORC_DECL(Jacob_F) ORC_DECL(Jacob_B)
+ORC_DECL(Link0Jacobian) ORC_DECL(Link1Jacobian) ORC_DECL(Link2Jacobian) ORC_DECL(Link3Jacobian) ORC_DECL(Link4Jacobian)
 #undef ORC_DECL
 }
 
@@ -1122,6 +1123,7 @@ int orc_eval(const char* name, const double* a0, const double* a1, const double*
     TRY(FBDynamics, 4, 1) TRY(FBDynamics_par, 4, 2)
     TRY(WB_FL1_terminal_constr, 1, 3) TRY(WB_FL2_terminal_constr, 1, 3)
     TRY(Jacob_F, 1, 2) TRY(Jacob_B, 1, 2)
+    TRY(Link0Jacobian, 2, 2) TRY(Link1Jacobian, 2, 2) TRY(Link2Jacobian, 2, 2) TRY(Link3Jacobian, 2, 2) TRY(Link4Jacobian, 2, 2)
 #undef TRY
     return -1;
 }

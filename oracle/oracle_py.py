@@ -192,6 +192,8 @@ _SHAPES = {  # name -> (n_in, in sizes, out shapes)
     "WB_FL1_terminal_constr": ([14], [(1, 1), (1, 14), (14, 14)]),
     "WB_FL2_terminal_constr": ([14], [(1, 1), (1, 14), (14, 14)]),
     "Jacob_F": ([14], [(2, 7), (2, 7)]), "Jacob_B": ([14], [(2, 7), (2, 7)]),
+    "Link0Jacobian": ([14, 2], [(2, 7), (2, 7)]), "Link1Jacobian": ([14, 2], [(2, 7), (2, 7)]), "Link2Jacobian": ([14, 2], [(2, 7), (2, 7)]),
+    "Link3Jacobian": ([14, 2], [(2, 7), (2, 7)]), "Link4Jacobian": ([14, 2], [(2, 7), (2, 7)]),
 }
 
 

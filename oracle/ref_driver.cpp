@@ -3,7 +3,14 @@
 // oracle/eigen_shim) so that tests can pin the restatement in hsddp_oracle.cpp against the reference itself.
 // `private` is opened for this translation unit only, to set a per-instance x0 (hard-coded in MHPCLocomotion.cpp:37-39)
 // and to read the trajectory arrays that print_debugInfo dumps (MHPCLocomotion.cpp:293-380).
+#include <algorithm>
 #include <cstring>
+#include <fstream>
+#include <iostream>
+#include <sstream>
+#include <string>
+#include <vector>
+#include <unistd.h>
 #define private public
 #define protected public
 #include "MHPCLocomotion.h"
@@ -54,6 +61,14 @@ void ref_solve(void* p) { ((RefHandle*)p)->loco->solve_mhpc(); }
 void ref_scalars(void* p, double* out3) {
     MHPCLocomotion<double>* l = ((RefHandle*)p)->loco;
     out3[0] = l->_actual_cost; out3[1] = l->_exp_cost_change; out3[2] = l->_tconstr_violation;
+}
+// MHPCLocomotion::print_debugInfo (MHPCLocomotion.cpp:293-380) writes state.txt, control.txt, gradient.txt, cost.txt into the
+// current directory: run it inside `dir`
+int ref_print_debugInfo(void* p, const char* dir) {
+    char cwd[4096];
+    if (!getcwd(cwd, sizeof(cwd)) || chdir(dir) != 0) return -1;
+    ((RefHandle*)p)->loco->print_debugInfo();
+    return chdir(cwd);
 }
 int ref_n_phases(void* p) { return ((RefHandle*)p)->loco->_n_phases; }
 void ref_schedule(void* p, int* mode, int* N) {

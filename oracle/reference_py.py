@@ -84,6 +84,12 @@ class ReferenceSolver:
         with quiet_stdout():
             return self.L.ref_forward_iteration(self.h)
 
+    def print_debugInfo(self, directory: str):
+        """the reference's own print_debugInfo: writes state.txt / control.txt / gradient.txt / cost.txt into `directory`"""
+        with quiet_stdout():
+            rc = self.L.ref_print_debugInfo(self.h, str(directory).encode())
+        assert rc == 0
+
     def scalars(self):
         o = (C.c_double * 3)()
         self.L.ref_scalars(self.h, o)

@@ -70,6 +70,14 @@ def test_generated_functions_match_reference_objects():
             assert e < TOL_JAC, (name, i, e)
             assert np.array_equal(got[0][i][:7, :], np.hstack([np.eye(7), np.zeros((7, 7))]))   # identity block of Px, exact
     print("worst per-matrix relative error of the Jacobian functions:", {k: "%.2e" % v for k, v in worst.items()})
+    # dormant in the reference, generated all the same: link-point Jacobians J, Jdot of a point p on link 0..4
+    P2 = rng.uniform(-0.2, 0.2, size=(n, 2))
+    for name in ("Link0Jacobian", "Link1Jacobian", "Link2Jacobian", "Link3Jacobian", "Link4Jacobian"):
+        got = m.eval_function(name, X, P2)
+        for i in range(n):
+            ref = eval_fn(name, X[i], P2[i])
+            for g, r in zip(got, ref):
+                assert relerr(g[i], r) < TOL_JAC, name
     xr = rng.normal(size=(n, 6))
     fh = rng.normal(size=(n, 4))
     for ct in ([0.0, 1.0], [1.0, 0.0], [0.0, 0.0]):
@@ -284,6 +292,24 @@ def test_solved_trajectories_and_gains_64_instances(cfg):
     assert len(skipped) <= 2
     for nm, (e, i, p) in worst.items():
         assert e < TOL_TRAJ, (cfg, nm, e, "instance", i, "phase", p)
+
+
+def test_smoothness_penalty_is_dormant_like_the_reference():
+    """SURVEY 8(f4): HSDDP_OPTION::smooth_active / AL_REB_PARAMETER::eps_smooth are carried by the reference, but
+    update_running_cost_with_smooth is an empty body that nothing calls (SinglePhase.cpp:252-254).  Same here: both are accepted
+    through the ABI and change nothing - results, records and trajectories are bit-identical."""
+    import mhpc_minimal_env_b200 as m
+    probs = [to_gpu_problem(s) for s in make_specs(16, 2)]
+    outs = []
+    for smooth, eps in ((0, 1.0), (1, 5.0)):
+        b = m.BatchedMHPC(probs, m.default_option(smooth_active=smooth))
+        b.set_eps_smooth(eps)
+        assert b.eps_smooth() == eps
+        b.initialization()
+        b.solve()
+        outs.append((b.results_array().tobytes(), [b.records(i) for i in range(16)], b.field(3, 0, "X_NOM").tobytes(), b.field(3, 1, "K").tobytes()))
+        b.close()
+    assert outs[0] == outs[1]
 
 
 def test_fixed_iteration_budget_and_early_exit_agree():
@@ -589,8 +615,55 @@ def test_cpp_batched_test_main_reproduces_default_run(tmp_path):
            [(r["iter_AL"], r["iter_DDP"], r["n_bws"], r["n_fit"]) for r in gold["records"]]
     lines = open(os.path.join(str(tmp_path), "state.txt")).read().splitlines()   # print_debugInfo: one knot per line
     assert len(lines) == 720 and len(lines[0].split()) == 14 and len(lines[-1].split()) == 6
-    assert abs(float(lines[0].split()[0]) - 0.0927) < 1e-15
-    assert abs(float(lines[0].split()[13]) - gold["final"]["x_first"][13]) < 1e-12
+    assert lines[0] == " 0.0927 -0.1093 -0.1542  1.0957 -2.2033  0.9742 -1.7098  0.9011  0.2756  0.7333  0.0446  0.0009  1.3219  2.7346"   # Eigen's format
+    assert abs(float(lines[0].split()[13]) - gold["final"]["x_first"][13]) < 1e-5
+
+
+def test_print_debugInfo_files_match_the_reference(tmp_path):
+    """SURVEY 8(f3): the four text dumps of MHPCLocomotion::print_debugInfo (MHPCLocomotion.cpp:293-380) and the
+    TIME_PER_ITERATION table.  The reference's OWN print_debugInfo (oracle/_ref/libmhpc_reference, the unmodified sources) and
+    include/mhpc_b200.hpp write state / control / gradient / cost.txt for the default problem with the fixed 2x3 budget; the
+    files must have the same lines, the same number of columns per line (Eigen's aligned default format) and the same numbers
+    to the 6 significant digits the format carries."""
+    import os
+    import subprocess
+    from oracle import reference_py
+    if not reference_py.available("strict"):
+        pytest.skip("oracle/_ref/libmhpc_reference_strict.so is not built")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    lib = os.path.join(root, "mhpc_minimal_env_b200", "libmhpc_b200.so")
+    exe = str(tmp_path / "test_main_batched")
+    subprocess.check_call(["g++", "-std=c++14", "-I", os.path.join(root, "include"), os.path.join(root, "examples", "test_main_batched.cpp"),
+                           lib, "-Wl,-rpath," + os.path.dirname(lib), "-o", exe])
+    ours = tmp_path / "ours"
+    ours.mkdir()
+    out = subprocess.run([exe, "2", "1"], capture_output=True, text=True, cwd=str(ours), check=True).stdout
+    ref = reference_py.ReferenceSolver(make_specs(1, 1)[0], "strict", DDP_thresh=-1.0, AL_thresh=-1.0)
+    ref.initialization()
+    ref.solve()
+    theirs = tmp_path / "theirs"
+    theirs.mkdir()
+    ref.print_debugInfo(str(theirs))
+    worst = 0.0
+    for name, rows in (("state.txt", 720), ("control.txt", 720), ("gradient.txt", 720), ("cost.txt", 720)):
+        a = open(ours / name).read().splitlines()
+        b = open(theirs / name).read().splitlines()
+        assert len(a) == len(b) == rows, (name, len(a), len(b))
+        for k, (la, lb) in enumerate(zip(a, b)):
+            va, vb = [float(x) for x in la.split()], [float(x) for x in lb.split()]
+            assert len(va) == len(vb), (name, k)
+            scale = max(max(abs(x) for x in vb), 1e-300)
+            for x, y in zip(va, vb):     # 6 significant digits per number; entries far below the row's scale carry the knot's rounding noise
+                err = abs(x - y) / max(abs(y), 1e-4 * scale)
+                worst = max(worst, err)
+                assert err < 5e-5, (name, k, x, y)
+    print("print_debugInfo files: worst relative difference of any number %.2e (6-digit format)" % worst)
+    # TIME_PER_ITERATION (MHPC_CompoundTypes.h:253-262): six records, the reference's n_bws pattern 2,1,1 (SURVEY A.2-7), times filled
+    rows = [ln.split() for ln in out.splitlines() if ln.startswith("time_ddp")]
+    assert len(rows) == 6
+    assert [int(r[2]) for r in rows] == [1, 2, 3, 4, 5, 6]
+    assert [int(r[4]) for r in rows][:3] == [2, 1, 1]
+    assert all(float(r[6]) > 0 and float(r[11]) > 0 and float(r[14]) > 0 for r in rows)
 
 
 def test_odd_shapes_and_start_modes():
