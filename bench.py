@@ -170,6 +170,9 @@ def main():
     # (2 warps/scheduler): four slots per launch, with a second launch for the few instances that need trials 5+, is faster
     # (line search 8.5 ms instead of 12.0 ms per solve); the outcome is the same (tests: line-search width invariance)
     ap.add_argument("--ls-width", type=int, default=4)
+    # BASELINE config 5: ONE batch of this many instances split over the ranks (strong scaling); default: weak scaling,
+    # --instances per GPU
+    ap.add_argument("--strong-total", type=int, default=0)
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -203,7 +206,7 @@ def main():
             os.close(saved_stdout)
 
     from mhpc_minimal_env_b200.sharding import gather_result_table, shard_range
-    n = args.instances
+    n = args.instances if not args.strong_total else (args.strong_total + world - 1) // world
     # weak scaling: n instances per rank; the job of n*world instances is sharded by instance into contiguous blocks
     # (no collective inside the solve)
     g_begin, g_end = shard_range(n * world, rank, world)
@@ -368,7 +371,7 @@ def main():
             pass
         cpu_v = cpu_baseline_single(args.cpu_sample)
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if args.strong_total else "weak", "vs_baseline": None, "dtype": "f64",
                 "data": "synthetic",
                 "config": {"workload": workload_name(n), "instances_per_gpu": n, "hsddp_budget": "2x3 (DDP_thresh=AL_thresh=-1)",
                            "ls_width": args.ls_width, "l2": "working set (>10 GB/GPU) far exceeds the 126 MB L2; no explicit flush",

@@ -88,6 +88,9 @@ struct mhpc_batch {
     bool ladder = true;
     int bws_kind = 2;                // backward sweep mapping: 2 = tensor cores, warp per instance (k_bwsT.cu, default); MHPC_BWS=8 / 16: eight / sixteen lanes per instance, DFMA (k_bws.cu, k_bws16.cu)
     int lad_rounds = 6, lad_first = 2, lad_smax = 16;
+    bool lad_sync = true;            // read the count of unresolved instances back after each round (one short host wait) instead of
+                                     // launching a fixed number of rounds blind; MHPC_LADDER_SYNC=0 keeps the solve free of host waits
+    int* h_unres = nullptr;          // pinned
     double eps_smooth = 1.0;         // AL_REB_PARAMETER::eps_smooth (MHPC_CompoundTypes.h:224): stored, never read - as in the reference
     bool want_bws_trace = false;     // diagnostic: where each attempt of the backward sweep stopped
     int* bws_trace_buf = nullptr;
@@ -276,6 +279,8 @@ int mhpc_batch_create(int n, const mhpc_hsddp_option* opt, int device, int ls_wi
     { const char* e = getenv("MHPC_LADDER"); if (e) b->ladder = e[0] != '0'; }
     { const char* e = getenv("MHPC_BWS"); if (e) b->bws_kind = (e[0] == 'T' || e[0] == 't') ? 2 : (!strcmp(e, "16") ? 1 : (!strcmp(e, "8") ? 0 : 2)); }
     { const char* e = getenv("MHPC_LADDER_ROUNDS"); if (e && atoi(e) > 0) b->lad_rounds = atoi(e); }
+    { const char* e = getenv("MHPC_LADDER_SYNC"); if (e) b->lad_sync = e[0] != '0'; }
+    CK(cudaHostAlloc((void**)&b->h_unres, sizeof(int), cudaHostAllocDefault));
     { const char* e = getenv("MHPC_LADDER_FIRST"); if (e && atoi(e) > 0) b->lad_first = atoi(e); }
     { const char* e = getenv("MHPC_LADDER_SMAX"); if (e && atoi(e) > 0) b->lad_smax = atoi(e); }
     *out = b;
@@ -289,6 +294,7 @@ void mhpc_batch_destroy(mhpc_batch* b) {
     if (b->stage) cudaFree(b->stage);
     if (b->rot_tmp) cudaFree(b->rot_tmp);
     if (b->bws_trace_buf) cudaFree(b->bws_trace_buf);
+    if (b->h_unres) cudaFreeHost(b->h_unres);
     if (b->d_user_of) cudaFree(b->d_user_of);
     if (b->side) { cudaStreamDestroy(b->side); cudaEventDestroy(b->ev_fork); cudaEventDestroy(b->ev_join); }
     if (b->side2) { cudaStreamDestroy(b->side2); cudaEventDestroy(b->ev_cfork); cudaEventDestroy(b->ev_cjoin); }
@@ -801,15 +807,30 @@ int mhpc_batch_solve(mhpc_batch* b, int sync_early_exit) {
               if (!b->ladder) { sweep(d, b->c, b->opt, MASK_DDP, 0, 0, s); b->launches++; }
               else {
                   sweep(d, b->c, b->opt, MASK_DDP, 0, b->lad_first, s); b->launches++;
-                  for (int r = 1; r <= b->lad_rounds; ++r) {
-                      const int last = r == b->lad_rounds;
-                      if (b->bws_kind == 0) launch_bws_ladder_round(d, b->c, b->opt, MASK_DDP, last, b->lad_smax, s);
-                      else {
-                          launch_lad_plan(d, b->opt, MASK_DDP, last, b->lad_smax, s);
-                          if (b->bws_kind == 2) launch_bwsT_tasks(d, b->c, b->opt, MASK_DDP, s); else launch_bws16_tasks(d, b->c, b->opt, MASK_DDP, s);
-                          launch_lad_finish(d, b->opt, s);
+                  auto round = [&](int last) {
+                      if (b->bws_kind == 2) launch_bwsT_tasks(d, b->c, b->opt, MASK_DDP, s); else if (b->bws_kind == 1) launch_bws16_tasks(d, b->c, b->opt, MASK_DDP, s);
+                      else launch_bws_tasks(d, b->c, b->opt, MASK_DDP, s);
+                      launch_lad_finish(d, b->opt, s);
+                      b->launches += 3;
+                      (void)last;
+                  };
+                  if (b->lad_sync) {
+                      // plan -> how many instances still have no passing rung? -> tasks, resolve, copy; until none is left.  One
+                      // 4-byte read-back per round: a stage whose first launch settles everything (5 of the 6 stages of the bench
+                      // workload) costs one plan kernel and one short wait instead of rounds of empty launches.
+                      for (int r = 1; r <= 64; ++r) {
+                          launch_lad_plan(d, b->opt, MASK_DDP, 0, b->lad_smax, s); b->launches++;
+                          CK(cudaMemcpyAsync(b->h_unres, d.lad_cnt + LAD_N_UNRES, sizeof(int), cudaMemcpyDeviceToHost, s));
+                          CK(cudaStreamSynchronize(s));
+                          if (*b->h_unres == 0) break;
+                          round(0);
                       }
-                      b->launches += 4;
+                  } else {
+                      for (int r = 1; r <= b->lad_rounds; ++r) {
+                          const int last = r == b->lad_rounds;
+                          launch_lad_plan(d, b->opt, MASK_DDP, last, b->lad_smax, s); b->launches++;
+                          round(last);
+                      }
                   }
               } }
             if (line_search(b, MASK_LS, MASK_DDP)) return -1;
@@ -1242,6 +1263,7 @@ int mhpc_batch_enable_bws_trace(mhpc_batch* b, int on) {
     if (b->bws_trace_cap < cnt) {
         CK(cudaStreamSynchronize(b->stream));
         if (b->bws_trace_buf) cudaFree(b->bws_trace_buf);
+    if (b->h_unres) cudaFreeHost(b->h_unres);
         CK(cudaMalloc(&b->bws_trace_buf, cnt * sizeof(int)));
         b->bws_trace_cap = cnt;
     }

@@ -663,16 +663,18 @@ __global__ void k_lad_copy(Dev d) {
     if (cidx >= d.lad_cnt[LAD_N_UNRES]) return;
     const int t = d.lad_u_copy[cidx];
     if (t < 0) return;
-    const int i = d.lad_u_inst[cidx], kk = blockIdx.x;
-    int p, k;
-    if (!knot_to_phase(d, i, kk, p, k)) return;
-    const int nx = (p < d.n_wb[i]) ? 14 : 6;
-    const bool term = (k == d.ph_N[ph_idx(d, p, i)] - 1);
+    const int i = d.lad_u_inst[cidx];
     const size_t ces = d.npad, es = d.npad;
-    for (int e = 0; e < nx; ++e) d.Gv[((size_t)kk * 14 + e) * es + i] = d.lad_G[((size_t)kk * 14 + e) * ces + t];
-    if (term) return;
-    for (int e = 0; e < 4 * nx; ++e) d.Kfb[((size_t)kk * KDIM + e) * es + i] = d.lad_K[((size_t)kk * KDIM + e) * ces + t];
-    for (int e = 0; e < 4; ++e) d.dufb[((size_t)kk * 4 + e) * es + i] = d.lad_du[((size_t)kk * 4 + e) * ces + t];
+    for (int kk = blockIdx.x; kk < d.KT; kk += gridDim.x) {
+        int p, k;
+        if (!knot_to_phase(d, i, kk, p, k)) continue;
+        const int nx = (p < d.n_wb[i]) ? 14 : 6;
+        const bool term = (k == d.ph_N[ph_idx(d, p, i)] - 1);
+        for (int e = 0; e < nx; ++e) d.Gv[((size_t)kk * 14 + e) * es + i] = d.lad_G[((size_t)kk * 14 + e) * ces + t];
+        if (term) continue;
+        for (int e = 0; e < 4 * nx; ++e) d.Kfb[((size_t)kk * KDIM + e) * es + i] = d.lad_K[((size_t)kk * KDIM + e) * ces + t];
+        for (int e = 0; e < 4; ++e) d.dufb[((size_t)kk * 4 + e) * es + i] = d.lad_du[((size_t)kk * 4 + e) * ces + t];
+    }
 }
 
 void launch_bws(const Dev& d, const Consts& c, const Opt& opt, int mask_mode, int single_attempt, int max_attempts, cudaStream_t s) {
@@ -685,15 +687,13 @@ void launch_lad_plan(const Dev& d, const Opt& opt, int mask_mode, int last_round
 }
 void launch_lad_finish(const Dev& d, const Opt& opt, cudaStream_t s) {
     k_lad_resolve<<<(d.n + 127) / 128, 128, 0, s>>>(d, opt);
-    dim3 g(d.KT, (std::min(d.lad_cap, d.npad) / 2 + 127) / 128);   // a winner is copied only when S >= 2, i.e. unresolved <= min(cap, npad) / 2
+    dim3 g(std::min(d.KT, 128), (std::min(d.lad_cap, d.npad) / 2 + 127) / 128);   // a winner is copied only when S >= 2, i.e. unresolved <= min(cap, npad) / 2
     k_lad_copy<<<g, 128, 0, s>>>(d);
 }
-void launch_bws_ladder_round(const Dev& d, const Consts& c, const Opt& opt, int mask_mode, int last_round, int smax, cudaStream_t s) {
+void launch_bws_tasks(const Dev& d, const Consts& c, const Opt& opt, int mask_mode, cudaStream_t s) {
     cudaFuncSetAttribute(k_bws<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BWS_SMEM);
-    launch_lad_plan(d, opt, mask_mode, last_round, smax, s);
     const int tcap = d.npad > d.lad_cap ? d.npad : d.lad_cap;
     k_bws<1><<<(tcap + BWS_INST - 1) / BWS_INST, BWS_THREADS, BWS_SMEM, s>>>(d, c, opt, mask_mode, 0, 0);
-    launch_lad_finish(d, opt, s);
 }
 // lane groups of k_bws that are resident at once on this device
 int bws_resident_lane_groups(int device) {

@@ -65,7 +65,7 @@ void launch_par_eval_IMPB(int n, size_t es, const double* st, double* o0, double
 // backward sweep (k_bws.cu)
 // max_attempts > 0 (with the ladder scheduler allocated): stop walking the ladder in the kernel after that many rungs
 void launch_bws(const Dev& d, const Consts& c, const Opt& o, int mask_mode, int single_attempt, int max_attempts, cudaStream_t s);
-void launch_bws_ladder_round(const Dev& d, const Consts& c, const Opt& o, int mask_mode, int last_round, int smax, cudaStream_t s);
+void launch_bws_tasks(const Dev& d, const Consts& c, const Opt& o, int mask_mode, cudaStream_t s);
 int bws_resident_lane_groups(int device);
 // the same sweep with sixteen lanes per instance (k_bws16.cu)
 void launch_bws16(const Dev& d, const Consts& c, const Opt& o, int mask_mode, int single_attempt, int max_attempts, cudaStream_t s);

@@ -493,8 +493,8 @@ def test_line_search_width_invariance(cfg):
                 assert abs(x["cost"] - y["cost"]) <= 1e-8 * abs(x["cost"]), (width, i, x["cost"], y["cost"])
 
 
-@pytest.mark.parametrize("cfg,rounds,first", [(2, 4, 2), (4, 4, 2), (4, 1, 1), (3, 2, 3), (4, 3, 2)])
-def test_regularisation_ladder_scheduler_equals_sequential_retries(cfg, rounds, first, monkeypatch):
+@pytest.mark.parametrize("cfg,rounds,first,sync", [(2, 4, 2, 1), (4, 4, 2, 1), (3, 4, 1, 1), (2, 4, 2, 0), (4, 1, 1, 0), (3, 2, 3, 0), (4, 3, 2, 0)])
+def test_regularisation_ladder_scheduler_equals_sequential_retries(cfg, rounds, first, sync, monkeypatch):
     """The backward sweep's regularisation retries (MultiPhaseDDP.cpp:209-227) run as scheduled rounds of side-by-side
     rungs (k_bws.cu, "ladder scheduler").  Whatever the schedule - number of rounds, rungs walked inside the first launch,
     widest fan - the outcome must be that of the sequential ladder in ONE launch (MHPC_LADDER=0), bit for bit: n_bws, reg,
@@ -510,6 +510,7 @@ def test_regularisation_ladder_scheduler_equals_sequential_retries(cfg, rounds, 
         monkeypatch.setenv("MHPC_LADDER", ladder)
         monkeypatch.setenv("MHPC_LADDER_ROUNDS", str(rounds))
         monkeypatch.setenv("MHPC_LADDER_FIRST", str(first))
+        monkeypatch.setenv("MHPC_LADDER_SYNC", str(sync))    # 1: rounds until no instance is left (count read back); 0: a fixed number, blind
         monkeypatch.setenv("MHPC_LADDER_SMAX", "16" if rounds != 3 else "3")
         b = m.BatchedMHPC(probs, m.default_option(**opt), ls_width=4)
         b.initialization()
