@@ -88,9 +88,10 @@ struct mhpc_batch {
     bool ladder = true;
     int bws_kind = 2;                // backward sweep mapping: 2 = tensor cores, warp per instance (k_bwsT.cu, default); MHPC_BWS=8 / 16: eight / sixteen lanes per instance, DFMA (k_bws.cu, k_bws16.cu)
     int lad_rounds = 6, lad_first = 2, lad_smax = 16;
+    bool lad_target_on = false;      // MHPC_LADDER_TARGET=0: rungs per round from the resident capacity only
     bool lad_sync = true;            // read the count of unresolved instances back after each round (one short host wait) instead of
                                      // launching a fixed number of rounds blind; MHPC_LADDER_SYNC=0 keeps the solve free of host waits
-    int* h_unres = nullptr;          // pinned
+    int* h_unres = nullptr;          // pinned copy of lad_cnt
     double eps_smooth = 1.0;         // AL_REB_PARAMETER::eps_smooth (MHPC_CompoundTypes.h:224): stored, never read - as in the reference
     bool want_bws_trace = false;     // diagnostic: where each attempt of the backward sweep stopped
     int* bws_trace_buf = nullptr;
@@ -280,7 +281,8 @@ int mhpc_batch_create(int n, const mhpc_hsddp_option* opt, int device, int ls_wi
     { const char* e = getenv("MHPC_BWS"); if (e) b->bws_kind = (e[0] == 'T' || e[0] == 't') ? 2 : (!strcmp(e, "16") ? 1 : (!strcmp(e, "8") ? 0 : 2)); }
     { const char* e = getenv("MHPC_LADDER_ROUNDS"); if (e && atoi(e) > 0) b->lad_rounds = atoi(e); }
     { const char* e = getenv("MHPC_LADDER_SYNC"); if (e) b->lad_sync = e[0] != '0'; }
-    CK(cudaHostAlloc((void**)&b->h_unres, sizeof(int), cudaHostAllocDefault));
+    { const char* e = getenv("MHPC_LADDER_TARGET"); if (e) b->lad_target_on = e[0] != '0'; }
+    CK(cudaHostAlloc((void**)&b->h_unres, LAD_CNT_N * sizeof(int), cudaHostAllocDefault));
     { const char* e = getenv("MHPC_LADDER_FIRST"); if (e && atoi(e) > 0) b->lad_first = atoi(e); }
     { const char* e = getenv("MHPC_LADDER_SMAX"); if (e && atoi(e) > 0) b->lad_smax = atoi(e); }
     *out = b;
@@ -476,7 +478,9 @@ static int set_problems_slots(mhpc_batch* b, const mhpc_problem* pr) {
         if (b->bws_kind == 2 && (double)KT * KDIM * npad >= 4294967296.0) b->bws_kind = 0;
         if (b->ladder) {
             d.lad_cap = b->bws_kind == 2 ? bwsT_resident_warps(b->device) : b->bws_kind == 1 ? bws16_resident_lane_groups(b->device) : bws_resident_lane_groups(b->device);
-            const size_t tcap = (size_t)std::max(npad, d.lad_cap);
+            d.lad_tcap = 2 * npad + d.lad_cap;
+            d.lad_target = (b->bws_kind == 2 && b->lad_target_on) ? n : 0;   // the tensor-core sweep is throughput-bound from ~2400 tasks on
+            const size_t tcap = (size_t)d.lad_tcap;
             rc |= dalloc(b, &d.lad_cnt, LAD_CNT_N); rc |= dalloc(b, &d.lad_unres, npad); rc |= dalloc(b, &d.lad_rung, npad);
             rc |= dalloc(b, &d.lad_t_inst, tcap); rc |= dalloc(b, &d.lad_t_rung, tcap); rc |= dalloc(b, &d.lad_t_reg, tcap); rc |= dalloc(b, &d.lad_t_dv, tcap);
             rc |= dalloc(b, &d.lad_u_inst, tcap); rc |= dalloc(b, &d.lad_u_copy, tcap);
@@ -807,12 +811,11 @@ int mhpc_batch_solve(mhpc_batch* b, int sync_early_exit) {
               if (!b->ladder) { sweep(d, b->c, b->opt, MASK_DDP, 0, 0, s); b->launches++; }
               else {
                   sweep(d, b->c, b->opt, MASK_DDP, 0, b->lad_first, s); b->launches++;
-                  auto round = [&](int last) {
-                      if (b->bws_kind == 2) launch_bwsT_tasks(d, b->c, b->opt, MASK_DDP, s); else if (b->bws_kind == 1) launch_bws16_tasks(d, b->c, b->opt, MASK_DDP, s);
-                      else launch_bws_tasks(d, b->c, b->opt, MASK_DDP, s);
+                  auto round = [&](int n_tasks) {
+                      if (b->bws_kind == 2) launch_bwsT_tasks(d, b->c, b->opt, MASK_DDP, n_tasks, s); else if (b->bws_kind == 1) launch_bws16_tasks(d, b->c, b->opt, MASK_DDP, n_tasks, s);
+                      else launch_bws_tasks(d, b->c, b->opt, MASK_DDP, n_tasks, s);
                       launch_lad_finish(d, b->opt, s);
                       b->launches += 3;
-                      (void)last;
                   };
                   if (b->lad_sync) {
                       // plan -> how many instances still have no passing rung? -> tasks, resolve, copy; until none is left.  One
@@ -820,16 +823,16 @@ int mhpc_batch_solve(mhpc_batch* b, int sync_early_exit) {
                       // workload) costs one plan kernel and one short wait instead of rounds of empty launches.
                       for (int r = 1; r <= 64; ++r) {
                           launch_lad_plan(d, b->opt, MASK_DDP, 0, b->lad_smax, s); b->launches++;
-                          CK(cudaMemcpyAsync(b->h_unres, d.lad_cnt + LAD_N_UNRES, sizeof(int), cudaMemcpyDeviceToHost, s));
+                          CK(cudaMemcpyAsync(b->h_unres, d.lad_cnt, LAD_CNT_N * sizeof(int), cudaMemcpyDeviceToHost, s));
                           CK(cudaStreamSynchronize(s));
-                          if (*b->h_unres == 0) break;
-                          round(0);
+                          if (b->h_unres[LAD_N_UNRES] == 0) break;
+                          round(b->h_unres[LAD_N_TASKS]);
                       }
                   } else {
                       for (int r = 1; r <= b->lad_rounds; ++r) {
                           const int last = r == b->lad_rounds;
                           launch_lad_plan(d, b->opt, MASK_DDP, last, b->lad_smax, s); b->launches++;
-                          round(last);
+                          round(0);
                       }
                   }
               } }

@@ -107,7 +107,9 @@ struct Dev {
     // attempt of the backward sweep stopped: it + 1 if Quu was not positive definite at backward step `it`, -1 = passed
     int* bws_trace;  // [max_rec][BWS_TRACE_ATT][npad] or null
     // regularisation-ladder scheduler of the backward sweep (k_bws.cu: k_lad_plan / k_lad_resolve / k_lad_copy); null = off
-    int lad_cap;          // task capacity = lane groups (8 lanes each) that are resident at once on this GPU
+    int lad_cap;          // lane groups / warps of the sweep kernel that are resident at once on this GPU
+    int lad_tcap;         // length of the task arrays
+    int lad_target;       // tasks a round should reach when the sweep kernel is throughput-bound (0: fill lad_cap only)
     int* lad_cnt;         // [LAD_CNT_N]
     int* lad_unres;       // [npad] the instance has no passing rung yet in this sweep
     int* lad_rung;        // [npad] next rung (0-based attempt index of this sweep) to test
@@ -116,10 +118,12 @@ struct Dev {
     double* lad_t_reg;    // [cap] in: regularisation of the task's rung; out: of the rung that passed
     double* lad_t_dv;     // [cap] out: expected cost change of the passing sweep
     int* lad_u_inst;      // [cap] compact list of the unresolved instances of this round
-    int* lad_u_copy;      // [cap] per unresolved instance: task whose scratch outputs are its result (-1: none / already in place)
+    int* lad_u_copy;      // [cap] per unresolved instance: scratch column that holds its result (-1: none / already in place)
     double *lad_K, *lad_du, *lad_G;   // outputs of the speculative tasks, shaped like Kfb / dufb / Gv (column = task index)
 };
 enum { LAD_N_TASKS = 0, LAD_N_UNRES, LAD_STRIDE, LAD_S, LAD_CNT_N };
+// scratch column of speculative task t (t % S != 0) when every instance has S tasks: the first task of an instance writes in place
+__host__ __device__ inline int lad_scratch_col(int t, int S) { return (t / S) * (S - 1) + (t % S) - 1; }
 constexpr int BWS_TRACE_ATT = 24;   // the ladder 0, 1e-3, 2e-3, ... exceeds 1000 at the 22nd attempt
 
 __host__ __device__ inline size_t st_idx(const Dev& d, int kk, int e, int i) { return ((size_t)kk * ST + e) * d.npad + i; }

@@ -77,7 +77,7 @@ __global__ void __launch_bounds__(BWS_THREADS, BWS_MINBLOCKS) k_bws(Dev d, Const
     // lane-constant parts of the output addresses (SoA over instances: the four instances of a warp fill one 32-byte
     // sector per element): only `kk * stride` is added per knot
     // (the scratch arrays have the element stride of the instance arrays, npad, so that only the base and the column differ)
-    const size_t ocol = to_scratch ? (size_t)task : (size_t)i;
+    const size_t ocol = to_scratch ? (size_t)lad_scratch_col(task, d.lad_cnt[LAD_S]) : (size_t)i;
     double* const gv_lane = (to_scratch ? d.lad_G : d.Gv) + (size_t)m * es + ocol;
     double* const kf_lane = (to_scratch ? d.lad_K : d.Kfb) + (size_t)(4 * m) * es + ocol;
     double* const du_lane = (to_scratch ? d.lad_du : d.dufb) + (size_t)m * es + ocol;
@@ -587,7 +587,16 @@ __global__ void __launch_bounds__(1024) k_lad_plan(Dev d, Opt opt, int mask_mode
     }
     const int total = s_scan[1023];
     int cidx = s_scan[tid] - cnt;
-    const int S = total > 0 ? max(1, min(smax, min(d.lad_cap, d.npad) / total)) : 1;   // speculative tasks need a scratch column < npad
+    // rungs per instance this round.  Latency regime (few unresolved instances): as many as fill the resident capacity - they
+    // cost no time.  Throughput regime (lad_target > 0): about one batch worth of tasks per round, because a round cannot
+    // be shorter than one sweep whatever its size; fewer, fuller rounds win although some speculative rungs are wasted.
+    int S = 1;
+    if (total > 0) {
+        const int s_cap = min(d.lad_cap, d.npad) / total;
+        const int s_tgt = d.lad_target > 0 ? (d.lad_target + total / 2) / total : 0;
+        S = max(1, min(smax, max(s_cap, s_tgt)));
+        while (S > 1 && ((long long)total * (S - 1) > d.npad || (long long)total * S > d.lad_tcap)) --S;   // scratch columns, task slots
+    }
     if (tid == 0) {
         d.lad_cnt[LAD_N_TASKS] = total * S;
         d.lad_cnt[LAD_N_UNRES] = total;
@@ -636,7 +645,7 @@ __global__ void k_lad_resolve(Dev d, Opt opt) {
         d.si[(size_t)SI_N_BWS * es + i] = best + 1;
         d.si[(size_t)SI_BWS_OK * es + i] = 1;
         d.lad_unres[i] = 0;
-        d.lad_u_copy[cidx] = (best_t % S != 0) ? best_t : -1;
+        d.lad_u_copy[cidx] = (best_t % S != 0) ? lad_scratch_col(best_t, S) : -1;
         return;
     }
     const double reg0 = d.sd[(size_t)SD_REG * es + i];
@@ -687,12 +696,12 @@ void launch_lad_plan(const Dev& d, const Opt& opt, int mask_mode, int last_round
 }
 void launch_lad_finish(const Dev& d, const Opt& opt, cudaStream_t s) {
     k_lad_resolve<<<(d.n + 127) / 128, 128, 0, s>>>(d, opt);
-    dim3 g(std::min(d.KT, 128), (std::min(d.lad_cap, d.npad) / 2 + 127) / 128);   // a winner is copied only when S >= 2, i.e. unresolved <= min(cap, npad) / 2
+    dim3 g(std::min(d.KT, 128), (d.npad + 127) / 128);   // a winner is copied only when S >= 2, i.e. unresolved <= npad
     k_lad_copy<<<g, 128, 0, s>>>(d);
 }
-void launch_bws_tasks(const Dev& d, const Consts& c, const Opt& opt, int mask_mode, cudaStream_t s) {
+void launch_bws_tasks(const Dev& d, const Consts& c, const Opt& opt, int mask_mode, int n_tasks, cudaStream_t s) {
     cudaFuncSetAttribute(k_bws<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BWS_SMEM);
-    const int tcap = d.npad > d.lad_cap ? d.npad : d.lad_cap;
+    const int tcap = n_tasks > 0 ? n_tasks : d.lad_tcap;
     k_bws<1><<<(tcap + BWS_INST - 1) / BWS_INST, BWS_THREADS, BWS_SMEM, s>>>(d, c, opt, mask_mode, 0, 0);
 }
 // lane groups of k_bws that are resident at once on this device

@@ -58,7 +58,7 @@ __global__ void __launch_bounds__(B16_THREADS, B16_MINBLOCKS) k_bws16(Dev d, Con
     const int ktb = max(nk, __shfl_xor_sync(FULL, nk, 16));            // knots this warp walks
     const double* lin_i = d.lin + (size_t)i * d.KT * REC;
     const bool rowl = m < 14;                                          // this sub-lane owns WB row m
-    const size_t ocol = to_scratch ? (size_t)task : (size_t)i;
+    const size_t ocol = to_scratch ? (size_t)lad_scratch_col(task, d.lad_cnt[LAD_S]) : (size_t)i;
     double* const gv_lane = (to_scratch ? d.lad_G : d.Gv) + (size_t)m * es + ocol;
     double* const kf_lane = (to_scratch ? d.lad_K : d.Kfb) + (size_t)(4 * m) * es + ocol;
     double* const du_lane = (to_scratch ? d.lad_du : d.dufb) + (size_t)m * es + ocol;
@@ -496,9 +496,9 @@ void launch_bws16(const Dev& d, const Consts& c, const Opt& opt, int mask_mode, 
     cudaFuncSetAttribute(k_bws16<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B16_SMEM);
     k_bws16<0><<<(d.n + B16_INST - 1) / B16_INST, B16_THREADS, B16_SMEM, s>>>(d, c, opt, mask_mode, single_attempt, d.lad_unres ? max_attempts : 0);
 }
-void launch_bws16_tasks(const Dev& d, const Consts& c, const Opt& opt, int mask_mode, cudaStream_t s) {
+void launch_bws16_tasks(const Dev& d, const Consts& c, const Opt& opt, int mask_mode, int n_tasks, cudaStream_t s) {
     cudaFuncSetAttribute(k_bws16<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B16_SMEM);
-    const int tcap = d.npad > d.lad_cap ? d.npad : d.lad_cap;
+    const int tcap = n_tasks > 0 ? n_tasks : d.lad_tcap;
     k_bws16<1><<<(tcap + B16_INST - 1) / B16_INST, B16_THREADS, B16_SMEM, s>>>(d, c, opt, mask_mode, 0, 0);
 }
 int bws16_resident_lane_groups(int device) {

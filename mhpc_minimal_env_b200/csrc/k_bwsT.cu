@@ -32,7 +32,7 @@
 // when the lane has no such element: no predicates, no selects in the knot loop.
 // The 4x4 part: Quu is symmetrised with one shuffle and written to shared memory as a doubly periodic 7x7 table, so that
 // each even-row lane forms the one cofactor-inverse entry it feeds to the K product from ONE lane-constant base address
-// (the determinant is a 4-lane shuffle sum); the positive-definite test is decided by the leading principal minors when
+// (the determinant is a 4-lane shuffle sum); the positive-definite test is decided by the pivots of an unpivoted LDL' when
 // they are far from zero and by the restated Eigen LDLT (bws_shared.cuh) otherwise.
 // The step knots of a phase run in one of three specialised loops (stance / flight / rigid body) so that only the lane
 // constants of that kind are live; the knot records arrive by one cp.async.bulk per knot (mbarrier completion), issued
@@ -104,33 +104,36 @@ __device__ __forceinline__ void bar_wait(void* bar, unsigned parity) {
         : "memory");
 }
 
-// positive-definite test of S = Quu - shift I (SinglePhase.cpp:202-205) from its leading principal minors (lower triangle, as
-// Eigen reads it): 1 = every minor is positive with a wide margin against rounding, 0 = one is negative with the same margin,
-// -1 = too close to call (the caller then runs the restated Eigen LDLT, whose pivot order decides ties).
-__device__ __forceinline__ int pd_by_minors(const double* q, double shift) {
+// positive-definite test of S = Quu - shift I (SinglePhase.cpp:202-205) by an LDL^T elimination without pivoting (lower triangle,
+// as Eigen reads it).  By Sylvester's law of inertia the signs of the pivots are those Eigen's pivoted LDL^T finds, whatever the
+// order - unless a pivot is lost in rounding.  Every pivot is therefore compared with its own diagonal entry: 1 = all pivots are
+// positive and none is smaller than 1e-9 of its diagonal entry (its rounding error is ~1e-16 of it), 0 = the first pivot that is
+// not clearly positive is clearly negative, -1 = too close to call (the caller then runs the restated Eigen LDLT, whose pivot
+// order decides ties).
+__device__ __forceinline__ int pd_quick(const double* q, double shift) {
 #define QL(r, c) q[(r) + 7 * (c)]
-    const double a00 = QL(0, 0) - shift, a11 = QL(1, 1) - shift, a22 = QL(2, 2) - shift, a33 = QL(3, 3) - shift;
-    const double a10 = QL(1, 0), a20 = QL(2, 0), a30 = QL(3, 0), a21 = QL(2, 1), a31 = QL(3, 1), a32 = QL(3, 2);
+    const double tol = 1e-9;
+    const double s00 = QL(0, 0) - shift, s11 = QL(1, 1) - shift, s22 = QL(2, 2) - shift, s33 = QL(3, 3) - shift;
+    const double s10 = QL(1, 0), s20 = QL(2, 0), s30 = QL(3, 0), s21 = QL(2, 1), s31 = QL(3, 1), s32 = QL(3, 2);
 #undef QL
-    const double tol = 1e-11;
-    const double m2 = a00 * a11 - a10 * a10;
-    const double s1 = a00 * a21 - a10 * a20, s2 = a00 * a31 - a10 * a30, s3 = a10 * a21 - a11 * a20, s4 = a10 * a31 - a11 * a30, s5 = a20 * a31 - a21 * a30;
-    const double m3 = m2 * a22 - s1 * a21 + s3 * a20;
-    const double c5 = a22 * a33 - a32 * a32, c4 = a21 * a33 - a31 * a32, c3 = a21 * a32 - a31 * a22, c2 = a20 * a33 - a30 * a32, c1 = a20 * a32 - a30 * a22,
-                 c0 = a20 * a31 - a30 * a21;
-    const double m4 = ((m2 * c5 - s1 * c4) + (s2 * c3 + s3 * c2)) + (s5 * c0 - s4 * c1);
-    const double p1 = fabs(a00), p2 = p1 * fabs(a11), p3 = p2 * fabs(a22), p4 = p3 * fabs(a33);
-    const bool pos = (a00 > 0.0) && (m2 > tol * p2) && (m3 > tol * p3) && (m4 > tol * p4);
-    if (pos) return 1;
-    // the first minor that is not clearly positive decides: clearly negative -> not positive definite
-    if (a00 < 0.0) return 0;
-    if (!(a00 > 0.0)) return -1;
-    if (m2 < -tol * p2) return 0;
-    if (!(m2 > tol * p2)) return -1;
-    if (m3 < -tol * p3) return 0;
-    if (!(m3 > tol * p3)) return -1;
-    if (m4 < -tol * p4) return 0;
-    return -1;
+    const double d0 = s00;
+    const double r0 = sx_rcp(d0);
+    const double l10 = s10 * r0, l20 = s20 * r0, l30 = s30 * r0;
+    const double d1 = s11 - l10 * s10;
+    const double r1 = sx_rcp(d1);
+    const double t21 = s21 - l20 * s10, t31 = s31 - l30 * s10;
+    const double l21 = t21 * r1, l31 = t31 * r1;
+    const double d2 = (s22 - l20 * s20) - l21 * t21;
+    const double r2 = sx_rcp(d2);
+    const double t32 = (s32 - l30 * s20) - l31 * t21;
+    const double l32 = t32 * r2;
+    const double d3 = ((s33 - l30 * s30) - l31 * t31) - l32 * t32;
+    const double a0 = tol * fabs(s00), a1 = tol * fabs(s11), a2 = tol * fabs(s22), a3 = tol * fabs(s33);
+    if (d0 > a0 && d1 > a1 && d2 > a2 && d3 > a3) return 1;
+    if (!(d0 > a0)) return (d0 < -a0) ? 0 : -1;
+    if (!(d1 > a1)) return (d1 < -a1) ? 0 : -1;
+    if (!(d2 > a2)) return (d2 < -a2) ? 0 : -1;
+    return (d3 < -a3) ? 0 : -1;
 }
 
 template <int task_mode>
@@ -169,7 +172,7 @@ __global__ void __launch_bounds__(BT_THREADS, BT_MINBLOCKS) k_bwsT(Dev d, Consts
     const int np = d.n_phases[i], nwb = d.n_wb[i];
     const double dtw = d.dt_wb[i], dtf = d.dt_fb[i];
     const double* lin_i = d.lin + (size_t)i * d.KT * REC;
-    const size_t ocol = to_scratch ? (size_t)task : (size_t)i;
+    const size_t ocol = to_scratch ? (size_t)lad_scratch_col(task, d.lad_cnt[LAD_S]) : (size_t)i;
     double* const Gout = (to_scratch ? d.lad_G : d.Gv) + ocol;
     double* const Kout = (to_scratch ? d.lad_K : d.Kfb) + ocol;
     double* const dUout = (to_scratch ? d.lad_du : d.dufb) + ocol;
@@ -396,7 +399,7 @@ __global__ void __launch_bounds__(BT_THREADS, BT_MINBLOCKS) k_bwsT(Dev d, Consts
                     if (WB) { q22.c0 = (q22.c0 + scr[sT0 + 80]) / 2; q22.c1 = (q22.c1 + scr[sT1 + 80]) / 2; }
                 }
                 // ---- 4x4 part: positive-definite test, my entry of the cofactor inverse ----
-                int pd = pd_by_minors(scr + S_QP, opt.quu_shift);
+                int pd = pd_quick(scr + S_QP, opt.quu_shift);
                 if (pd < 0) {
                     double tst[4][4];
 #pragma unroll
@@ -676,8 +679,8 @@ __global__ void __launch_bounds__(BT_THREADS, BT_MINBLOCKS) k_bwsT(Dev d, Consts
 void launch_bwsT(const Dev& d, const Consts& c, const Opt& opt, int mask_mode, int single_attempt, int max_attempts, cudaStream_t s) {
     k_bwsT<0><<<d.n, BT_THREADS, BT_SMEM, s>>>(d, c, opt, mask_mode, single_attempt, d.lad_unres ? max_attempts : 0);
 }
-void launch_bwsT_tasks(const Dev& d, const Consts& c, const Opt& opt, int mask_mode, cudaStream_t s) {
-    const int tcap = d.npad > d.lad_cap ? d.npad : d.lad_cap;
+void launch_bwsT_tasks(const Dev& d, const Consts& c, const Opt& opt, int mask_mode, int n_tasks, cudaStream_t s) {
+    const int tcap = n_tasks > 0 ? n_tasks : d.lad_tcap;
     k_bwsT<1><<<tcap, BT_THREADS, BT_SMEM, s>>>(d, c, opt, mask_mode, 0, 0);
 }
 int bwsT_resident_warps(int device) {

@@ -65,15 +65,15 @@ void launch_par_eval_IMPB(int n, size_t es, const double* st, double* o0, double
 // backward sweep (k_bws.cu)
 // max_attempts > 0 (with the ladder scheduler allocated): stop walking the ladder in the kernel after that many rungs
 void launch_bws(const Dev& d, const Consts& c, const Opt& o, int mask_mode, int single_attempt, int max_attempts, cudaStream_t s);
-void launch_bws_tasks(const Dev& d, const Consts& c, const Opt& o, int mask_mode, cudaStream_t s);
+void launch_bws_tasks(const Dev& d, const Consts& c, const Opt& o, int mask_mode, int n_tasks, cudaStream_t s);   // n_tasks <= 0: unknown on the host
 int bws_resident_lane_groups(int device);
 // the same sweep with sixteen lanes per instance (k_bws16.cu)
 void launch_bws16(const Dev& d, const Consts& c, const Opt& o, int mask_mode, int single_attempt, int max_attempts, cudaStream_t s);
-void launch_bws16_tasks(const Dev& d, const Consts& c, const Opt& o, int mask_mode, cudaStream_t s);
+void launch_bws16_tasks(const Dev& d, const Consts& c, const Opt& o, int mask_mode, int n_tasks, cudaStream_t s);
 int bws16_resident_lane_groups(int device);
 // ... and on the FP64 tensor cores, one warp per instance (k_bwsT.cu)
 void launch_bwsT(const Dev& d, const Consts& c, const Opt& o, int mask_mode, int single_attempt, int max_attempts, cudaStream_t s);
-void launch_bwsT_tasks(const Dev& d, const Consts& c, const Opt& o, int mask_mode, cudaStream_t s);
+void launch_bwsT_tasks(const Dev& d, const Consts& c, const Opt& o, int mask_mode, int n_tasks, cudaStream_t s);
 int bwsT_resident_warps(int device);
 void launch_lad_plan(const Dev& d, const Opt& o, int mask_mode, int last_round, int smax, cudaStream_t s);
 void launch_lad_finish(const Dev& d, const Opt& o, cudaStream_t s);
