@@ -1,5 +1,5 @@
 """Time the BASELINE.json configs 2-5 on one GPU (device-timed, CUDA events inside the library): default thresholds
-(the reference's own convergence flow) and the fixed 2x3 budget.  Writes profiles/r1_configs.json."""
+(the reference's own convergence flow) and the fixed 2x3 budget.  Writes gpurun_out/r2_configs.json (copied to profiles/ when kept)."""
 import json, os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -25,4 +25,4 @@ for name, cfg, n in (("config2 (1024, default split)", 2, 1024), ("config2 at 40
                      "device_GB": b.device_bytes() / 1e9})
         print(rows[-1], flush=True)
         b.close()
-json.dump(rows, open(os.path.join(ROOT, "gpurun_out", "r1_configs.json"), "w"), indent=1)
+json.dump(rows, open(os.path.join(ROOT, "gpurun_out", "r2_configs.json"), "w"), indent=1)
