@@ -81,6 +81,7 @@ struct mhpc_batch {
     void* stage = nullptr;
     size_t stage_bytes = 0;
     bool keep_dead_partials = false;
+    bool recost = true;   // outer iterations after the first: cost-only pass instead of the step-size-0 rollout (MHPC_RECOST=0: rollout)
     void* rot_tmp = nullptr;
     size_t rot_bytes = 0;
     // regularisation-ladder scheduler of the backward sweep (k_bws.cu): rounds after the first launch, rungs the first
@@ -277,6 +278,7 @@ int mhpc_batch_create(int n, const mhpc_hsddp_option* opt, int device, int ls_wi
     fill_eps(b->eps, b->opt.alpha);
     fill_consts(b->c);
     { const char* e = getenv("MHPC_KEEP_DEAD_PARTIALS"); b->keep_dead_partials = e && e[0] == '1'; }
+    { const char* e = getenv("MHPC_RECOST"); b->recost = !(e && e[0] == '0'); }
     { const char* e = getenv("MHPC_LADDER"); if (e) b->ladder = e[0] != '0'; }
     { const char* e = getenv("MHPC_BWS"); if (e) b->bws_kind = (e[0] == 'T' || e[0] == 't') ? 2 : (!strcmp(e, "16") ? 1 : (!strcmp(e, "8") ? 0 : 2)); }
     { const char* e = getenv("MHPC_LADDER_ROUNDS"); if (e && atoi(e) > 0) b->lad_rounds = atoi(e); }
@@ -471,6 +473,7 @@ static int set_problems_slots(mhpc_batch* b, const mhpc_problem* pr) {
         rc |= dalloc(b, &d.par, (size_t)P * NPAR * npad);
         rc |= dalloc(b, &d.tr_cost, (size_t)d.W * npad); rc |= dalloc(b, &d.tr_viol2, (size_t)d.W * npad);
         rc |= dalloc(b, &d.tr_h, (size_t)d.W * P * npad);
+        rc |= dalloc(b, &d.knot_cost, (size_t)KT * npad);
         rc |= dalloc(b, &d.sd, (size_t)SD_N * npad); rc |= dalloc(b, &d.si, (size_t)SI_N * npad);
         rc |= dalloc(b, &d.rec_i, (size_t)d.max_rec * REC_I * npad); rc |= dalloc(b, &d.rec_d, (size_t)d.max_rec * REC_D * npad);
         rc |= dalloc(b, &d.n_active, 1);
@@ -798,11 +801,19 @@ int mhpc_batch_solve(mhpc_batch* b, int sync_early_exit) {
         b->cur_iter = al * 1000 + 1;   // the full forward sweep of an outer iteration is booked on its first inner iteration
         { Stage st(b, TB_OTHER); launch_al_begin(d, b->opt, s); b->launches++; }
         if (join_copy(b)) return -1;
-        { Stage st(b, TB_ROLLOUT);                                   // forward_sweep(0): rollout ...
-          launch_rollout(d, b->c, b->opt, MASK_RUNNING, nfs, 0, zero, s);
-          launch_accept_slot0(d, MASK_RUNNING, 2, s); b->launches += 2; }
-        if (linearize(b, MASK_RUNNING)) return -1;                   // ... and its derivatives
-        { Stage st(b, TB_OTHER); if (fork_copy_nominal(b, MASK_RUNNING)) return -1; }   // update_nominal_trajectory
+        if (al == 1 || !b->recost) {
+            { Stage st(b, TB_ROLLOUT);                                   // forward_sweep(0): rollout ...
+              launch_rollout(d, b->c, b->opt, MASK_RUNNING, nfs, 0, zero, s);
+              launch_accept_slot0(d, MASK_RUNNING, 2, s); b->launches += 2; }
+            if (linearize(b, MASK_RUNNING)) return -1;                   // ... and its derivatives
+            { Stage st(b, TB_OTHER); if (fork_copy_nominal(b, MASK_RUNNING)) return -1; }   // update_nominal_trajectory
+        } else {
+            // After the first outer iteration the step-size-0 rollout reproduces the nominal trajectory bit for bit (k_rollout.cu,
+            // "cost-only pass"): only its costs are new.  The accepted trial slot of the last line search still holds that
+            // trajectory and the nominal copy of it, so neither is rewritten.
+            { Stage st(b, TB_ROLLOUT); launch_recost(d, b->c, b->opt, MASK_RUNNING, 2, s); b->launches += 2; }
+            if (linearize(b, MASK_RUNNING)) return -1;
+        }
         for (int it = 1; it <= maxDDP; ++it) {
             b->cur_iter = al * 1000 + it;
             { Stage st(b, TB_OTHER); launch_ls_begin(d, MASK_DDP, s); b->launches++; }

@@ -98,6 +98,7 @@ struct Dev {
     double* tr_cost; // [W][npad]
     double* tr_viol2;// [W][npad]
     double* tr_h;    // [W][P][npad]
+    double* knot_cost;  // [KT][npad] per-knot cost terms of the cost-only pass (k_recost_knots)
     double* sd;      // [SD_N][npad]
     int* si;         // [SI_N][npad]
     int* rec_i;      // [max_rec][REC_I][npad]

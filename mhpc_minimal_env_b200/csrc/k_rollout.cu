@@ -20,9 +20,20 @@ namespace mhpc {
 // The lanes that hold the trials of one instance stream that instance's next knot into shared memory with cp.async, one
 // two steps ahead of the math (three-deep ring, synchronised inside the lane group only, so instances with different
 // phase lengths may share a warp).
-constexpr int RO_X = 0, RO_U = 14, RO_K = 18, RO_DU = 74, RO_POS = 78, RO_STAGE = 80;
+// A whole-body knot is 79 doubles (x 14 | u 4 | K 56 | du 4 | pos), a rigid-body knot 39 (6 | 4 | 24 | 4 | 1): the same
+// 240 doubles per instance hold a ring of three whole-body knots or of six rigid-body knots.  The rigid-body steps are
+// short (~0.4 us), so two steps of lead do not cover a DRAM round trip there (ncu: a quarter of the kernel's samples sat
+// on the copy wait and the first reads of the rigid-body loop); five do.
+template <int NXP> struct RoLay;
+template <> struct RoLay<14> { enum { X = 0, U = 14, K = 18, DU = 74, POS = 78, STAGE = 80, DEPTH = 3 }; };
+template <> struct RoLay<6> { enum { X = 0, U = 6, K = 10, DU = 34, POS = 38, STAGE = 40, DEPTH = 6 }; };
+constexpr int RO_RING = 240;   // doubles per instance
 
-constexpr int RO_DEPTH = 3;   // ring of staged knots: the copy of knot k+2 is issued while knot k is computed
+// The lanes of a warp address the stages of 32 / n_slots different instances at once; with the stages a multiple of 16
+// doubles apart all of them hit the same bank pair (ncu: 79 % of the shared-memory wavefronts of the 4-trial launch were
+// bank conflicts).  n_slots doubles of padding put instance j of a warp at bank offset j * n_slots, so the copies
+// (n_slots consecutive doubles per instance) and the broadcast reads are conflict-free.
+__host__ __device__ constexpr int ro_stride(int n_slots) { return RO_RING + (n_slots < 16 ? n_slots : 0); }
 
 // NL > 0: the lane-group size is a compile-time constant (the 8-trial line search), so the copy loops unroll into copies at
 // constant multiples of the element stride; NL == 0 takes it from n_lanes.  Always commits one group (possibly empty):
@@ -30,6 +41,7 @@ constexpr int RO_DEPTH = 3;   // ring of staged knots: the copy of knot k+2 is i
 template <int NXP, int NL>   // NXP: 14 whole-body, 6 rigid-body
 __device__ __forceinline__ void stage_knot(const Dev& d, bool copy, int kk, int i, int w, int n_lanes, double* dst) {
     if (copy) {
+        typedef RoLay<NXP> L;
         const int nl = NL > 0 ? NL : n_lanes;
         const size_t es = d.npad;
         const double* sn = d.st_nom + st_idx(d, kk, 0, i) + (size_t)w * es;
@@ -37,19 +49,19 @@ __device__ __forceinline__ void stage_knot(const Dev& d, bool copy, int kk, int 
         double* dw = dst + w;
 #pragma unroll
         for (int t = 0; t < 4 * NXP; t += (NL > 0 ? NL : 1)) {
-            if (NL > 0) { if (t + w < 4 * NXP) __pipeline_memcpy_async(dw + RO_K + t, kf + (size_t)t * es, 8); }
-            else if (t % nl == 0 && t + w < 4 * NXP) __pipeline_memcpy_async(dw + RO_K + t, kf + (size_t)t * es, 8);
+            if (NL > 0) { if (t + w < 4 * NXP) __pipeline_memcpy_async(dw + L::K + t, kf + (size_t)t * es, 8); }
+            else if (t % nl == 0 && t + w < 4 * NXP) __pipeline_memcpy_async(dw + L::K + t, kf + (size_t)t * es, 8);
         }
 #pragma unroll
         for (int t = 0; t < NXP; t += (NL > 0 ? NL : 1)) {
-            if (NL > 0) { if (t + w < NXP) __pipeline_memcpy_async(dw + RO_X + t, sn + (size_t)t * es, 8); }
-            else if (t % nl == 0 && t + w < NXP) __pipeline_memcpy_async(dw + RO_X + t, sn + (size_t)t * es, 8);
+            if (NL > 0) { if (t + w < NXP) __pipeline_memcpy_async(dw + L::X + t, sn + (size_t)t * es, 8); }
+            else if (t % nl == 0 && t + w < NXP) __pipeline_memcpy_async(dw + L::X + t, sn + (size_t)t * es, 8);
         }
         for (int t = w; t < 4; t += nl) {
-            __pipeline_memcpy_async(dst + RO_U + t, d.st_nom + st_idx(d, kk, 14 + t, i), 8);
-            __pipeline_memcpy_async(dst + RO_DU + t, d.dufb + ((size_t)kk * 4 + t) * es + i, 8);
+            __pipeline_memcpy_async(dst + L::U + t, d.st_nom + st_idx(d, kk, 14 + t, i), 8);
+            __pipeline_memcpy_async(dst + L::DU + t, d.dufb + ((size_t)kk * 4 + t) * es + i, 8);
         }
-        if (w == nl - 1) __pipeline_memcpy_async(dst + RO_POS, d.pos_ref + (size_t)kk * es + i, 8);
+        if (w == nl - 1) __pipeline_memcpy_async(dst + L::POS, d.pos_ref + (size_t)kk * es + i, 8);
     }
     __pipeline_commit();
 }
@@ -63,7 +75,7 @@ __global__ void __launch_bounds__(128) k_rollout(Dev d, Consts c, Opt opt, int m
     const int w = lane % n_slots;
     const int i = (tid >> 5) * per_warp + lane / n_slots;
     const unsigned grp = (n_used == 32 ? 0xffffffffu : ((1u << n_used) - 1u)) << (lane - w);   // lanes holding the trials of my instance
-    double* stage = ro_smem + (size_t)(threadIdx.x / n_slots) * RO_DEPTH * RO_STAGE;         // [RO_DEPTH][RO_STAGE] of my instance
+    double* stage = ro_smem + (size_t)(threadIdx.x / n_slots) * ro_stride(n_slots);          // [RO_DEPTH][RO_STAGE] of my instance
     if (w >= n_used || i >= d.n) return;
     if (!inst_enabled(d, i, mask_mode)) return;
     if (mask_mode == MASK_LS && d.si[(size_t)SI_LS_DONE * d.npad + i]) return;
@@ -90,23 +102,24 @@ __global__ void __launch_bounds__(128) k_rollout(Dev d, Consts c, Opt opt, int m
             if (STAGED) {
                 __syncwarp(grp);
                 stage_knot<14, NL>(d, 0 < N - 1, off, i, w, n_used, stage);
-                stage_knot<14, NL>(d, 1 < N - 1, off + 1, i, w, n_used, stage + RO_STAGE);
+                stage_knot<14, NL>(d, 1 < N - 1, off + 1, i, w, n_used, stage + RoLay<14>::STAGE);
             }
             for (int k = 0; k < N - 1; ++k) {
                 const int kk = off + k;
                 const size_t b = st_idx(d, kk, 0, i);
                 double dx[14], u[4], y[4], xn[14];
-                const double* sg = stage + (k % RO_DEPTH) * RO_STAGE;
+                typedef RoLay<14> L;
+                const double* sg = stage + (k % L::DEPTH) * L::STAGE;
                 if (STAGED) {
-                    __pipeline_wait_prior(1);   // everything but the newest group (knot k + 1) has landed
+                    __pipeline_wait_prior(L::DEPTH - 2);   // everything but the newest group (knot k + 1) has landed
                     __syncwarp(grp);
-                    stage_knot<14, NL>(d, k + 2 < N - 1, kk + 2, i, w, n_used, stage + ((k + 2) % RO_DEPTH) * RO_STAGE);
+                    stage_knot<14, NL>(d, k + 2 < N - 1, kk + 2, i, w, n_used, stage + ((k + 2) % L::DEPTH) * L::STAGE);
                 }
-#define RO_NOM(e) (STAGED ? sg[RO_X + (e)] : d.st_nom[b + (size_t)(e) * es])
-#define RO_UNOM(r) (STAGED ? sg[RO_U + (r)] : d.st_nom[b + (size_t)(14 + (r)) * es])
-#define RO_KF(q) (STAGED ? sg[RO_K + (q)] : d.Kfb[((size_t)kk * KDIM + (q)) * es + i])
-#define RO_DUF(r) (STAGED ? sg[RO_DU + (r)] : d.dufb[((size_t)kk * 4 + (r)) * es + i])
-#define RO_PREF() (STAGED ? sg[RO_POS] : d.pos_ref[(size_t)kk * es + i])
+#define RO_NOM(e) (STAGED ? sg[L::X + (e)] : d.st_nom[b + (size_t)(e) * es])
+#define RO_UNOM(r) (STAGED ? sg[L::U + (r)] : d.st_nom[b + (size_t)(14 + (r)) * es])
+#define RO_KF(q) (STAGED ? sg[L::K + (q)] : d.Kfb[((size_t)kk * KDIM + (q)) * es + i])
+#define RO_DUF(r) (STAGED ? sg[L::DU + (r)] : d.dufb[((size_t)kk * 4 + (r)) * es + i])
+#define RO_PREF() (STAGED ? sg[L::POS] : d.pos_ref[(size_t)kk * es + i])
 #pragma unroll
                 for (int e = 0; e < 14; ++e) { act[b + e * es] = x[e]; dx[e] = x[e] - RO_NOM(e); }
                 // u = u_nom + eps*du + K (x - x_nom)   (SinglePhase.cpp:76)
@@ -120,7 +133,7 @@ __global__ void __launch_bounds__(128) k_rollout(Dev d, Consts c, Opt opt, int m
                 wb_step(mode, dt, x, u, xn, y);
 #pragma unroll
                 for (int r = 0; r < 4; ++r) { act[b + (14 + r) * es] = u[r]; act[b + (18 + r) * es] = y[r]; }
-                V += wb_running_cost(c, mode, dt, x, u, y, RO_PREF(), vel, height, reb, par);
+                V = __dadd_rn(V, wb_running_cost(c, mode, dt, x, u, y, RO_PREF(), vel, height, reb, par));
 #pragma unroll
                 for (int e = 0; e < 14; ++e) x[e] = xn[e];
             }
@@ -128,28 +141,15 @@ __global__ void __launch_bounds__(128) k_rollout(Dev d, Consts c, Opt opt, int m
             const int kk = off + N - 1;
             const size_t b = st_idx(d, kk, 0, i);
             const double pos = d.pos_ref[(size_t)kk * es + i];
-            double Phi = 0.0;
 #pragma unroll
-            for (int e = 0; e < 14; ++e) {
-                act[b + e * es] = x[e];
-                const double dd = x[e] - wb_xref_term(c, mode, e, pos, vel);
-                const double t = (dd * c.wbQf[mode - 1][e]) * dd;
-                Phi = (e == 0) ? t : Phi + t;
-            }
-            Phi *= 0.5;
-            double h = 0.0;
-            if (mode == 2) tconstr_fl1_h(x, &h);
-            else if (mode == 4) tconstr_fl2_h(x, &h);
-            if (mode == 2 || mode == 4) {
-                viol2 += h * h;
-                if (opt.AL_active) {
-                    const double sigma = d.par[par_idx(d, p, PAR_SIGMA, i)], lam = d.par[par_idx(d, p, PAR_LAMBDA, i)];
-                    const double a = sigma * h / 2;
-                    Phi += 50 * (a * a + lam * h);
-                }
-            }
+            for (int e = 0; e < 14; ++e) act[b + e * es] = x[e];
+            const bool al_term = (mode == 2 || mode == 4) && opt.AL_active;
+            const double sigma = al_term ? d.par[par_idx(d, p, PAR_SIGMA, i)] : 0.0, lam = al_term ? d.par[par_idx(d, p, PAR_LAMBDA, i)] : 0.0;
+            double h;
+            const double Phi = wb_terminal_cost(c, mode, x, pos, vel, opt.AL_active != 0, sigma, lam, h);
+            if (mode == 2 || mode == 4) viol2 = fma(h, h, viol2);
             d.tr_h[((size_t)w * d.P + p) * es + i] = h;
-            V += Phi;
+            V = __dadd_rn(V, Phi);
             // phase transition (MultiPhaseDDP.cpp:351-379)
             if (p + 1 < np) {
                 double xp[14];
@@ -167,18 +167,19 @@ __global__ void __launch_bounds__(128) k_rollout(Dev d, Consts c, Opt opt, int m
             rb_foothold(c, mode, x, dt * (double)N, fh);
             if (STAGED) {
                 __syncwarp(grp);
-                stage_knot<6, NL>(d, 0 < N - 1, off, i, w, n_used, stage);
-                stage_knot<6, NL>(d, 1 < N - 1, off + 1, i, w, n_used, stage + RO_STAGE);
+#pragma unroll
+                for (int q = 0; q < RoLay<6>::DEPTH - 1; ++q) stage_knot<6, NL>(d, q < N - 1, off + q, i, w, n_used, stage + q * RoLay<6>::STAGE);
             }
             for (int k = 0; k < N - 1; ++k) {
                 const int kk = off + k;
                 const size_t b = st_idx(d, kk, 0, i);
                 double dx[6], u[4], xn[6];
-                const double* sg = stage + (k % RO_DEPTH) * RO_STAGE;
+                typedef RoLay<6> L;
+                const double* sg = stage + (k % L::DEPTH) * L::STAGE;
                 if (STAGED) {
-                    __pipeline_wait_prior(1);   // everything but the newest group (knot k + 1) has landed
+                    __pipeline_wait_prior(L::DEPTH - 2);   // everything but the newest four groups (knots k + 1 .. k + 4) has landed
                     __syncwarp(grp);
-                    stage_knot<6, NL>(d, k + 2 < N - 1, kk + 2, i, w, n_used, stage + ((k + 2) % RO_DEPTH) * RO_STAGE);
+                    stage_knot<6, NL>(d, k + L::DEPTH - 1 < N - 1, kk + L::DEPTH - 1, i, w, n_used, stage + ((k + L::DEPTH - 1) % L::DEPTH) * L::STAGE);
                 }
 #pragma unroll
                 for (int e = 0; e < 6; ++e) { act[b + e * es] = x[e]; dx[e] = x[e] - RO_NOM(e); }
@@ -192,27 +193,20 @@ __global__ void __launch_bounds__(128) k_rollout(Dev d, Consts c, Opt opt, int m
                 rb_step(mode, dt, x, u, fh, xn);
 #pragma unroll
                 for (int r = 0; r < 4; ++r) { act[b + (14 + r) * es] = u[r]; act[b + (18 + r) * es] = 0.0; }
-                V += rb_running_cost(c, mode, dt, x, u, RO_PREF(), vel, height);
+                V = __dadd_rn(V, rb_running_cost(c, mode, dt, x, u, RO_PREF(), vel, height));
 #pragma unroll
                 for (int e = 0; e < 6; ++e) x[e] = xn[e];
             }
             const int kk = off + N - 1;
             const size_t b = st_idx(d, kk, 0, i);
             const double pos = d.pos_ref[(size_t)kk * es + i];
-            double Phi = 0.0;
 #pragma unroll
-            for (int e = 0; e < 6; ++e) {
-                act[b + e * es] = x[e];
-                const double dd = x[e] - rb_xref(e, pos, vel, height);
-                const double t = (dd * c.rbQf[e]) * dd;
-                Phi = (e == 0) ? t : Phi + t;
-            }
-            Phi *= 0.5;
-            V += Phi;
+            for (int e = 0; e < 6; ++e) act[b + e * es] = x[e];
+            V = __dadd_rn(V, rb_terminal_cost(c, x, pos, vel, height));
             d.tr_h[((size_t)w * d.P + p) * es + i] = 0.0;
             // RB -> RB transition is the identity (MultiPhaseDDP.cpp:374-378)
         }
-        total += V;
+        total = __dadd_rn(total, V);
     }
     d.tr_cost[(size_t)w * es + i] = total;
     d.tr_viol2[(size_t)w * es + i] = viol2;
@@ -234,7 +228,7 @@ void launch_rollout(const Dev& d, const Consts& c, const Opt& opt, int mask_mode
     const int threads = ns == 1 ? 32 : std::min(128, 16 * ns);      // at most 16 staged instances (30 KB) per block
     const int inst_per_block = threads / ns;
     const unsigned blocks = (unsigned)((d.npad + inst_per_block - 1) / inst_per_block);
-    const size_t smem = (size_t)inst_per_block * RO_DEPTH * RO_STAGE * sizeof(double);
+    const size_t smem = (size_t)inst_per_block * ro_stride(ns) * sizeof(double);
     if (n_slots == 8) {          // the lane-group sizes of the usual line-search widths are compile-time constants
         k_rollout<true, 8><<<blocks, threads, smem, s>>>(d, c, opt, mask_mode, ns, n_slots, trial0, eps);
     } else if (n_slots == 4) {
@@ -246,6 +240,97 @@ void launch_rollout(const Dev& d, const Consts& c, const Opt& opt, int mask_mode
     } else {   // one trial per instance: nothing to share, every lane reads its own instance in place
         k_rollout<false, 0><<<blocks, threads, 0, s>>>(d, c, opt, mask_mode, ns, n_slots, trial0, eps);
     }
+}
+
+// ---- cost-only pass --------------------------------------------------------------------------------------------
+// forward_sweep(0) at the top of an outer (AL) iteration other than the first re-integrates the nominal trajectory with
+// step size 0: u = u_nom + 0 du + K (x - x_nom) reproduces u_nom and, step by step, x_nom exactly, so the
+// sweep changes nothing but the costs, which are re-evaluated with the new multipliers, penalties and barrier
+// parameters (MultiPhaseDDP.cpp:178-200).  Those are independent per knot: one thread per (knot, instance) evaluates the
+// knot's term from the trajectory the last line search accepted (still in its trial slot), one thread per instance adds
+// them in the rollout's order.  The rollout sums with explicit adds for the same reason: knot term and running sum are
+// then separate roundings in both kernels, and the result is bit-identical (tests: MHPC_RECOST=0 against 1).
+__global__ void __launch_bounds__(128) k_recost_knots(Dev d, Consts c, Opt opt, int mask_mode) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= d.n || !inst_enabled(d, i, mask_mode)) return;
+    const int kk = blockIdx.y;
+    int p, k;
+    if (!knot_to_phase(d, i, kk, p, k)) return;
+    const size_t es = d.npad;
+    const int slot = d.si[(size_t)SI_ACC_SLOT * es + i];
+    const double* st = d.st_act + act_idx(d, slot, kk, 0, i);
+    const int mode = d.ph_mode[ph_idx(d, p, i)], N = d.ph_N[ph_idx(d, p, i)];
+    const bool wb = p < d.n_wb[i];
+    const double vel = d.vel[i], height = d.height[i], pos = d.pos_ref[(size_t)kk * es + i];
+    double out;
+    if (wb) {
+        double x[14];
+#pragma unroll
+        for (int e = 0; e < 14; ++e) x[e] = st[(size_t)e * es];
+        if (k < N - 1) {
+            double u[4], y[4], par[6];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) { u[r] = st[(size_t)(14 + r) * es]; y[r] = st[(size_t)(18 + r) * es]; }
+#pragma unroll
+            for (int q = 0; q < 6; ++q) par[q] = d.par[par_idx(d, p, PAR_DELTA_T + q, i)];
+            const bool reb = d.si[(size_t)SI_REB_ON * es + i] != 0;
+            out = wb_running_cost(c, mode, d.dt_wb[i], x, u, y, pos, vel, height, reb, par);
+        } else {
+            const bool al_term = (mode == 2 || mode == 4) && opt.AL_active;
+            const double sigma = al_term ? d.par[par_idx(d, p, PAR_SIGMA, i)] : 0.0, lam = al_term ? d.par[par_idx(d, p, PAR_LAMBDA, i)] : 0.0;
+            double h;
+            out = wb_terminal_cost(c, mode, x, pos, vel, opt.AL_active != 0, sigma, lam, h);
+            d.par[par_idx(d, p, PAR_H, i)] = h;
+        }
+    } else {
+        double x[6];
+#pragma unroll
+        for (int e = 0; e < 6; ++e) x[e] = st[(size_t)e * es];
+        if (k < N - 1) {
+            double u[4];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) u[r] = st[(size_t)(14 + r) * es];
+            out = rb_running_cost(c, mode, d.dt_fb[i], x, u, pos, vel, height);
+        } else {
+            out = rb_terminal_cost(c, x, pos, vel, height);
+            d.par[par_idx(d, p, PAR_H, i)] = 0.0;
+        }
+    }
+    d.knot_cost[(size_t)kk * es + i] = out;
+}
+
+__global__ void __launch_bounds__(128) k_recost_sum(Dev d, int mask_mode, int lin_mode) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= d.n || !inst_enabled(d, i, mask_mode)) return;
+    const size_t es = d.npad;
+    const int np = d.n_phases[i];
+    double total = 0.0, viol2 = 0.0;
+    for (int p = 0; p < np; ++p) {
+        const int mode = d.ph_mode[ph_idx(d, p, i)], N = d.ph_N[ph_idx(d, p, i)], off = d.ph_off[ph_idx(d, p, i)];
+        const double* kc = d.knot_cost + (size_t)off * es + i;
+        double V = 0.0;
+        int k = 0;
+        for (; k + 8 <= N; k += 8) {     // eight loads in flight, added in order
+            double t[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) t[q] = kc[(size_t)(k + q) * es];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) V = __dadd_rn(V, t[q]);
+        }
+        for (; k < N; ++k) V = __dadd_rn(V, kc[(size_t)k * es]);
+        if (p < d.n_wb[i] && (mode == 2 || mode == 4)) { const double h = d.par[par_idx(d, p, PAR_H, i)]; viol2 = fma(h, h, viol2); }
+        total = __dadd_rn(total, V);
+    }
+    // what k_accept_slot0 does after a rollout; the accepted trial slot stays the one the last line search chose
+    d.sd[(size_t)SD_COST * es + i] = total;
+    d.sd[(size_t)SD_VIOL * es + i] = sqrt(viol2);
+    d.si[(size_t)SI_AL_PARTIALS * es + i] = lin_mode;
+}
+
+void launch_recost(const Dev& d, const Consts& c, const Opt& opt, int mask_mode, int lin_mode, cudaStream_t s) {
+    const dim3 grid((unsigned)((d.n + 127) / 128), (unsigned)d.KT);
+    k_recost_knots<<<grid, 128, 0, s>>>(d, c, opt, mask_mode);
+    k_recost_sum<<<(unsigned)((d.n + 127) / 128), 128, 0, s>>>(d, mask_mode, lin_mode);
 }
 
 }  // namespace mhpc

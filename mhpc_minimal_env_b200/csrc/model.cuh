@@ -252,6 +252,40 @@ static __device__ __forceinline__ double rb_running_cost(const Consts& c, int mo
     return l;
 }
 
+// Terminal cost of a whole-body phase (SinglePhase.cpp:101-113 / 138-143): quadratic term, touchdown constraint h of the
+// flight modes and, when the augmented Lagrangian is active, its penalty terms.  Shared by the rollout and the cost-only
+// pass (k_recost_knots) so that both evaluate the same expression.
+static __device__ __forceinline__ double wb_terminal_cost(const Consts& c, int mode, const double* x, double pos, double vel, bool al_active,
+                                                          double sigma, double lam, double& h) {
+    double Phi = 0.0;
+#pragma unroll
+    for (int e = 0; e < 14; ++e) {
+        const double dd = x[e] - wb_xref_term(c, mode, e, pos, vel);
+        const double t = (dd * c.wbQf[mode - 1][e]) * dd;
+        Phi = (e == 0) ? t : Phi + t;
+    }
+    Phi *= 0.5;
+    h = 0.0;
+    if (mode == 2) tconstr_fl1_h(x, &h);
+    else if (mode == 4) tconstr_fl2_h(x, &h);
+    if ((mode == 2 || mode == 4) && al_active) {
+        const double a = sigma * h / 2;
+        Phi += 50 * (a * a + lam * h);
+    }
+    return Phi;
+}
+static __device__ __forceinline__ double rb_terminal_cost(const Consts& c, const double* x, double pos, double vel, double height) {
+    double Phi = 0.0;
+#pragma unroll
+    for (int e = 0; e < 6; ++e) {
+        const double dd = x[e] - rb_xref(e, pos, vel, height);
+        const double t = (dd * c.rbQf[e]) * dd;
+        Phi = (e == 0) ? t : Phi + t;
+    }
+    Phi *= 0.5;
+    return Phi;
+}
+
 // phase p and in-phase index k of knot slot kk (phase p owns slots [p*KSTRIDE, p*KSTRIDE + N_p))
 static __device__ __forceinline__ bool knot_to_phase(const Dev& d, int i, int kk, int& p, int& k) {
     p = kk / KSTRIDE;

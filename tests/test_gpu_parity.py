@@ -527,6 +527,36 @@ def test_regularisation_ladder_scheduler_equals_sequential_retries(cfg, rounds, 
     assert runs[0][2] == runs[1][2]
 
 
+@pytest.mark.parametrize("cfg,width,opt", [(2, 4, dict(DDP_thresh=-1.0, AL_thresh=-1.0)), (4, 8, dict(DDP_thresh=-1.0, AL_thresh=-1.0, max_AL_iter=3)),
+                                           (3, 4, dict()), (2, 1, dict(max_AL_iter=3))])
+def test_cost_only_pass_equals_the_step_size_zero_rollout(cfg, width, opt, monkeypatch):
+    """forward_sweep(0) at the top of outer iterations 2.. (MultiPhaseDDP.cpp:197-200) reproduces the nominal trajectory
+    exactly and only re-prices it under the new multipliers / penalties / barrier parameters; the solver
+    therefore runs a knot-parallel cost-only pass there (k_rollout.cu: k_recost_knots / k_recost_sum).  It must be
+    indistinguishable from the rollout (MHPC_RECOST=0): every record (costs included), result and trajectory bit for bit,
+    with fixed budgets, with the reference's own thresholds (instances leave the inner loop at different iterations), with
+    three outer iterations and with 1, 4 and 8 trial slots."""
+    import mhpc_minimal_env_b200 as m
+    n = 512
+    probs = [to_gpu_problem(s) for s in make_specs(n, cfg)]
+    runs = []
+    for recost in ("0", "1"):
+        monkeypatch.setenv("MHPC_RECOST", recost)
+        b = m.BatchedMHPC(probs, m.default_option(**opt), ls_width=width)
+        b.initialization()
+        b.solve()
+        recs = [b.records(i) for i in range(n)]
+        pick = list(range(0, n, 37))
+        fields = {(i, p, nm): b.field(i, p, nm).tobytes() for i in pick for p in range(len(b.schedule(i)[0]))
+                  for nm in ("K", "DU", "G", "X_NOM", "U_NOM", "Y_NOM", "X_ACT", "U_ACT", "Y_ACT", "A", "B", "LX", "PHIX")}
+        runs.append((b.results_array().tobytes(), recs, fields))
+        b.close()
+    assert max(r["iter_AL"] for rr in runs[0][1] for r in rr) >= 2    # the pass was exercised
+    assert runs[0][1] == runs[1][1]
+    assert runs[0][0] == runs[1][0]
+    assert runs[0][2] == runs[1][2]
+
+
 @pytest.mark.parametrize("cfg", [2, 3, 4])
 def test_backward_sweep_mappings_agree(cfg, monkeypatch):
     """The three lane mappings of the backward sweep - tensor cores with a warp per instance (k_bwsT.cu, the default), eight
