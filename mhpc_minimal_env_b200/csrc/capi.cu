@@ -466,9 +466,7 @@ static int set_problems_slots(mhpc_batch* b, const mhpc_problem* pr) {
         rc |= dalloc(b, &d.pos_ref, (size_t)KT * npad);
         rc |= dalloc(b, &d.st_nom, (size_t)KT * ST * npad);
         rc |= dalloc(b, &d.st_act, (size_t)d.W * KT * ST * npad);
-        rc |= dalloc(b, &d.Kfb, (size_t)KT * KDIM * npad);
-        rc |= dalloc(b, &d.dufb, (size_t)KT * 4 * npad);
-        rc |= dalloc(b, &d.Gv, (size_t)KT * 14 * npad);
+        rc |= dalloc(b, &d.gain, (size_t)KT * GREC * npad);
         rc |= dalloc(b, &d.lin, (size_t)npad * KT * REC);
         rc |= dalloc(b, &d.par, (size_t)P * NPAR * npad);
         rc |= dalloc(b, &d.tr_cost, (size_t)d.W * npad); rc |= dalloc(b, &d.tr_viol2, (size_t)d.W * npad);
@@ -478,7 +476,6 @@ static int set_problems_slots(mhpc_batch* b, const mhpc_problem* pr) {
         rc |= dalloc(b, &d.rec_i, (size_t)d.max_rec * REC_I * npad); rc |= dalloc(b, &d.rec_d, (size_t)d.max_rec * REC_D * npad);
         rc |= dalloc(b, &d.n_active, 1);
         // the tensor-core sweep addresses its outputs with 32-bit element offsets
-        if (b->bws_kind == 2 && (double)KT * KDIM * npad >= 4294967296.0) b->bws_kind = 0;
         if (b->ladder) {
             d.lad_cap = b->bws_kind == 2 ? bwsT_resident_warps(b->device) : b->bws_kind == 1 ? bws16_resident_lane_groups(b->device) : bws_resident_lane_groups(b->device);
             d.lad_tcap = 2 * npad + d.lad_cap;
@@ -487,9 +484,8 @@ static int set_problems_slots(mhpc_batch* b, const mhpc_problem* pr) {
             rc |= dalloc(b, &d.lad_cnt, LAD_CNT_N); rc |= dalloc(b, &d.lad_unres, npad); rc |= dalloc(b, &d.lad_rung, npad);
             rc |= dalloc(b, &d.lad_t_inst, tcap); rc |= dalloc(b, &d.lad_t_rung, tcap); rc |= dalloc(b, &d.lad_t_reg, tcap); rc |= dalloc(b, &d.lad_t_dv, tcap);
             rc |= dalloc(b, &d.lad_u_inst, tcap); rc |= dalloc(b, &d.lad_u_copy, tcap);
-            // scratch outputs of the speculative tasks: same shape as Kfb / dufb / Gv (column = task index < npad)
-            rc |= dalloc(b, &d.lad_K, (size_t)KT * KDIM * npad); rc |= dalloc(b, &d.lad_du, (size_t)KT * 4 * npad);
-            rc |= dalloc(b, &d.lad_G, (size_t)KT * 14 * npad);
+            // scratch outputs of the speculative tasks: gain records, one column per task that does not write in place (< npad)
+            rc |= dalloc(b, &d.lad_gain, (size_t)KT * GREC * npad);
         }
         for (int c = 0; c < CLS_N; ++c) rc |= dalloc(b, &b->knot_list[c], KT);
         if (rc) return -1;
@@ -642,9 +638,7 @@ int mhpc_batch_initialization(mhpc_batch* b) {
     // memory_reset (MHPCLocomotion.cpp:265-290)
     CK(cudaMemsetAsync(d.st_nom, 0, (size_t)d.KT * ST * d.npad * sizeof(double), b->stream));
     CK(cudaMemsetAsync(d.st_act, 0, (size_t)d.W * d.KT * ST * d.npad * sizeof(double), b->stream));
-    CK(cudaMemsetAsync(d.Kfb, 0, (size_t)d.KT * KDIM * d.npad * sizeof(double), b->stream));
-    CK(cudaMemsetAsync(d.dufb, 0, (size_t)d.KT * 4 * d.npad * sizeof(double), b->stream));
-    CK(cudaMemsetAsync(d.Gv, 0, (size_t)d.KT * 14 * d.npad * sizeof(double), b->stream));
+    CK(cudaMemsetAsync(d.gain, 0, (size_t)d.KT * GREC * d.npad * sizeof(double), b->stream));
     // (the knot records `lin` - more than half of the footprint - are not reset: every record of a used knot is written in
     //  full by the linearisation before the sweep reads it, and no kernel or getter reads the record of an unused knot)
     launch_setup(d, b->c, b->stream);                 // build_problem: references + AL/ReB parameters
@@ -671,7 +665,7 @@ int mhpc_batch_update_problem(mhpc_batch* b) {
     if (need(b)) return -1;
     Dev& d = b->d;
     // (1) rotate the phase buffers of each model group on the device (nominal, accepted rollout, K, du, G)
-    const size_t tmp_need = (size_t)d.KT * KDIM * d.npad * sizeof(double);
+    const size_t tmp_need = (size_t)d.KT * GREC * d.npad * sizeof(double);
     if (b->rot_bytes < tmp_need) {
         if (b->rot_tmp) cudaFree(b->rot_tmp);
         CK(cudaMalloc(&b->rot_tmp, tmp_need));
@@ -679,7 +673,14 @@ int mhpc_batch_update_problem(mhpc_batch* b) {
     }
     double* tmp = (double*)b->rot_tmp;
     struct Arr { double* p; int elems; int acc; };
-    const Arr arrs[5] = {{d.st_nom, ST, 0}, {d.st_act, ST, 1}, {d.Kfb, KDIM, 0}, {d.dufb, 4, 0}, {d.Gv, 14, 0}};
+    const Arr arrs[2] = {{d.st_nom, ST, 0}, {d.st_act, ST, 1}};
+    {   // gain records (instance-major): same rotation, one thread per (knot slot, instance)
+        const size_t bytes = (size_t)d.KT * GREC * d.npad * sizeof(double);
+        CK(cudaMemcpyAsync(tmp, d.gain, bytes, cudaMemcpyDeviceToDevice, b->stream));
+        launch_rotate_gain(d, d.gain, tmp, b->stream);
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(d.gain, tmp, bytes, cudaMemcpyDeviceToDevice, b->stream));
+    }
     for (const Arr& a : arrs) {
         const size_t bytes = (size_t)d.KT * a.elems * d.npad * sizeof(double);
         CK(cudaMemcpyAsync(tmp, a.p, bytes, cudaMemcpyDeviceToDevice, b->stream));      // rows of unused phases keep their content
@@ -822,10 +823,10 @@ int mhpc_batch_solve(mhpc_batch* b, int sync_early_exit) {
               if (!b->ladder) { sweep(d, b->c, b->opt, MASK_DDP, 0, 0, s); b->launches++; }
               else {
                   sweep(d, b->c, b->opt, MASK_DDP, 0, b->lad_first, s); b->launches++;
-                  auto round = [&](int n_tasks) {
+                  auto round = [&](int n_tasks, int n_unres) {
                       if (b->bws_kind == 2) launch_bwsT_tasks(d, b->c, b->opt, MASK_DDP, n_tasks, s); else if (b->bws_kind == 1) launch_bws16_tasks(d, b->c, b->opt, MASK_DDP, n_tasks, s);
                       else launch_bws_tasks(d, b->c, b->opt, MASK_DDP, n_tasks, s);
-                      launch_lad_finish(d, b->opt, s);
+                      launch_lad_finish(d, b->opt, n_unres, s);
                       b->launches += 3;
                   };
                   if (b->lad_sync) {
@@ -837,13 +838,13 @@ int mhpc_batch_solve(mhpc_batch* b, int sync_early_exit) {
                           CK(cudaMemcpyAsync(b->h_unres, d.lad_cnt, LAD_CNT_N * sizeof(int), cudaMemcpyDeviceToHost, s));
                           CK(cudaStreamSynchronize(s));
                           if (b->h_unres[LAD_N_UNRES] == 0) break;
-                          round(b->h_unres[LAD_N_TASKS]);
+                          round(b->h_unres[LAD_N_TASKS], b->h_unres[LAD_N_UNRES]);
                       }
                   } else {
                       for (int r = 1; r <= b->lad_rounds; ++r) {
                           const int last = r == b->lad_rounds;
                           launch_lad_plan(d, b->opt, MASK_DDP, last, b->lad_smax, s); b->launches++;
-                          round(0);
+                          round(0, 0);
                       }
                   }
               } }
@@ -1013,13 +1014,13 @@ int mhpc_batch_get_field(mhpc_batch* b, int inst, int phase, int field, double* 
         case MHPC_F_U_NOM: return state_field(d.st_nom, 14, 4);
         case MHPC_F_Y_NOM: return state_field(d.st_nom, 18, 4);
         case MHPC_F_K: case MHPC_F_DU: case MHPC_F_G: {
-            const int stride = field == MHPC_F_K ? KDIM : field == MHPC_F_DU ? 4 : 14;
+            const int e0 = field == MHPC_F_K ? GR_K : field == MHPC_F_DU ? GR_DU : GR_G;
             const int dim = field == MHPC_F_K ? 4 * nx : field == MHPC_F_DU ? 4 : nx;
             if (!out) return dim;
-            const double* base = field == MHPC_F_K ? d.Kfb : field == MHPC_F_DU ? d.dufb : d.Gv;
-            std::vector<double> tmp((size_t)N * stride);
-            if (pull_rows(b, base + (size_t)off * stride * npad, N * stride, inst, tmp.data())) return -1;
-            for (int k = 0; k < N; ++k) for (int e = 0; e < dim; ++e) out[(size_t)k * dim + e] = tmp[(size_t)k * stride + e];
+            std::vector<double> tmp((size_t)N * GREC);     // the instance's records of this phase are contiguous
+            CK(cudaMemcpyAsync(tmp.data(), d.gain + gain_idx(d, off, (size_t)inst), tmp.size() * sizeof(double), cudaMemcpyDeviceToHost, b->stream));
+            CK(cudaStreamSynchronize(b->stream));
+            for (int k = 0; k < N; ++k) for (int e = 0; e < dim; ++e) out[(size_t)k * dim + e] = tmp[(size_t)k * GREC + e0 + e];
             return dim;
         }
         case MHPC_F_X_REF: case MHPC_F_U_REF: case MHPC_F_Y_REF: {
@@ -1137,8 +1138,8 @@ __global__ void k_gather_exec(Dev d, const int* __restrict__ user_of, int kn, in
     }
     if (st_out) for (int e = 0; e < ST; ++e) st_out[((size_t)u * kn + k) * ST + e] = kk >= 0 ? d.st_nom[((size_t)kk * ST + e) * d.npad + i] : 0.0;
     if (gain_out) {
-        for (int e = 0; e < KDIM; ++e) gain_out[((size_t)u * kn + k) * 60 + e] = kk >= 0 ? d.Kfb[((size_t)kk * KDIM + e) * d.npad + i] : 0.0;
-        for (int e = 0; e < 4; ++e) gain_out[((size_t)u * kn + k) * 60 + 56 + e] = kk >= 0 ? d.dufb[((size_t)kk * 4 + e) * d.npad + i] : 0.0;
+        const double* gr = d.gain + gain_idx(d, kk >= 0 ? kk : 0, (size_t)i);     // K | du are the first 60 entries of the record
+        for (int e = 0; e < 60; ++e) gain_out[((size_t)u * kn + k) * 60 + e] = kk >= 0 ? gr[e] : 0.0;
     }
 }
 __global__ void k_results_pack(Dev d, const int* __restrict__ user_of, mhpc_result* out) {

@@ -16,6 +16,9 @@ namespace mhpc {
 constexpr int NXW = 14, NXR = 6, NU = 4, NY = 4;
 constexpr int ST = 22;            // x(14) u(4) y(4) per knot
 constexpr int KDIM = 56;          // K is 4x14 column-major (RB uses the first 24 = 4x6)
+// Gain record of a knot: everything the backward sweep produces there, contiguous per (instance, knot) so that the warp that
+// owns the instance writes whole sectors and the rollout streams K, du with 16-byte copies
+constexpr int GREC = 74, GR_K = 0, GR_DU = 56, GR_G = 60;   // K 4x14 | du 4 | G 14  (592 B)
 constexpr int REC = 176;          // doubles per knot record
 constexpr int MAXP = 16;          // phases per instance (reference default 8)
 constexpr int KSTRIDE = 110;      // knot slots per phase = N_TIMESTEPS_MAX (MHPC_CPPTypes.h:9): phase p owns knots [p*110, p*110 + N_p),
@@ -89,9 +92,7 @@ struct Dev {
     // trajectories
     double* st_nom;  // [KT][ST][npad]
     double* st_act;  // [W][KT][ST][npad]
-    double* Kfb;     // [KT][56][npad]
-    double* dufb;    // [KT][4][npad]
-    double* Gv;      // [KT][14][npad]
+    double* gain;    // [npad][KT][GREC] gain records: K | du | G
     double* lin;     // AoSoA records
     // parameters and solver state
     double* par;     // [P][NPAR][npad]
@@ -120,7 +121,7 @@ struct Dev {
     double* lad_t_dv;     // [cap] out: expected cost change of the passing sweep
     int* lad_u_inst;      // [cap] compact list of the unresolved instances of this round
     int* lad_u_copy;      // [cap] per unresolved instance: scratch column that holds its result (-1: none / already in place)
-    double *lad_K, *lad_du, *lad_G;   // outputs of the speculative tasks, shaped like Kfb / dufb / Gv (column = task index)
+    double* lad_gain;     // [npad][KT][GREC] outputs of the speculative tasks: gain records, first index = scratch column
 };
 enum { LAD_N_TASKS = 0, LAD_N_UNRES, LAD_STRIDE, LAD_S, LAD_CNT_N };
 // scratch column of speculative task t (t % S != 0) when every instance has S tasks: the first task of an instance writes in place
@@ -128,6 +129,7 @@ __host__ __device__ inline int lad_scratch_col(int t, int S) { return (t / S) * 
 constexpr int BWS_TRACE_ATT = 24;   // the ladder 0, 1e-3, 2e-3, ... exceeds 1000 at the 22nd attempt
 
 __host__ __device__ inline size_t st_idx(const Dev& d, int kk, int e, int i) { return ((size_t)kk * ST + e) * d.npad + i; }
+__host__ __device__ inline size_t gain_idx(const Dev& d, int kk, size_t col) { return (col * d.KT + kk) * GREC; }   // col: instance slot (gain) or scratch column (lad_gain)
 __host__ __device__ inline size_t act_idx(const Dev& d, int w, int kk, int e, int i) {
     return (((size_t)w * d.KT + kk) * ST + e) * d.npad + i;
 }

@@ -78,10 +78,11 @@ __global__ void __launch_bounds__(BWS_THREADS, BWS_MINBLOCKS) k_bws(Dev d, Const
     // sector per element): only `kk * stride` is added per knot
     // (the scratch arrays have the element stride of the instance arrays, npad, so that only the base and the column differ)
     const size_t ocol = to_scratch ? (size_t)lad_scratch_col(task, d.lad_cnt[LAD_S]) : (size_t)i;
-    double* const gv_lane = (to_scratch ? d.lad_G : d.Gv) + (size_t)m * es + ocol;
-    double* const kf_lane = (to_scratch ? d.lad_K : d.Kfb) + (size_t)(4 * m) * es + ocol;
-    double* const du_lane = (to_scratch ? d.lad_du : d.dufb) + (size_t)m * es + ocol;
-    const size_t gv_knot = 14 * es, kf_knot = (size_t)KDIM * es, du_knot = 4 * es;
+    double* const grec = (to_scratch ? d.lad_gain : d.gain) + gain_idx(d, 0, ocol);     // [KT][GREC] of this instance / scratch column
+    double* const gv_lane = grec + GR_G + m;
+    double* const kf_lane = grec + GR_K + 4 * m;
+    double* const du_lane = grec + GR_DU + m;
+    const size_t gv_knot = GREC, kf_knot = GREC, du_knot = GREC;
 
     // per-instance schedule walker (phase p, in-phase knot k; knot slot = p*KSTRIDE + k), used both by the prefetcher
     // (one knot ahead) and by the math; it visits the nk used knots from the last one backwards
@@ -187,7 +188,7 @@ __global__ void __launch_bounds__(BWS_THREADS, BWS_MINBLOCKS) k_bws(Dev d, Const
                             const double gb = wb_terminal_row(m + 7, buf, last ? 0.0 : scr[S_G + m + 7], Hb);
                             scr[S_G + m] = ga; scr[S_G + m + 7] = gb;
                             gv_lane[(size_t)kk * gv_knot] = ga;
-                            gv_lane[(size_t)kk * gv_knot + 7 * es] = gb;
+                            gv_lane[(size_t)kk * gv_knot + 7] = gb;
                         }
                     } else if (m < 6) {
                         double gv = last ? 0.0 : scr[S_G + m];
@@ -384,11 +385,11 @@ __global__ void __launch_bounds__(BWS_THREADS, BWS_MINBLOCKS) k_bws(Dev d, Const
                         if (rowl) {
                             scr[S_G + la] = goa; scr[S_G + lb] = gob;
                             gv_lane[(size_t)kk * gv_knot] = goa;
-                            gv_lane[(size_t)kk * gv_knot + 7 * es] = gob;
+                            gv_lane[(size_t)kk * gv_knot + 7] = gob;
 #pragma unroll
                             for (int cc = 0; cc < 4; ++cc) {
-                                kf_lane[(size_t)kk * kf_knot + (size_t)cc * es] = ka[cc];
-                                kf_lane[(size_t)kk * kf_knot + (size_t)(28 + cc) * es] = kb[cc];
+                                kf_lane[(size_t)kk * kf_knot + cc] = ka[cc];
+                                kf_lane[(size_t)kk * kf_knot + 28 + cc] = kb[cc];
                             }
                         }
                         if (m < 4) du_lane[(size_t)kk * du_knot] = du[m];
@@ -484,7 +485,7 @@ __global__ void __launch_bounds__(BWS_THREADS, BWS_MINBLOCKS) k_bws(Dev d, Const
                             scr[S_G + l] = gout;
                             gv_lane[(size_t)kk * gv_knot] = gout;
 #pragma unroll
-                            for (int cc = 0; cc < 4; ++cc) kf_lane[(size_t)kk * kf_knot + (size_t)cc * es] = ka[cc];
+                            for (int cc = 0; cc < 4; ++cc) kf_lane[(size_t)kk * kf_knot + cc] = ka[cc];
                         }
                         if (m < 4) du_lane[(size_t)kk * du_knot] = du[m];
                     }
@@ -665,25 +666,28 @@ __global__ void k_lad_resolve(Dev d, Opt opt) {
     }
 }
 
-// K, du, G of a winner that ran as a speculative task: scratch column -> the instance's own column, exactly the entries a
-// passing sweep writes (step knots: K, du, G; terminal knots: G)
+// K, du, G of a winner that ran as a speculative task: scratch column -> the instance's own records, exactly the entries a
+// passing sweep writes (step knots: K, du, G; terminal knots: G).  One block row per unresolved instance; consecutive threads
+// copy consecutive elements of the instance's records.
 __global__ void k_lad_copy(Dev d) {
-    const int cidx = blockIdx.y * blockDim.x + threadIdx.x;
-    if (cidx >= d.lad_cnt[LAD_N_UNRES]) return;
+  for (int cidx = blockIdx.y; cidx < d.lad_cnt[LAD_N_UNRES]; cidx += gridDim.y) {
     const int t = d.lad_u_copy[cidx];
-    if (t < 0) return;
+    if (t < 0) continue;
     const int i = d.lad_u_inst[cidx];
-    const size_t ces = d.npad, es = d.npad;
-    for (int kk = blockIdx.x; kk < d.KT; kk += gridDim.x) {
-        int p, k;
-        if (!knot_to_phase(d, i, kk, p, k)) continue;
-        const int nx = (p < d.n_wb[i]) ? 14 : 6;
-        const bool term = (k == d.ph_N[ph_idx(d, p, i)] - 1);
-        for (int e = 0; e < nx; ++e) d.Gv[((size_t)kk * 14 + e) * es + i] = d.lad_G[((size_t)kk * 14 + e) * ces + t];
-        if (term) continue;
-        for (int e = 0; e < 4 * nx; ++e) d.Kfb[((size_t)kk * KDIM + e) * es + i] = d.lad_K[((size_t)kk * KDIM + e) * ces + t];
-        for (int e = 0; e < 4; ++e) d.dufb[((size_t)kk * 4 + e) * es + i] = d.lad_du[((size_t)kk * 4 + e) * ces + t];
+    const double* __restrict__ src = d.lad_gain + gain_idx(d, 0, (size_t)t);
+    double* __restrict__ dst = d.gain + gain_idx(d, 0, (size_t)i);
+    const int nwb = d.n_wb[i], np = d.n_phases[i];
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < np * KSTRIDE * GREC; idx += gridDim.x * blockDim.x) {
+        const int kk = idx / GREC, e = idx - kk * GREC;
+        const int p = kk / KSTRIDE, k = kk - p * KSTRIDE;
+        const int N = d.ph_N[ph_idx(d, p, i)];
+        if (k >= N) continue;
+        const int nx = (p < nwb) ? 14 : 6;
+        const bool term = (k == N - 1);
+        const bool mine = e >= GR_G ? (e - GR_G < nx) : (!term && (e >= GR_DU || e < 4 * nx));
+        if (mine) dst[idx] = src[idx];
     }
+  }
 }
 
 void launch_bws(const Dev& d, const Consts& c, const Opt& opt, int mask_mode, int single_attempt, int max_attempts, cudaStream_t s) {
@@ -694,10 +698,11 @@ void launch_bws(const Dev& d, const Consts& c, const Opt& opt, int mask_mode, in
 void launch_lad_plan(const Dev& d, const Opt& opt, int mask_mode, int last_round, int smax, cudaStream_t s) {
     k_lad_plan<<<1, 1024, 0, s>>>(d, opt, mask_mode, last_round, smax);
 }
-void launch_lad_finish(const Dev& d, const Opt& opt, cudaStream_t s) {
+void launch_lad_finish(const Dev& d, const Opt& opt, int n_unres, cudaStream_t s) {
     k_lad_resolve<<<(d.n + 127) / 128, 128, 0, s>>>(d, opt);
-    dim3 g(std::min(d.KT, 128), (d.npad + 127) / 128);   // a winner is copied only when S >= 2, i.e. unresolved <= npad
-    k_lad_copy<<<g, 128, 0, s>>>(d);
+    // one block row per unresolved instance of this round (n_unres <= 0: not known on the host - rows loop over the device count)
+    dim3 g(8, (unsigned)(n_unres > 0 ? std::min(n_unres, 32768) : std::min(d.npad, 2048)));
+    k_lad_copy<<<g, 256, 0, s>>>(d);
 }
 void launch_bws_tasks(const Dev& d, const Consts& c, const Opt& opt, int mask_mode, int n_tasks, cudaStream_t s) {
     cudaFuncSetAttribute(k_bws<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BWS_SMEM);

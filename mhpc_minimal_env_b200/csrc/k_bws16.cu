@@ -59,10 +59,11 @@ __global__ void __launch_bounds__(B16_THREADS, B16_MINBLOCKS) k_bws16(Dev d, Con
     const double* lin_i = d.lin + (size_t)i * d.KT * REC;
     const bool rowl = m < 14;                                          // this sub-lane owns WB row m
     const size_t ocol = to_scratch ? (size_t)lad_scratch_col(task, d.lad_cnt[LAD_S]) : (size_t)i;
-    double* const gv_lane = (to_scratch ? d.lad_G : d.Gv) + (size_t)m * es + ocol;
-    double* const kf_lane = (to_scratch ? d.lad_K : d.Kfb) + (size_t)(4 * m) * es + ocol;
-    double* const du_lane = (to_scratch ? d.lad_du : d.dufb) + (size_t)m * es + ocol;
-    const size_t gv_knot = 14 * es, kf_knot = (size_t)KDIM * es, du_knot = 4 * es;
+    double* const grec = (to_scratch ? d.lad_gain : d.gain) + gain_idx(d, 0, ocol);     // [KT][GREC] of this instance / scratch column
+    double* const gv_lane = grec + GR_G + m;
+    double* const kf_lane = grec + GR_K + 4 * m;
+    double* const du_lane = grec + GR_DU + m;
+    const size_t gv_knot = GREC, kf_knot = GREC, du_knot = GREC;
 
     struct Walk { int p, N, mode, k; };
     auto walk_load = [&](Walk& w) {
@@ -336,7 +337,7 @@ __global__ void __launch_bounds__(B16_THREADS, B16_MINBLOCKS) k_bws16(Dev d, Con
                             scr[S_G + l] = gout;
                             gv_lane[(size_t)kk * gv_knot] = gout;
 #pragma unroll
-                            for (int cc = 0; cc < 4; ++cc) kf_lane[(size_t)kk * kf_knot + (size_t)cc * es] = kc[cc];
+                            for (int cc = 0; cc < 4; ++cc) kf_lane[(size_t)kk * kf_knot + cc] = kc[cc];
                         }
                         if (m < 4) du_lane[(size_t)kk * du_knot] = du[m];
                     }
@@ -424,7 +425,7 @@ __global__ void __launch_bounds__(B16_THREADS, B16_MINBLOCKS) k_bws16(Dev d, Con
                             scr[S_G + l] = gout;
                             gv_lane[(size_t)kk * gv_knot] = gout;
 #pragma unroll
-                            for (int cc = 0; cc < 4; ++cc) kf_lane[(size_t)kk * kf_knot + (size_t)cc * es] = kc[cc];
+                            for (int cc = 0; cc < 4; ++cc) kf_lane[(size_t)kk * kf_knot + cc] = kc[cc];
                         }
                         if (m < 4) du_lane[(size_t)kk * du_knot] = du[m];
                     }

@@ -57,9 +57,6 @@ static_assert(WB_STEP_LEN == REC - 1 && WB_TERM_LEN < REC - 1 && RB_STEP_LEN < R
 #ifndef BT_SYM_MASK
 #define BT_SYM_MASK 0     // Qxx is symmetrised on the knots k with (k & mask) == 0 (every knot, like the reference; mask 3 is not faster)
 #endif
-#ifndef BT_OFF32
-#define BT_OFF32 0          // 32-bit output offsets: slower (2.55 ms), kept for the record
-#endif
 #ifndef BT_CT_SELECT
 #define BT_CT_SELECT 1      // right factor of the output-cost products by selects instead of three more loads
 #endif
@@ -173,9 +170,7 @@ __global__ void __launch_bounds__(BT_THREADS, BT_MINBLOCKS) k_bwsT(Dev d, Consts
     const double dtw = d.dt_wb[i], dtf = d.dt_fb[i];
     const double* lin_i = d.lin + (size_t)i * d.KT * REC;
     const size_t ocol = to_scratch ? (size_t)lad_scratch_col(task, d.lad_cnt[LAD_S]) : (size_t)i;
-    double* const Gout = (to_scratch ? d.lad_G : d.Gv) + ocol;
-    double* const Kout = (to_scratch ? d.lad_K : d.Kfb) + ocol;
-    double* const dUout = (to_scratch ? d.lad_du : d.dufb) + ocol;
+    double* const grec = (to_scratch ? d.lad_gain : d.gain) + gain_idx(d, 0, ocol);   // gain records [KT][GREC] of this instance / scratch column
     const unsigned bar_a = smem_u32(smem + BT_BAR), buf_a = smem_u32(bufs);   // shared-window addresses of barrier 0 / stage 0
     if (lane < np) sN[lane] = d.ph_N[ph_idx(d, lane, i)];
     if (lane < BT_NST) {
@@ -232,15 +227,11 @@ __global__ void __launch_bounds__(BT_THREADS, BT_MINBLOCKS) k_bwsT(Dev d, Consts
     const bool rep_r = qr < 3, rep_c = qc < 3;
     const int oCof = S_QP + qr + 7 * qc;                                  // cofactor of (i, jj) = (g/2, t): elements QP[oCof + a + 7 b], a, b = 1..3
     const double sgn = ((qr + qc) & 1) ? -1.0 : 1.0;
-#if BT_OFF32
-    // output element offsets of this lane (32-bit: the host checks KT * 56 * npad < 2^32)
-    const unsigned ues = (unsigned)es;
-    const unsigned oK = (unsigned)(4 * (gf ? g : 0) + t) * ues, oG = hom ? (unsigned)(7 + n0) * ues : (unsigned)(gf ? g : 0) * ues, oU4 = (unsigned)t * ues;
-#else
-    double* const pK1 = Kout + (size_t)(4 * (gf ? g : 0) + t) * es;
-    double* const pG = hom ? Gout + (size_t)(7 + n0) * es : Gout + (size_t)(gf ? g : 0) * es;
-    double* const pdU = dUout + (size_t)t * es;
-#endif
+    // my elements of a knot's gain record (K | du | G, contiguous: a store instruction of the warp fills whole sectors); the knot
+    // offset added per store is the same for all lanes
+    double* const pK1 = grec + GR_K + 4 * (gf ? g : 0) + t;
+    double* const pG = grec + GR_G + (hom ? 7 + n0 : (gf ? g : 0));
+    double* const pdU = grec + GR_DU + t;
 
     while (true) {
         // ---- one attempt -----------------------------------------------------------------
@@ -307,13 +298,8 @@ __global__ void __launch_bounds__(BT_THREADS, BT_MINBLOCKS) k_bwsT(Dev d, Consts
                 oYt = (t == 0) ? oZt0 : (t == 1) ? oZt1 : ZSLOT; oYb = (t == 0) ? oZb0 : (t == 1) ? oZb1 : ZSLOT; oYu = (t == 0) ? oZu0 : (t == 1) ? oZu1 : ZSLOT;
                 zt2 = hom ? 1.0 : 0.0; cYt = (hom && t == 2) ? 1.0 : 0.0;
             }
-#if BT_OFF32
-            unsigned koff = (unsigned)(p * KSTRIDE + N - 2) * (unsigned)es;       // (knot slot) x (instance stride) of the current knot
-            for (int k = N - 2; k >= 0; --k, ++it, ++cnt, koff -= (unsigned)es) {
-#else
-            size_t koff = (size_t)(p * KSTRIDE + N - 2) * es;
-            for (int k = N - 2; k >= 0; --k, ++it, ++cnt, koff -= es) {
-#endif
+            int koff = (p * KSTRIDE + N - 2) * GREC;       // element offset of the current knot's gain record
+            for (int k = N - 2; k >= 0; --k, ++it, ++cnt, koff -= GREC) {
                 const double* buf = bufs + (cnt & (BT_NST - 1)) * REC;
                 landed(cnt);
                 __syncwarp();                        // everyone is done with the stage of the previous knot (and with its scratch)
@@ -434,46 +420,24 @@ __global__ void __launch_bounds__(BT_THREADS, BT_MINBLOCKS) k_bwsT(Dev d, Consts
                 if (lane == 31) q11.c1 = 0.0;
                 T11 = q11; T12 = q12; T22 = q22;
                 // K (4 x nx column-major), du, G of this knot
-#if BT_OFF32
-                const unsigned kK = koff * KDIM + oK, kG = koff * 14 + oG;
                 if (WB) {
                     if (gf) {
-                        Kout[kK] = kt1.c0;
-                        Kout[kK + 28 * ues] = kt2.c0;
-                        if (t == 3) Gout[kG] = T11.c1;
+                        pK1[koff] = kt1.c0;
+                        pK1[koff + 28] = kt2.c0;
+                        if (t == 3) pG[koff] = T11.c1;
                     } else {
-                        dUout[koff * 4 + oU4] = kt1.c0;
-                        Gout[kG] = T12.c0;
-                        if (k1ok) Gout[kG + ues] = T12.c1;
+                        pdU[koff] = kt1.c0;
+                        pG[koff] = T12.c0;
+                        if (k1ok) pG[koff + 1] = T12.c1;
                     }
                 } else {
                     if (g6) {
-                        Kout[kK] = kt1.c0;
-                        if (t == 3) Gout[kG] = T11.c1;
+                        pK1[koff] = kt1.c0;
+                        if (t == 3) pG[koff] = T11.c1;
                     } else if (hom) {
-                        dUout[koff * 4 + oU4] = kt1.c0;
+                        pdU[koff] = kt1.c0;
                     }
                 }
-#else
-                if (WB) {
-                    if (gf) {
-                        pK1[koff * KDIM] = kt1.c0;
-                        pK1[koff * KDIM + 28 * es] = kt2.c0;
-                        if (t == 3) pG[koff * 14] = T11.c1;
-                    } else {
-                        pdU[koff * 4] = kt1.c0;
-                        pG[koff * 14] = T12.c0;
-                        if (k1ok) pG[koff * 14 + es] = T12.c1;
-                    }
-                } else {
-                    if (g6) {
-                        pK1[koff * KDIM] = kt1.c0;
-                        if (t == 3) pG[koff * 14] = T11.c1;
-                    } else if (hom) {
-                        pdU[koff * 4] = kt1.c0;
-                    }
-                }
-#endif
             }
         };
 
@@ -561,7 +525,7 @@ __global__ void __launch_bounds__(BT_THREADS, BT_MINBLOCKS) k_bwsT(Dev d, Consts
                     if (rowl) {
                         const double ga = wb_terminal_row(m, buf, last ? 0.0 : scr[S_G + m], Hr);
                         scr[S_G + m] = ga;
-                        Gout[((size_t)kk * 14 + m) * es] = ga;
+                        grec[(size_t)kk * GREC + GR_G + m] = ga;
                     }
                 } else if (m < 6) {
                     double gv = last ? 0.0 : scr[S_G + m];
@@ -569,7 +533,7 @@ __global__ void __launch_bounds__(BT_THREADS, BT_MINBLOCKS) k_bwsT(Dev d, Consts
                     for (int jc = 0; jc < 6; ++jc) Hr[jc] = ((jc == m) ? c.rbQf[m] : 0.0) + Hr[jc];
                     gv = buf[R_RPHIX + m] + gv;
                     scr[S_G + m] = gv;
-                    Gout[((size_t)kk * 14 + m) * es] = gv;
+                    grec[(size_t)kk * GREC + GR_G + m] = gv;
                 }
                 __syncwarp();
                 // rows -> tiles of this phase's model

@@ -314,6 +314,21 @@ __global__ void k_rotate(Dev d, const double* __restrict__ src, double* __restri
     const size_t slot_off = use_acc_slot ? (size_t)SI(SI_ACC_SLOT) * d.KT * elems * d.npad : 0;
     dst[(size_t)row * d.npad + i] = src[slot_off + ((size_t)(q * KSTRIDE + k) * elems + e) * d.npad + i];
 }
+// the same rotation for the gain records [npad][KT][GREC]: one thread per (knot slot, instance)
+__global__ void k_rotate_gain(Dev d, const double* __restrict__ src, double* __restrict__ dst) {
+    const int i = blockIdx.y * blockDim.x + threadIdx.x;
+    if (i >= d.n) return;
+    const int kk = blockIdx.x;
+    const int p = kk / KSTRIDE, k = kk - p * KSTRIDE;
+    const int np = d.n_phases[i], nwb = d.n_wb[i];
+    if (p >= np) return;
+    int q;
+    if (p < nwb) q = (p + 1 < nwb) ? p + 1 : 0;
+    else q = (p + 1 < np) ? p + 1 : nwb;
+    const double* s = src + gain_idx(d, q * KSTRIDE + k, (size_t)i);
+    double* t = dst + gain_idx(d, kk, (size_t)i);
+    for (int e = 0; e < GREC; ++e) t[e] = s[e];
+}
 // after the rotation every line-search slot must carry the same never-recomputed u,y of the last knot of each phase
 //  as the single `act` buffer of the reference
 __global__ void k_spread_last_knot(Dev d) {
@@ -387,6 +402,10 @@ void launch_reb_from_option(const Dev& d, cudaStream_t s) { k_reb_from_option<<<
 void launch_rotate(const Dev& d, const double* src, double* dst, int elems, int use_acc_slot, cudaStream_t s) {
     dim3 grid(d.KT * elems, nb(d.n, 128));
     k_rotate<<<grid, 128, 0, s>>>(d, src, dst, elems, use_acc_slot);
+}
+void launch_rotate_gain(const Dev& d, const double* src, double* dst, cudaStream_t s) {
+    dim3 grid(d.KT, nb(d.n, 128));
+    k_rotate_gain<<<grid, 128, 0, s>>>(d, src, dst);
 }
 void launch_spread_last_knot(const Dev& d, cudaStream_t s) {
     dim3 grid(nb(d.n, 128), d.P);

@@ -45,22 +45,22 @@ __device__ __forceinline__ void stage_knot(const Dev& d, bool copy, int kk, int 
         const int nl = NL > 0 ? NL : n_lanes;
         const size_t es = d.npad;
         const double* sn = d.st_nom + st_idx(d, kk, 0, i) + (size_t)w * es;
-        const double* kf = d.Kfb + ((size_t)kk * KDIM + w) * es + i;
-        double* dw = dst + w;
+        // K | du: the head of the knot's gain record, contiguous -> 16-byte copies (whole-body: one run of 30; rigid body: K 4x6, then du)
+        const double* gr = d.gain + gain_idx(d, kk, (size_t)i);
+        constexpr int NK16 = 2 * NXP + (NXP == 14 ? 2 : 0);
 #pragma unroll
-        for (int t = 0; t < 4 * NXP; t += (NL > 0 ? NL : 1)) {
-            if (NL > 0) { if (t + w < 4 * NXP) __pipeline_memcpy_async(dw + L::K + t, kf + (size_t)t * es, 8); }
-            else if (t % nl == 0 && t + w < 4 * NXP) __pipeline_memcpy_async(dw + L::K + t, kf + (size_t)t * es, 8);
+        for (int t = 0; t < NK16; t += (NL > 0 ? NL : 1)) {
+            if (NL > 0) { if (t + w < NK16) __pipeline_memcpy_async(dst + L::K + 2 * (t + w), gr + 2 * (t + w), 16); }
+            else if (t % nl == 0 && t + w < NK16) __pipeline_memcpy_async(dst + L::K + 2 * (t + w), gr + 2 * (t + w), 16);
         }
+        if (NXP != 14 && w < 2) __pipeline_memcpy_async(dst + L::DU + 2 * w, gr + GR_DU + 2 * w, 16);
+        double* dw = dst + w;
 #pragma unroll
         for (int t = 0; t < NXP; t += (NL > 0 ? NL : 1)) {
             if (NL > 0) { if (t + w < NXP) __pipeline_memcpy_async(dw + L::X + t, sn + (size_t)t * es, 8); }
             else if (t % nl == 0 && t + w < NXP) __pipeline_memcpy_async(dw + L::X + t, sn + (size_t)t * es, 8);
         }
-        for (int t = w; t < 4; t += nl) {
-            __pipeline_memcpy_async(dst + L::U + t, d.st_nom + st_idx(d, kk, 14 + t, i), 8);
-            __pipeline_memcpy_async(dst + L::DU + t, d.dufb + ((size_t)kk * 4 + t) * es + i, 8);
-        }
+        for (int t = w; t < 4; t += nl) __pipeline_memcpy_async(dst + L::U + t, d.st_nom + st_idx(d, kk, 14 + t, i), 8);
         if (w == nl - 1) __pipeline_memcpy_async(dst + L::POS, d.pos_ref + (size_t)kk * es + i, 8);
     }
     __pipeline_commit();
@@ -117,8 +117,8 @@ __global__ void __launch_bounds__(128) k_rollout(Dev d, Consts c, Opt opt, int m
                 }
 #define RO_NOM(e) (STAGED ? sg[L::X + (e)] : d.st_nom[b + (size_t)(e) * es])
 #define RO_UNOM(r) (STAGED ? sg[L::U + (r)] : d.st_nom[b + (size_t)(14 + (r)) * es])
-#define RO_KF(q) (STAGED ? sg[L::K + (q)] : d.Kfb[((size_t)kk * KDIM + (q)) * es + i])
-#define RO_DUF(r) (STAGED ? sg[L::DU + (r)] : d.dufb[((size_t)kk * 4 + (r)) * es + i])
+#define RO_KF(q) (STAGED ? sg[L::K + (q)] : d.gain[gain_idx(d, kk, (size_t)i) + GR_K + (q)])
+#define RO_DUF(r) (STAGED ? sg[L::DU + (r)] : d.gain[gain_idx(d, kk, (size_t)i) + GR_DU + (r)])
 #define RO_PREF() (STAGED ? sg[L::POS] : d.pos_ref[(size_t)kk * es + i])
 #pragma unroll
                 for (int e = 0; e < 14; ++e) { act[b + e * es] = x[e]; dx[e] = x[e] - RO_NOM(e); }

@@ -44,6 +44,7 @@ void launch_count_active(const Dev& d, cudaStream_t s);
 void launch_reset_option_state(const Dev& d, const Opt& o, cudaStream_t s);
 void launch_reb_from_option(const Dev& d, cudaStream_t s);
 void launch_rotate(const Dev& d, const double* src, double* dst, int elems, int use_acc_slot, cudaStream_t s);
+void launch_rotate_gain(const Dev& d, const double* src, double* dst, cudaStream_t s);   // the same for the gain records (dst <- rotated src)
 void launch_spread_last_knot(const Dev& d, cudaStream_t s);
 void launch_setup_refs_params(const Dev& d, const Consts& c, cudaStream_t s);
 // rollout (k_rollout.cu)
@@ -78,7 +79,7 @@ void launch_bwsT(const Dev& d, const Consts& c, const Opt& o, int mask_mode, int
 void launch_bwsT_tasks(const Dev& d, const Consts& c, const Opt& o, int mask_mode, int n_tasks, cudaStream_t s);
 int bwsT_resident_warps(int device);
 void launch_lad_plan(const Dev& d, const Opt& o, int mask_mode, int last_round, int smax, cudaStream_t s);
-void launch_lad_finish(const Dev& d, const Opt& o, cudaStream_t s);
+void launch_lad_finish(const Dev& d, const Opt& o, int n_unres, cudaStream_t s);
 // standalone evaluation of one generated function over a batch (Jacobian parity tests; k_eval.cu)
 int launch_eval(int fn, int n, const double* in0, const double* in1, const double* in2, const double* in3,
                 double* o0, double* o1, double* o2, double* o3, cudaStream_t s);
