@@ -812,7 +812,7 @@ int mhpc_batch_solve(mhpc_batch* b, int sync_early_exit) {
             // After the first outer iteration the step-size-0 rollout reproduces the nominal trajectory bit for bit (k_rollout.cu,
             // "cost-only pass"): only its costs are new.  The accepted trial slot of the last line search still holds that
             // trajectory and the nominal copy of it, so neither is rewritten.
-            { Stage st(b, TB_ROLLOUT); launch_recost(d, b->c, b->opt, MASK_RUNNING, 2, s); b->launches += 2; }
+            { Stage st(b, TB_ROLLOUT); launch_recost(d, b->c, b->opt, MASK_RUNNING, 2, s); b->launches += 3; }
             if (linearize(b, MASK_RUNNING)) return -1;
         }
         for (int it = 1; it <= maxDDP; ++it) {
@@ -1017,8 +1017,9 @@ int mhpc_batch_get_field(mhpc_batch* b, int inst, int phase, int field, double* 
             const int e0 = field == MHPC_F_K ? GR_K : field == MHPC_F_DU ? GR_DU : GR_G;
             const int dim = field == MHPC_F_K ? 4 * nx : field == MHPC_F_DU ? 4 : nx;
             if (!out) return dim;
-            std::vector<double> tmp((size_t)N * GREC);     // the instance's records of this phase are contiguous
-            CK(cudaMemcpyAsync(tmp.data(), d.gain + gain_idx(d, off, (size_t)inst), tmp.size() * sizeof(double), cudaMemcpyDeviceToHost, b->stream));
+            std::vector<double> tmp((size_t)N * GREC);
+            CK(cudaMemcpy2DAsync(tmp.data(), GREC * sizeof(double), d.gain + gain_idx(d, off, (size_t)inst), gain_knot_stride(d) * sizeof(double), GREC * sizeof(double), N,
+                                 cudaMemcpyDeviceToHost, b->stream));
             CK(cudaStreamSynchronize(b->stream));
             for (int k = 0; k < N; ++k) for (int e = 0; e < dim; ++e) out[(size_t)k * dim + e] = tmp[(size_t)k * GREC + e0 + e];
             return dim;

@@ -129,7 +129,13 @@ __host__ __device__ inline int lad_scratch_col(int t, int S) { return (t / S) * 
 constexpr int BWS_TRACE_ATT = 24;   // the ladder 0, 1e-3, 2e-3, ... exceeds 1000 at the 22nd attempt
 
 __host__ __device__ inline size_t st_idx(const Dev& d, int kk, int e, int i) { return ((size_t)kk * ST + e) * d.npad + i; }
-__host__ __device__ inline size_t gain_idx(const Dev& d, int kk, size_t col) { return (col * d.KT + kk) * GREC; }   // col: instance slot (gain) or scratch column (lad_gain)
+// col: instance slot (gain) or scratch column (lad_gain).  GAIN_KNOT_MAJOR: [KT][npad][GREC] (the records of one knot side by side)
+// instead of [npad][KT][GREC]
+#ifndef GAIN_KNOT_MAJOR
+#define GAIN_KNOT_MAJOR 0
+#endif
+__host__ __device__ inline size_t gain_idx(const Dev& d, int kk, size_t col) { return GAIN_KNOT_MAJOR ? ((size_t)kk * d.npad + col) * GREC : (col * d.KT + kk) * GREC; }
+__host__ __device__ inline size_t gain_knot_stride(const Dev& d) { return GAIN_KNOT_MAJOR ? (size_t)d.npad * GREC : (size_t)GREC; }
 __host__ __device__ inline size_t act_idx(const Dev& d, int w, int kk, int e, int i) {
     return (((size_t)w * d.KT + kk) * ST + e) * d.npad + i;
 }

@@ -82,7 +82,7 @@ __global__ void __launch_bounds__(BWS_THREADS, BWS_MINBLOCKS) k_bws(Dev d, Const
     double* const gv_lane = grec + GR_G + m;
     double* const kf_lane = grec + GR_K + 4 * m;
     double* const du_lane = grec + GR_DU + m;
-    const size_t gv_knot = GREC, kf_knot = GREC, du_knot = GREC;
+    const size_t gv_knot = gain_knot_stride(d), kf_knot = gv_knot, du_knot = gv_knot;
 
     // per-instance schedule walker (phase p, in-phase knot k; knot slot = p*KSTRIDE + k), used both by the prefetcher
     // (one knot ahead) and by the math; it visits the nk used knots from the last one backwards
@@ -676,6 +676,7 @@ __global__ void k_lad_copy(Dev d) {
     const int i = d.lad_u_inst[cidx];
     const double* __restrict__ src = d.lad_gain + gain_idx(d, 0, (size_t)t);
     double* __restrict__ dst = d.gain + gain_idx(d, 0, (size_t)i);
+    const size_t ks = gain_knot_stride(d);
     const int nwb = d.n_wb[i], np = d.n_phases[i];
     for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < np * KSTRIDE * GREC; idx += gridDim.x * blockDim.x) {
         const int kk = idx / GREC, e = idx - kk * GREC;
@@ -685,7 +686,7 @@ __global__ void k_lad_copy(Dev d) {
         const int nx = (p < nwb) ? 14 : 6;
         const bool term = (k == N - 1);
         const bool mine = e >= GR_G ? (e - GR_G < nx) : (!term && (e >= GR_DU || e < 4 * nx));
-        if (mine) dst[idx] = src[idx];
+        if (mine) dst[(size_t)kk * ks + e] = src[(size_t)kk * ks + e];
     }
   }
 }

@@ -63,7 +63,7 @@ __global__ void __launch_bounds__(B16_THREADS, B16_MINBLOCKS) k_bws16(Dev d, Con
     double* const gv_lane = grec + GR_G + m;
     double* const kf_lane = grec + GR_K + 4 * m;
     double* const du_lane = grec + GR_DU + m;
-    const size_t gv_knot = GREC, kf_knot = GREC, du_knot = GREC;
+    const size_t gv_knot = gain_knot_stride(d), kf_knot = gv_knot, du_knot = gv_knot;
 
     struct Walk { int p, N, mode, k; };
     auto walk_load = [&](Walk& w) {

@@ -298,8 +298,9 @@ __global__ void __launch_bounds__(BT_THREADS, BT_MINBLOCKS) k_bwsT(Dev d, Consts
                 oYt = (t == 0) ? oZt0 : (t == 1) ? oZt1 : ZSLOT; oYb = (t == 0) ? oZb0 : (t == 1) ? oZb1 : ZSLOT; oYu = (t == 0) ? oZu0 : (t == 1) ? oZu1 : ZSLOT;
                 zt2 = hom ? 1.0 : 0.0; cYt = (hom && t == 2) ? 1.0 : 0.0;
             }
-            int koff = (p * KSTRIDE + N - 2) * GREC;       // element offset of the current knot's gain record
-            for (int k = N - 2; k >= 0; --k, ++it, ++cnt, koff -= GREC) {
+            const size_t gks = gain_knot_stride(d);
+            size_t koff = (size_t)(p * KSTRIDE + N - 2) * gks;       // element offset of the current knot's gain record
+            for (int k = N - 2; k >= 0; --k, ++it, ++cnt, koff -= gks) {
                 const double* buf = bufs + (cnt & (BT_NST - 1)) * REC;
                 landed(cnt);
                 __syncwarp();                        // everyone is done with the stage of the previous knot (and with its scratch)
@@ -525,7 +526,7 @@ __global__ void __launch_bounds__(BT_THREADS, BT_MINBLOCKS) k_bwsT(Dev d, Consts
                     if (rowl) {
                         const double ga = wb_terminal_row(m, buf, last ? 0.0 : scr[S_G + m], Hr);
                         scr[S_G + m] = ga;
-                        grec[(size_t)kk * GREC + GR_G + m] = ga;
+                        grec[(size_t)kk * gain_knot_stride(d) + GR_G + m] = ga;
                     }
                 } else if (m < 6) {
                     double gv = last ? 0.0 : scr[S_G + m];
@@ -533,7 +534,7 @@ __global__ void __launch_bounds__(BT_THREADS, BT_MINBLOCKS) k_bwsT(Dev d, Consts
                     for (int jc = 0; jc < 6; ++jc) Hr[jc] = ((jc == m) ? c.rbQf[m] : 0.0) + Hr[jc];
                     gv = buf[R_RPHIX + m] + gv;
                     scr[S_G + m] = gv;
-                    grec[(size_t)kk * GREC + GR_G + m] = gv;
+                    grec[(size_t)kk * gain_knot_stride(d) + GR_G + m] = gv;
                 }
                 __syncwarp();
                 // rows -> tiles of this phase's model

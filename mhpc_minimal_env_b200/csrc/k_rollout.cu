@@ -225,7 +225,7 @@ void launch_rollout(const Dev& d, const Consts& c, const Opt& opt, int mask_mode
     int ns = 1;
     while (ns < n_slots) ns *= 2;
     if (ns > 32) ns = 32;
-    const int threads = ns == 1 ? 32 : std::min(128, 16 * ns);      // at most 16 staged instances (30 KB) per block
+    const int threads = ns == 1 ? 32 : std::min(64, 16 * ns);       // two warps per block: 4096 x 8 trials = 512 blocks spread evenly over the SMs (256 blocks of four warps left 40 SMs half empty: 1.89 ms against 1.70 for the 8-trial launch)
     const int inst_per_block = threads / ns;
     const unsigned blocks = (unsigned)((d.npad + inst_per_block - 1) / inst_per_block);
     const size_t smem = (size_t)inst_per_block * ro_stride(ns) * sizeof(double);
@@ -247,8 +247,8 @@ void launch_rollout(const Dev& d, const Consts& c, const Opt& opt, int mask_mode
 // step size 0: u = u_nom + 0 du + K (x - x_nom) reproduces u_nom and, step by step, x_nom exactly, so the
 // sweep changes nothing but the costs, which are re-evaluated with the new multipliers, penalties and barrier
 // parameters (MultiPhaseDDP.cpp:178-200).  Those are independent per knot: one thread per (knot, instance) evaluates the
-// knot's term from the trajectory the last line search accepted (still in its trial slot), one thread per instance adds
-// them in the rollout's order.  The rollout sums with explicit adds for the same reason: knot term and running sum are
+// knot's term from the trajectory the last line search accepted (still in its trial slot), one thread per (phase,
+// instance) and then one per instance add them in the rollout's order.  The rollout sums with explicit adds for the same reason: knot term and running sum are
 // then separate roundings in both kernels, and the result is bit-identical (tests: MHPC_RECOST=0 against 1).
 __global__ void __launch_bounds__(128) k_recost_knots(Dev d, Consts c, Opt opt, int mask_mode) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -299,6 +299,28 @@ __global__ void __launch_bounds__(128) k_recost_knots(Dev d, Consts c, Opt opt, 
     d.knot_cost[(size_t)kk * es + i] = out;
 }
 
+// one thread per (phase, instance): the phase's knot terms in knot order
+__global__ void __launch_bounds__(128) k_recost_phase(Dev d, int mask_mode) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= d.n || !inst_enabled(d, i, mask_mode)) return;
+    const int p = blockIdx.y;
+    if (p >= d.n_phases[i]) return;
+    const size_t es = d.npad;
+    const int N = d.ph_N[ph_idx(d, p, i)], off = d.ph_off[ph_idx(d, p, i)];
+    const double* kc = d.knot_cost + (size_t)off * es + i;
+    double V = 0.0;
+    int k = 0;
+    for (; k + 8 <= N; k += 8) {     // eight loads in flight, added in order
+        double t[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) t[q] = kc[(size_t)(k + q) * es];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) V = __dadd_rn(V, t[q]);
+    }
+    for (; k < N; ++k) V = __dadd_rn(V, kc[(size_t)k * es]);
+    d.tr_h[(size_t)p * es + i] = V;     // trial slot 0 of tr_h is free here (k_recost_knots wrote h straight into the parameters)
+}
+
 __global__ void __launch_bounds__(128) k_recost_sum(Dev d, int mask_mode, int lin_mode) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= d.n || !inst_enabled(d, i, mask_mode)) return;
@@ -306,20 +328,9 @@ __global__ void __launch_bounds__(128) k_recost_sum(Dev d, int mask_mode, int li
     const int np = d.n_phases[i];
     double total = 0.0, viol2 = 0.0;
     for (int p = 0; p < np; ++p) {
-        const int mode = d.ph_mode[ph_idx(d, p, i)], N = d.ph_N[ph_idx(d, p, i)], off = d.ph_off[ph_idx(d, p, i)];
-        const double* kc = d.knot_cost + (size_t)off * es + i;
-        double V = 0.0;
-        int k = 0;
-        for (; k + 8 <= N; k += 8) {     // eight loads in flight, added in order
-            double t[8];
-#pragma unroll
-            for (int q = 0; q < 8; ++q) t[q] = kc[(size_t)(k + q) * es];
-#pragma unroll
-            for (int q = 0; q < 8; ++q) V = __dadd_rn(V, t[q]);
-        }
-        for (; k < N; ++k) V = __dadd_rn(V, kc[(size_t)k * es]);
+        const int mode = d.ph_mode[ph_idx(d, p, i)];
         if (p < d.n_wb[i] && (mode == 2 || mode == 4)) { const double h = d.par[par_idx(d, p, PAR_H, i)]; viol2 = fma(h, h, viol2); }
-        total = __dadd_rn(total, V);
+        total = __dadd_rn(total, d.tr_h[(size_t)p * es + i]);
     }
     // what k_accept_slot0 does after a rollout; the accepted trial slot stays the one the last line search chose
     d.sd[(size_t)SD_COST * es + i] = total;
@@ -330,6 +341,7 @@ __global__ void __launch_bounds__(128) k_recost_sum(Dev d, int mask_mode, int li
 void launch_recost(const Dev& d, const Consts& c, const Opt& opt, int mask_mode, int lin_mode, cudaStream_t s) {
     const dim3 grid((unsigned)((d.n + 127) / 128), (unsigned)d.KT);
     k_recost_knots<<<grid, 128, 0, s>>>(d, c, opt, mask_mode);
+    k_recost_phase<<<dim3((unsigned)((d.n + 127) / 128), (unsigned)d.P), 128, 0, s>>>(d, mask_mode);
     k_recost_sum<<<(unsigned)((d.n + 127) / 128), 128, 0, s>>>(d, mask_mode, lin_mode);
 }
 

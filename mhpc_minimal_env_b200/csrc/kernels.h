@@ -49,7 +49,7 @@ void launch_spread_last_knot(const Dev& d, cudaStream_t s);
 void launch_setup_refs_params(const Dev& d, const Consts& c, cudaStream_t s);
 // rollout (k_rollout.cu)
 void launch_rollout(const Dev& d, const Consts& c, const Opt& o, int mask_mode, int n_slots, int trial0, const EpsList& e, cudaStream_t s);
-// forward_sweep(0) of an outer iteration after the first: costs of the unchanged trajectory under the new AL / ReB parameters (2 launches)
+// forward_sweep(0) of an outer iteration after the first: costs of the unchanged trajectory under the new AL / ReB parameters (3 launches)
 void launch_recost(const Dev& d, const Consts& c, const Opt& o, int mask_mode, int lin_mode, cudaStream_t s);
 // linearisation (k_lin.cu compiled once per knot class)
 void launch_linearize(const Dev& d, const Consts& c, const Opt& o, int mask_mode, const int* const* knot_lists, const int* n_knots, cudaStream_t s);
