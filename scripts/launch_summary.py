@@ -13,7 +13,7 @@ for r in rows[1:]:
     try: t = float(r[ix["Metric Value"]].replace(",", ""))
     except ValueError: continue
     t *= {"nsecond": 1e-6, "usecond": 1e-3, "msecond": 1, "ns": 1e-6, "us": 1e-3, "ms": 1}.get(r[ix["Metric Unit"]], 1e-6)
-    name = r[ix["Kernel Name"]].split("(")[0].replace("mhpc::<unnamed>::", "").replace("mhpc::", "").replace("void ", "")
+    name = r[ix["Kernel Name"]].split("(")[0].replace("mhpc::<unnamed>::", "").replace("unnamed>::", "").replace("mhpc::", "").replace("void ", "")
     if name == "k_lin": name = f"k_lin grid {r[ix['Grid Size']]}"
     agg[name] += t; cnt[name] += 1
 tot = sum(agg.values())
