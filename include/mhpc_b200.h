@@ -76,9 +76,16 @@ enum mhpc_field {
     MHPC_F_A, MHPC_F_B, MHPC_F_C, MHPC_F_D,         /* DynDerivative, dense                       */
     MHPC_F_LX, MHPC_F_LU, MHPC_F_LY, MHPC_F_LXX, MHPC_F_LUU, MHPC_F_LYY,   /* RCostStruct derivatives */
     MHPC_F_K, MHPC_F_DU, MHPC_F_G,                  /* CostToGoStruct K, du, G                    */
-    MHPC_F_H_UNUSED,                                /* (H is not stored per knot)                 */
+    MHPC_F_H,                                       /* CostToGoStruct H (recomputed on request, see below) */
     MHPC_F_PHIX, MHPC_F_PHIXX,                      /* TCostStruct derivatives                    */
-    MHPC_F_PX                                       /* impact Jacobian used by impact_aware_step  */
+    MHPC_F_PX,                                      /* impact Jacobian used by impact_aware_step  */
+    MHPC_F_QX, MHPC_F_QU, MHPC_F_QXX, MHPC_F_QUX, MHPC_F_QUU   /* the Q-function of CostToGoStruct (MHPC_CompoundTypes.h:100-144), as it is
+                                                       left by valuefunction_update: Qxx regularised and symmetrised, Quu regularised.
+                                                       H and the Q-function are not kept by the solver (the sweep holds them on chip):
+                                                       the first request for an instance re-runs its last accepted backward sweep on the
+                                                       device (same knot records and regularisation; no solver state changes) and keeps
+                                                       the result until any other entry point is called.  Valid after a solve or a
+                                                       successful backward_sweep; an error if that sweep did not pass. */
 };
 
 /* ---- lifetime --------------------------------------------------------------------------------- */

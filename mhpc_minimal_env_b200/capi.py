@@ -14,7 +14,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("MHPC_B200_LIB") or os.path.join(HERE, "libmhpc_b200.so")   # (the override is for timing build variants)
 
 FIELDS = ["X_ACT", "U_ACT", "Y_ACT", "X_NOM", "U_NOM", "Y_NOM", "X_REF", "U_REF", "Y_REF",
-          "A", "B", "C", "D", "LX", "LU", "LY", "LXX", "LUU", "LYY", "K", "DU", "G", "H_UNUSED", "PHIX", "PHIXX", "PX"]
+          "A", "B", "C", "D", "LX", "LU", "LY", "LXX", "LUU", "LYY", "K", "DU", "G", "H", "PHIX", "PHIXX", "PX",
+          "QX", "QU", "QXX", "QUX", "QUU"]
 FIELD_ID = {n: i for i, n in enumerate(FIELDS)}
 STATUS = {0: "running", 1: "converged", 2: "max_AL_iter", 3: "regularization_abort"}
 

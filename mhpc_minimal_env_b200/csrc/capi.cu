@@ -81,6 +81,10 @@ struct mhpc_batch {
     void* stage = nullptr;
     size_t stage_bytes = 0;
     bool keep_dead_partials = false;
+    // replay cache of mhpc_batch_get_field (H / Q fields): instance slot whose CostToGoStruct is in d.ctg_dump, and the call
+    // generation it was computed in (every entry point other than get_field advances the generation)
+    long long gen = 0, ctg_gen = -1;
+    int ctg_inst = -1;
     bool recost = true;   // outer iterations after the first: cost-only pass instead of the step-size-0 rollout (MHPC_RECOST=0: rollout)
     void* rot_tmp = nullptr;
     size_t rot_bytes = 0;
@@ -628,6 +632,39 @@ static int linearize(mhpc_batch* b, int mask_mode) {
 static int need(mhpc_batch* b) {
     if (!b || !b->have_problems) return fail("no problems set (call mhpc_batch_set_problems first)");
     CK(cudaSetDevice(b->device));
+    b->gen++;
+    return 0;
+}
+
+// The per-knot H, Qx, Qu, Qxx, Qux, Quu of CostToGoStruct (MHPC_CompoundTypes.h:100-144) are not kept by the solver: the sweep holds
+// them on chip.  On request they are recomputed for ONE instance by running its last accepted backward sweep again - same
+// knot records, same regularisation - as a single task of the ladder scheduler's task kernel in dump mode (k_bws<1, 1>): the
+// task writes its K, du, G into a scratch column and its outcome into the task arrays, so no solver state changes.
+static int replay_cost_to_go(mhpc_batch* b, int slot) {
+    Dev& d = b->d;
+    if (!d.lad_unres) return fail("get_field: H / Q fields need the ladder scheduler's task arrays (MHPC_LADDER=0 is set)");
+    if (!d.ctg_dump) { if (dalloc(b, &d.ctg_dump, (size_t)d.KT * CTGREC)) return -1; }
+    double reg = 0.0; int nbws = 0, ok = 0;
+    CK(cudaMemcpyAsync(&reg, d.sd + (size_t)SD_REG_USED * d.npad + slot, sizeof(double), cudaMemcpyDeviceToHost, b->stream));
+    CK(cudaMemcpyAsync(&nbws, d.si + (size_t)SI_N_BWS * d.npad + slot, sizeof(int), cudaMemcpyDeviceToHost, b->stream));
+    CK(cudaMemcpyAsync(&ok, d.si + (size_t)SI_BWS_OK * d.npad + slot, sizeof(int), cudaMemcpyDeviceToHost, b->stream));
+    CK(cudaStreamSynchronize(b->stream));
+    if (!ok) return fail("get_field: the last backward sweep of this instance did not pass: no CostToGoStruct to report");
+    const int cnt[LAD_CNT_N] = {2, 1, 0, 2};            // LAD_N_TASKS, LAD_N_UNRES, LAD_STRIDE, LAD_S: task 1 = speculative task of instance `slot`
+    const int t_inst[2] = {-1, slot}, t_rung[2] = {0, nbws > 0 ? nbws - 1 : 0};
+    const double t_reg[2] = {0.0, reg};
+    static_assert(LAD_N_TASKS == 0 && LAD_N_UNRES == 1 && LAD_STRIDE == 2 && LAD_S == 3, "task-list header layout");
+    CK(cudaMemcpyAsync(d.lad_cnt, cnt, sizeof(cnt), cudaMemcpyHostToDevice, b->stream));
+    CK(cudaMemcpyAsync(d.lad_t_inst, t_inst, sizeof(t_inst), cudaMemcpyHostToDevice, b->stream));
+    CK(cudaMemcpyAsync(d.lad_t_rung, t_rung, sizeof(t_rung), cudaMemcpyHostToDevice, b->stream));
+    CK(cudaMemcpyAsync(d.lad_t_reg, t_reg, sizeof(t_reg), cudaMemcpyHostToDevice, b->stream));
+    CK(cudaMemsetAsync(d.ctg_dump, 0, (size_t)d.KT * CTGREC * sizeof(double), b->stream));
+    launch_bws_replay(d, b->c, b->opt, b->stream);
+    int passed[2] = {0, -1};
+    CK(cudaMemcpyAsync(passed, d.lad_t_rung, sizeof(passed), cudaMemcpyDeviceToHost, b->stream));
+    CK(cudaStreamSynchronize(b->stream));
+    CK(cudaGetLastError());
+    if (passed[1] < 0) return fail("get_field: the replay of the accepted backward sweep did not pass (the knot records have changed since)");
     return 0;
 }
 
@@ -984,6 +1021,7 @@ static int pull_rows(mhpc_batch* b, const double* base, int rows, int inst, doub
 
 int mhpc_batch_get_field(mhpc_batch* b, int inst, int phase, int field, double* out) {
     if (need(b)) return -1;
+    b->gen--;   // a read-only call: the replay cache below stays valid across consecutive get_field calls
     const Dev& d = b->d;
     if (inst < 0 || inst >= b->n || phase < 0 || phase >= b->h_nph[SL(b, inst)]) return fail("get_field: bad instance/phase");
     const mhpc_problem& prob = b->problems[inst];   // caller's order
@@ -1044,6 +1082,25 @@ int mhpc_batch_get_field(mhpc_batch* b, int inst, int phase, int field, double* 
                     if (!wb && !term) { o[1] = b->c.GRF; o[3] = b->c.GRF; }
                 }
             }
+            return dim;
+        }
+        case MHPC_F_H: case MHPC_F_QX: case MHPC_F_QU: case MHPC_F_QXX: case MHPC_F_QUX: case MHPC_F_QUU: {
+            // H, G exist on every knot; the Q-function on the step knots 0..N-2 (zero rows for the terminal knot, like the reference's zeroed struct)
+            const int rows = (field == MHPC_F_QU || field == MHPC_F_QUX || field == MHPC_F_QUU) ? 4 : nx;
+            const int cols = (field == MHPC_F_H || field == MHPC_F_QXX || field == MHPC_F_QUX) ? nx : field == MHPC_F_QUU ? 4 : 1;
+            const int ld = rows == 4 ? 4 : 14;
+            const int e0 = field == MHPC_F_H ? CG_H : field == MHPC_F_QX ? CG_QX : field == MHPC_F_QU ? CG_QU : field == MHPC_F_QXX ? CG_QXX : field == MHPC_F_QUX ? CG_QUX : CG_QUU;
+            const int dim = rows * cols;
+            if (!out) return dim;
+            if (b->ctg_inst != inst || b->ctg_gen != b->gen) {
+                if (replay_cost_to_go(b, inst)) return -1;
+                b->ctg_inst = inst; b->ctg_gen = b->gen;
+            }
+            std::vector<double> tmp((size_t)N * CTGREC);
+            CK(cudaMemcpyAsync(tmp.data(), d.ctg_dump + (size_t)off * CTGREC, tmp.size() * sizeof(double), cudaMemcpyDeviceToHost, b->stream));
+            CK(cudaStreamSynchronize(b->stream));
+            for (int k = 0; k < N; ++k) for (int cc = 0; cc < cols; ++cc) for (int r = 0; r < rows; ++r)
+                out[(size_t)k * dim + r + rows * cc] = tmp[(size_t)k * CTGREC + e0 + r + ld * cc];
             return dim;
         }
         default: break;

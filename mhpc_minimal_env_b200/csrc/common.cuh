@@ -19,6 +19,9 @@ constexpr int KDIM = 56;          // K is 4x14 column-major (RB uses the first 2
 // Gain record of a knot: everything the backward sweep produces there, contiguous per (instance, knot) so that the warp that
 // owns the instance writes whole sectors and the rollout streams K, du with 16-byte copies
 constexpr int GREC = 74, GR_K = 0, GR_DU = 56, GR_G = 60;   // K 4x14 | du 4 | G 14  (592 B)
+// The rest of a knot's CostToGoStruct (MHPC_CompoundTypes.h:100-144), written only by the replay sweep behind
+// mhpc_batch_get_field (k_bws<1, 1>): column-major with leading dimension 14 (4 for Qux, Quu)
+constexpr int CTGREC = 496, CG_H = 0, CG_G = 196, CG_QX = 210, CG_QU = 224, CG_QXX = 228, CG_QUX = 424, CG_QUU = 480;
 constexpr int REC = 176;          // doubles per knot record
 constexpr int MAXP = 16;          // phases per instance (reference default 8)
 constexpr int KSTRIDE = 110;      // knot slots per phase = N_TIMESTEPS_MAX (MHPC_CPPTypes.h:9): phase p owns knots [p*110, p*110 + N_p),
@@ -93,6 +96,7 @@ struct Dev {
     double* st_nom;  // [KT][ST][npad]
     double* st_act;  // [W][KT][ST][npad]
     double* gain;    // [npad][KT][GREC] gain records: K | du | G
+    double* ctg_dump;   // [KT][CTGREC] of ONE instance, or null: filled by the replay sweep (capi.cu: replay_cost_to_go)
     double* lin;     // AoSoA records
     // parameters and solver state
     double* par;     // [P][NPAR][npad]

@@ -38,7 +38,7 @@ constexpr size_t BWS_SMEM = (size_t)BWS_REGION * BWS_INST * sizeof(double);
 // `max_attempts` rungs when the ladder scheduler is on: what is left goes to the scheduler's rounds below).
 // task_mode == 1: lane group = one task (instance, rung, regularisation) of the list built by k_lad_plan; tasks that are
 // not the first of their instance write K, du, G into the task-indexed scratch arrays instead of the instance's own.
-template <int task_mode>
+template <int task_mode, int dump = 0>   // dump: also write H, G, Qx, Qu, Qxx, Qux, Quu of every knot to d.ctg_dump (replay of one instance)
 __global__ void __launch_bounds__(BWS_THREADS, BWS_MINBLOCKS) k_bws(Dev d, Consts c, Opt opt, int mask_mode, int single_attempt, int max_attempts) {
     extern __shared__ __align__(16) double smem[];
     const unsigned FULL = 0xffffffffu;
@@ -189,6 +189,12 @@ __global__ void __launch_bounds__(BWS_THREADS, BWS_MINBLOCKS) k_bws(Dev d, Const
                             scr[S_G + m] = ga; scr[S_G + m + 7] = gb;
                             gv_lane[(size_t)kk * gv_knot] = ga;
                             gv_lane[(size_t)kk * gv_knot + 7] = gb;
+                            if (dump) {
+                                double* cg = d.ctg_dump + (size_t)kk * CTGREC;
+                                cg[CG_G + m] = ga; cg[CG_G + m + 7] = gb;
+#pragma unroll
+                                for (int jc = 0; jc < 14; ++jc) { cg[CG_H + m + 14 * jc] = Ha[jc]; cg[CG_H + m + 7 + 14 * jc] = Hb[jc]; }
+                            }
                         }
                     } else if (m < 6) {
                         double gv = last ? 0.0 : scr[S_G + m];
@@ -197,6 +203,12 @@ __global__ void __launch_bounds__(BWS_THREADS, BWS_MINBLOCKS) k_bws(Dev d, Const
                         gv = RBUF(R_RPHIX + m) + gv;
                         scr[S_G + m] = gv;
                         gv_lane[(size_t)kk * gv_knot] = gv;
+                        if (dump) {
+                            double* cg = d.ctg_dump + (size_t)kk * CTGREC;
+                            cg[CG_G + m] = gv;
+#pragma unroll
+                            for (int jc = 0; jc < 6; ++jc) cg[CG_H + m + 14 * jc] = Ha[jc];
+                        }
                     }
                 }
                 __syncwarp();
@@ -374,6 +386,18 @@ __global__ void __launch_bounds__(BWS_THREADS, BWS_MINBLOCKS) k_bws(Dev d, Const
                         Hb[jc] = (Hb[jc] + scr[S_MQ + jc * MQ_LD + lb]) / 2;
                     }
                 }
+                if (dump && on) {   // the Q-function as CostToGoStruct holds it after valuefunction_update: Qxx regularised and symmetrised, Quu regularised
+                    double* cg = d.ctg_dump + (size_t)kk * CTGREC;
+                    if (rowl) {
+#pragma unroll
+                        for (int jc = 0; jc < 14; ++jc) { cg[CG_QXX + la + 14 * jc] = Ha[jc]; cg[CG_QXX + lb + 14 * jc] = Hb[jc]; }
+#pragma unroll
+                        for (int cc = 0; cc < 4; ++cc) { cg[CG_QUX + cc + 4 * la] = quxa[cc]; cg[CG_QUX + cc + 4 * lb] = quxb[cc]; }
+                        cg[CG_QX + la] = qxa; cg[CG_QX + lb] = qxb;
+                    }
+                    cg[CG_QUU + m] = scr[S_QUU + m]; cg[CG_QUU + m + 8] = scr[S_QUU + m + 8];
+                    if (m < 4) cg[CG_QU + m] = scr[S_QU + m];
+                }
                 double ka[4], kb[4], du[4], goa = 0.0, gob = 0.0, dvs = 0.0;
                 __syncwarp();
                 const bool ok = value_update<14, true, BWS_LPI>(on, rw, m, scr, quxa, quxb, qxa, qxb, Ha, Hb, opt.quu_shift, ka, kb, du, goa, gob, dvs);
@@ -382,6 +406,12 @@ __global__ void __launch_bounds__(BWS_THREADS, BWS_MINBLOCKS) k_bws(Dev d, Const
                     if (!ok) { failed = true; fail_it = it; }
                     else {
                         dV += dvs;
+                        if (dump && rowl) {
+                            double* cg = d.ctg_dump + (size_t)kk * CTGREC;
+                            cg[CG_G + la] = goa; cg[CG_G + lb] = gob;
+#pragma unroll
+                            for (int jc = 0; jc < 14; ++jc) { cg[CG_H + la + 14 * jc] = Ha[jc]; cg[CG_H + lb + 14 * jc] = Hb[jc]; }
+                        }
                         if (rowl) {
                             scr[S_G + la] = goa; scr[S_G + lb] = gob;
                             gv_lane[(size_t)kk * gv_knot] = goa;
@@ -474,6 +504,18 @@ __global__ void __launch_bounds__(BWS_THREADS, BWS_MINBLOCKS) k_bws(Dev d, Const
 #pragma unroll
                     for (int jc = 0; jc < 6; ++jc) Ha[jc] = (Ha[jc] + scr[S_MQ + jc * MQ_LD + l]) / 2;
                 }
+                if (dump && on) {
+                    double* cg = d.ctg_dump + (size_t)kk * CTGREC;
+                    if (l < 6) {
+#pragma unroll
+                        for (int jc = 0; jc < 6; ++jc) cg[CG_QXX + l + 14 * jc] = Ha[jc];
+#pragma unroll
+                        for (int cc = 0; cc < 4; ++cc) cg[CG_QUX + cc + 4 * l] = qux[cc];
+                        cg[CG_QX + l] = qx;
+                    }
+                    cg[CG_QUU + m] = scr[S_QUU + m]; cg[CG_QUU + m + 8] = scr[S_QUU + m + 8];
+                    if (m < 4) cg[CG_QU + m] = scr[S_QU + m];
+                }
                 double ka[4], kb[4], du[4], gout = 0.0, gdummy = 0.0, dvs = 0.0;
                 __syncwarp();
                 const bool ok = value_update<6, false, BWS_LPI>(on, rw, m, scr, qux, qux, qx, qx, Ha, Hb, opt.quu_shift, ka, kb, du, gout, gdummy, dvs);
@@ -481,6 +523,12 @@ __global__ void __launch_bounds__(BWS_THREADS, BWS_MINBLOCKS) k_bws(Dev d, Const
                     if (!ok) { failed = true; fail_it = it; }
                     else {
                         dV += dvs;
+                        if (dump && l < 6) {
+                            double* cg = d.ctg_dump + (size_t)kk * CTGREC;
+                            cg[CG_G + l] = gout;
+#pragma unroll
+                            for (int jc = 0; jc < 6; ++jc) cg[CG_H + l + 14 * jc] = Ha[jc];
+                        }
                         if (l < 6) {
                             scr[S_G + l] = gout;
                             gv_lane[(size_t)kk * gv_knot] = gout;
@@ -499,7 +547,7 @@ __global__ void __launch_bounds__(BWS_THREADS, BWS_MINBLOCKS) k_bws(Dev d, Const
 
         // ---- outcome of the attempt (MultiPhaseDDP.cpp:209-241) ----
         int retry = 0;
-        if (!done && d.bws_trace && m == 0 && rung < BWS_TRACE_ATT) {
+        if (!dump && !done && d.bws_trace && m == 0 && rung < BWS_TRACE_ATT) {
             const int r = d.si[(size_t)SI_N_REC * es + i];
             if (r < d.max_rec) d.bws_trace[((size_t)r * BWS_TRACE_ATT + rung) * es + i] = failed ? fail_it + 1 : -1;
         }
@@ -709,6 +757,11 @@ void launch_bws_tasks(const Dev& d, const Consts& c, const Opt& opt, int mask_mo
     cudaFuncSetAttribute(k_bws<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BWS_SMEM);
     const int tcap = n_tasks > 0 ? n_tasks : d.lad_tcap;
     k_bws<1><<<(tcap + BWS_INST - 1) / BWS_INST, BWS_THREADS, BWS_SMEM, s>>>(d, c, opt, mask_mode, 0, 0);
+}
+// one task in dump mode (capi.cu: replay_cost_to_go): a single block
+void launch_bws_replay(const Dev& d, const Consts& c, const Opt& opt, cudaStream_t s) {
+    cudaFuncSetAttribute(k_bws<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BWS_SMEM);
+    k_bws<1, 1><<<1, BWS_THREADS, BWS_SMEM, s>>>(d, c, opt, MASK_ALL, 0, 0);
 }
 // lane groups of k_bws that are resident at once on this device
 int bws_resident_lane_groups(int device) {

@@ -79,6 +79,7 @@ void launch_bwsT(const Dev& d, const Consts& c, const Opt& o, int mask_mode, int
 void launch_bwsT_tasks(const Dev& d, const Consts& c, const Opt& o, int mask_mode, int n_tasks, cudaStream_t s);
 int bwsT_resident_warps(int device);
 void launch_lad_plan(const Dev& d, const Opt& o, int mask_mode, int last_round, int smax, cudaStream_t s);
+void launch_bws_replay(const Dev& d, const Consts& c, const Opt& o, cudaStream_t s);   // task 1 of a two-entry task list, writing every knot's H, G, Q* to d.ctg_dump
 void launch_lad_finish(const Dev& d, const Opt& o, int n_unres, cudaStream_t s);
 // standalone evaluation of one generated function over a batch (Jacobian parity tests; k_eval.cu)
 int launch_eval(int fn, int n, const double* in0, const double* in1, const double* in2, const double* in3,

@@ -695,6 +695,11 @@ struct Phase : PhaseBase {
             case ORC_F_H: return put(n * n, [&](int k) { return CTG[k].H.d; });
             case ORC_F_PHIX: if (out) std::memcpy(out, tcost.Phix.d, n * sizeof(double)); return n;
             case ORC_F_PHIXX: if (out) std::memcpy(out, tcost.Phixx.d, n * n * sizeof(double)); return n * n;
+            case ORC_F_QX: return put(n, [&](int k) { return CTG[k].Qx.d; });
+            case ORC_F_QU: return put(m, [&](int k) { return CTG[k].Qu.d; });
+            case ORC_F_QXX: return put(n * n, [&](int k) { return CTG[k].Qxx.d; });
+            case ORC_F_QUX: return put(m * n, [&](int k) { return CTG[k].Qux.d; });
+            case ORC_F_QUU: return put(m * m, [&](int k) { return CTG[k].Quu.d; });
         }
         return -1;
     }

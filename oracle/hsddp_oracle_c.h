@@ -25,7 +25,8 @@ enum {
     ORC_F_X_ACT = 0, ORC_F_U_ACT, ORC_F_Y_ACT, ORC_F_X_NOM, ORC_F_U_NOM, ORC_F_Y_NOM,
     ORC_F_X_REF, ORC_F_U_REF, ORC_F_Y_REF, ORC_F_A, ORC_F_B, ORC_F_C, ORC_F_D,
     ORC_F_LX, ORC_F_LU, ORC_F_LY, ORC_F_LXX, ORC_F_LUU, ORC_F_LYY,
-    ORC_F_K, ORC_F_DU, ORC_F_G, ORC_F_H, ORC_F_PHIX, ORC_F_PHIXX
+    ORC_F_K, ORC_F_DU, ORC_F_G, ORC_F_H, ORC_F_PHIX, ORC_F_PHIXX,
+    ORC_F_QX, ORC_F_QU, ORC_F_QXX, ORC_F_QUX, ORC_F_QUU   /* the rest of CostToGoStruct (MHPC_CompoundTypes.h:100-144) */
 };
 
 void* orc_create(const orc_problem* p);

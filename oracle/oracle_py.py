@@ -16,7 +16,8 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 
 FIELDS = ["X_ACT", "U_ACT", "Y_ACT", "X_NOM", "U_NOM", "Y_NOM", "X_REF", "U_REF", "Y_REF",
-          "A", "B", "C", "D", "LX", "LU", "LY", "LXX", "LUU", "LYY", "K", "DU", "G", "H", "PHIX", "PHIXX"]
+          "A", "B", "C", "D", "LX", "LU", "LY", "LXX", "LUU", "LYY", "K", "DU", "G", "H", "PHIX", "PHIXX",
+          "QX", "QU", "QXX", "QUX", "QUU"]
 FIELD_ID = {n: i for i, n in enumerate(FIELDS)}
 
 DEFAULT_X0 = [0.0927, -0.1093, -0.1542, 1.0957, -2.2033, 0.9742, -1.7098,

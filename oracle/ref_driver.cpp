@@ -75,27 +75,32 @@ void ref_schedule(void* p, int* mode, int* N) {
     MHPCLocomotion<double>* l = ((RefHandle*)p)->loco;
     for (int i = 0; i < l->_n_phases; ++i) { mode[i] = l->mode_seq[i]; N[i] = l->N_TIMESTEPS[i]; }
 }
-// nominal x (which=0), u (1), y (2), K (3), du (4), G (5) of one phase, knot-major; returns doubles per knot
+// nominal x (which=0), u (1), y (2), K (3), du (4), G (5), H (6), Qx (7), Qu (8), Qxx (9), Qux (10), Quu (11) of one phase, knot-major;
+// returns doubles per knot
 int ref_get(void* p, int phase, int which, double* out) {
     MHPCLocomotion<double>* l = ((RefHandle*)p)->loco;
     const int N = l->N_TIMESTEPS[phase];
     if (phase < l->n_wbphase) {
         const int pidx = l->pidx_WB[phase];   // buffers rotate in update_problem (MHPCLocomotion.cpp:112-121)
         auto* ms = l->ms_nom_WB[pidx]; auto* ctg = l->CTG_WB[pidx];
-        const int dims[6] = {14, 4, 4, 56, 4, 14};
+        const int dims[12] = {14, 4, 4, 56, 4, 14, 196, 14, 4, 196, 56, 16};
         for (int k = 0; k < N && out; ++k) {
             const double* src = which == 0 ? ms[k].x.data() : which == 1 ? ms[k].u.data() : which == 2 ? ms[k].y.data()
-                              : which == 3 ? ctg[k].K.data() : which == 4 ? ctg[k].du.data() : ctg[k].G.data();
+                              : which == 3 ? ctg[k].K.data() : which == 4 ? ctg[k].du.data() : which == 5 ? ctg[k].G.data()
+                              : which == 6 ? ctg[k].H.data() : which == 7 ? ctg[k].Qx.data() : which == 8 ? ctg[k].Qu.data()
+                              : which == 9 ? ctg[k].Qxx.data() : which == 10 ? ctg[k].Qux.data() : ctg[k].Quu.data();
             std::memcpy(out + (size_t)k * dims[which], src, dims[which] * sizeof(double));
         }
         return dims[which];
     }
     const int q = l->pidx_FB[phase - l->n_wbphase];
     auto* ms = l->ms_nom_FB[q]; auto* ctg = l->CTG_FB[q];
-    const int dims[6] = {6, 4, 4, 24, 4, 6};
+    const int dims[12] = {6, 4, 4, 24, 4, 6, 36, 6, 4, 36, 24, 16};
     for (int k = 0; k < N && out; ++k) {
         const double* src = which == 0 ? ms[k].x.data() : which == 1 ? ms[k].u.data() : which == 2 ? ms[k].y.data()
-                          : which == 3 ? ctg[k].K.data() : which == 4 ? ctg[k].du.data() : ctg[k].G.data();
+                          : which == 3 ? ctg[k].K.data() : which == 4 ? ctg[k].du.data() : which == 5 ? ctg[k].G.data()
+                          : which == 6 ? ctg[k].H.data() : which == 7 ? ctg[k].Qx.data() : which == 8 ? ctg[k].Qu.data()
+                          : which == 9 ? ctg[k].Qxx.data() : which == 10 ? ctg[k].Qux.data() : ctg[k].Quu.data();
         std::memcpy(out + (size_t)k * dims[which], src, dims[which] * sizeof(double));
     }
     return dims[which];

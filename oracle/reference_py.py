@@ -102,7 +102,7 @@ class ReferenceSolver:
         return list(m), list(N)
 
     def field(self, phase: int, name: str) -> np.ndarray:
-        which = {"X_NOM": 0, "U_NOM": 1, "Y_NOM": 2, "K": 3, "DU": 4, "G": 5}[name]
+        which = {"X_NOM": 0, "U_NOM": 1, "Y_NOM": 2, "K": 3, "DU": 4, "G": 5, "H": 6, "QX": 7, "QU": 8, "QXX": 9, "QUX": 10, "QUU": 11}[name]
         dim = self.L.ref_get(self.h, phase, which, None)
         _, N = self.schedule()
         out = np.zeros((N[phase], dim))

@@ -250,7 +250,7 @@ def _oracle_final(args):
     o = OracleSolver(to_orc_problem(make_specs(n, cfg)[i]))
     o.initialization()
     o.solve()
-    fields = {nm: [o.field(p, nm) for p in range(o.n_phases)] for nm in ("X_NOM", "U_NOM", "Y_NOM", "K", "DU", "G")}
+    fields = {nm: [o.field(p, nm) for p in range(o.n_phases)] for nm in ("X_NOM", "U_NOM", "Y_NOM", "K", "DU", "G", "H", "QX", "QU", "QXX", "QUX", "QUU")}
     return i, [(r["iter_AL"], r["iter_DDP"], r["n_bws"], r["n_fit"]) for r in o.records()], fields, o.scalars()["cost"]
 
 
@@ -259,7 +259,9 @@ def test_solved_trajectories_and_gains_64_instances(cfg):
     """North-star tolerance "converged trajectories and feedback gains within 1e-5" on 64 instances of each of BASELINE
     configs 2, 3 and 4 (taken evenly from a 1024-instance batch): the final nominal x, u, y, the feedback gains K, the
     feed-forward du and the value gradient G of EVERY knot of EVERY phase after a full default solve, each knot's
-    vector / matrix on its own norm."""
+    vector / matrix on its own norm.  The same for the rest of CostToGoStruct - H, Qx, Qu, Qxx, Qux, Quu - which the device
+    recomputes on request by replaying the instance's accepted backward sweep (mhpc_batch_get_field); the replay must leave
+    every result, record and gain of the batch untouched."""
     import multiprocessing as mp
     import os
     import mhpc_minimal_env_b200 as m
@@ -272,6 +274,7 @@ def test_solved_trajectories_and_gains_64_instances(cfg):
     gpu.solve()
     with mp.get_context("fork").Pool(min(os.cpu_count() or 1, 16)) as pool:
         outs = pool.map(_oracle_final, [(i, cfg, n) for i in pick])
+    before = (gpu.results_array().tobytes(), [gpu.records(i) for i in pick], [gpu.field(i, 0, "K").tobytes() for i in pick])
     worst = {}
     skipped = []
     for i, trace, fields, cost in outs:
@@ -290,8 +293,10 @@ def test_solved_trajectories_and_gains_64_instances(cfg):
     print("config", cfg, "worst per-knot relative error over 64 instances:", {k: ("%.2e" % v[0], "inst %d phase %d" % v[1:]) for k, v in worst.items()},
           "NaN instances skipped:", skipped)
     assert len(skipped) <= 2
+    assert set(worst) >= {"K", "H", "QXX", "QUU"}
     for nm, (e, i, p) in worst.items():
         assert e < TOL_TRAJ, (cfg, nm, e, "instance", i, "phase", p)
+    assert before == (gpu.results_array().tobytes(), [gpu.records(i) for i in pick], [gpu.field(i, 0, "K").tobytes() for i in pick])
 
 
 def test_smoothness_penalty_is_dormant_like_the_reference():

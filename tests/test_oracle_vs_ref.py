@@ -38,7 +38,7 @@ def test_solve_bit_exact_against_reference_sources(cfg, idx, opt):
     so, sr = orc.scalars(), ref.scalars()
     assert so["cost"] == sr["cost"] and so["exp_cost_change"] == sr["exp_cost_change"] and so["viol"] == sr["viol"]
     for p in range(len(N)):
-        for nm in ("X_NOM", "U_NOM", "Y_NOM", "K", "DU", "G"):
+        for nm in ("X_NOM", "U_NOM", "Y_NOM", "K", "DU", "G", "H", "QX", "QU", "QXX", "QUX", "QUU"):
             assert np.array_equal(orc.field(p, nm), ref.field(p, nm)), (p, nm)
 
 
