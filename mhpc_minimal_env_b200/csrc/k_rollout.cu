@@ -225,7 +225,9 @@ void launch_rollout(const Dev& d, const Consts& c, const Opt& opt, int mask_mode
     int ns = 1;
     while (ns < n_slots) ns *= 2;
     if (ns > 32) ns = 32;
-    const int threads = ns == 1 ? 32 : std::min(64, 16 * ns);       // two warps per block: 4096 x 8 trials = 512 blocks spread evenly over the SMs (256 blocks of four warps left 40 SMs half empty: 1.89 ms against 1.70 for the 8-trial launch)
+    const int threads = ns == 1 ? 32 : std::min(128, 16 * ns);      // at most 16 staged instances (30 KB) per block.  (Two-warp blocks for the 8-trial
+    // launch balance the SMs better when it is timed alone - 1.70 ms against 1.89 - but inside a solve the line search of 4096 ... 32768
+    // instances was 4-10 % slower with them.)
     const int inst_per_block = threads / ns;
     const unsigned blocks = (unsigned)((d.npad + inst_per_block - 1) / inst_per_block);
     const size_t smem = (size_t)inst_per_block * ro_stride(ns) * sizeof(double);
