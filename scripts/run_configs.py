@@ -13,9 +13,11 @@ for name, cfg, n in (("config2 (1024, default split)", 2, 1024), ("config2 at 40
     t0 = time.time()
     probs = [to_gpu_problem(s) for s in make_specs(n, cfg)]
     for label, kw in (("default thresholds", {}), ("fixed 2x3", dict(DDP_thresh=-1.0, AL_thresh=-1.0))):
-        b = m.BatchedMHPC(probs, m.default_option(**kw))
+        opt = m.default_option(**kw)
+        b = m.BatchedMHPC(probs, opt)
         b.enable_timing(True)
         for _ in range(2):
+            b.set_option(opt)      # a fresh MHPCLocomotion per solve, as in bench.py: solve() leaves its option copy modified
             b.initialization(); b.solve(); b.synchronize()
         tm = b.timing()
         res = b.results_array()
