@@ -10,10 +10,16 @@ A "step" = MHPCLocomotion::initialization() + solve_mhpc() of the whole batch.  
 
 value : solves/s with the problems resident in HBM (device-timed, CUDA events, max over ranks)
 e2e   : solves/s through the host-facing call mhpc_batch_solve_host: problems from pinned host memory (H2D), solve,
-        results + the first `exec_knots` knots of the execution bag back to the host (D2H), all inside the timed region
-roofline     : the linearisation launch group (dominant FP64 kernel family) against a DFMA peak measured live
-cpu_baseline : the oracle (CPU restatement around the reference's generated C) on one host core, bounded sample
---impl reference : the same oracle on all host cores (multiprocessing), bounded sample per step
+        results + the reference's execution bag back to the host (D2H: x,u,y,K,du of the first two whole-body phases, 180 knots per
+        instance, --exec-knots), all inside the timed region;  e2e_first10: the same with the 10 knots one control period uses
+roofline     : the dominant kernel k_bwsT (backward sweep on the FP64 tensor cores) - algorithmic bytes per launch / launch time,
+               timed live, against the measured HBM copy bandwidth (MEASURED_PEAKS.json); traffic from profiles/r2_bwsT_ncu_traffic.json
+roofline_lin_*: the linearisation kernels: EXECUTED flops / DFMA peak measured live (the reference formulation's flop count over the
+               same time is kept under reference_formulation_*)
+hsddp_iteration_ms(_max), iteration_ms: CUDA-event time per HSDDP iteration of the batch (the 10 ms control period of the north star)
+strong_scaling: BASELINE config 5, one 32768-instance batch over 1/2/4/8 GPUs (--strong-total; recorded in profiles/r2_strong_scaling.json)
+cpu_baseline : the reference's own sources (oracle/_ref; else the oracle port) on one host core, bounded sample
+--impl reference : the same on all host cores (one process per core), bounded sample per step
 """
 from __future__ import annotations
 
