@@ -90,7 +90,7 @@ def build(ref: str = "/root/reference", force: bool = False, verbose: bool = Tru
     srcs += [os.path.join(GEN, f) for f in os.listdir(GEN) if f.endswith(".inc")]
     srcs += [os.path.join(HERE, "..", "include", "mhpc_b200.h"), os.path.abspath(__file__)]
     stamp = os.path.join(OBJ, "stamp.txt")
-    dig = _digest(srcs) + f":mb{LIN_MINBLOCKS}:{LIN_OPT}:{os.environ.get('MHPC_RA_CAP', '')}:{os.environ.get('MHPC_RA_LOOKAHEAD', '')}:{os.environ.get('MHPC_RA_WINDOW', '')}:{os.environ.get('MHPC_SHARE_RCP', '')}:{os.environ.get('MHPC_RA_SMEM', '')}:{os.environ.get('MHPC_RA_FAR', '')}:{os.environ.get('MHPC_LIN_EXTRA', '')}:{os.environ.get('MHPC_BWS_EXTRA', '')}"
+    dig = _digest(srcs) + f":mb{LIN_MINBLOCKS}:{LIN_OPT}:{os.environ.get('MHPC_RA_CAP', '')}:{os.environ.get('MHPC_RA_LOOKAHEAD', '')}:{os.environ.get('MHPC_RA_WINDOW', '')}:{os.environ.get('MHPC_SHARE_RCP', '')}:{os.environ.get('MHPC_RA_SMEM', '')}:{os.environ.get('MHPC_RA_FAR', '')}:{os.environ.get('MHPC_RA_STAGE', '')}:{os.environ.get('MHPC_RA_ORDER', '')}:{os.environ.get('MHPC_RA_IN_SMEM', '')}:{os.environ.get('MHPC_LIN_EXTRA', '')}:{os.environ.get('MHPC_BWS_EXTRA', '')}"
     if not force and os.path.exists(LIB) and os.path.exists(stamp) and open(stamp).read() == dig:
         if verbose:
             print(f"[build] up to date: {LIB}")

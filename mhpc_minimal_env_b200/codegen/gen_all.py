@@ -25,7 +25,7 @@ import sys
 
 from .emit import critical_path_order, emit_c, emit_inc, reordered
 from .implicit import implicit_jacobian, structured_primal
-from .regalloc import emit_c_regalloc, emit_inc_regalloc
+from .regalloc import pressure_order, spill_cost, allocate as ra_allocate, emit_c_regalloc, emit_inc_regalloc
 from .sxdag import CONST, SXFunction, parse_casadi_c, share_reciprocals
 
 FUNCTIONS = [
@@ -54,12 +54,18 @@ STRUCT_PRIMAL = os.environ.get("MHPC_STRUCT_PRIMAL", "1") == "1"
 USE_LDLT = os.environ.get("MHPC_LDLT", "1") == "1"
 CP_ORDER = os.environ.get("MHPC_CP_ORDER", "0") == "1"      # primal dynamics emitted along their critical path: neutral (ptxas -O3 re-schedules)
 JAC_CP = os.environ.get("MHPC_JAC_CP", "0") == "1"          # same for the Jacobian bodies, which ptxas -O1 keeps in the generator's order
-RA_CAP = int(os.environ.get("MHPC_RA_CAP", "104"))
+RA_CAP = int(os.environ.get("MHPC_RA_CAP", "108"))
 RA_LOOKAHEAD = int(os.environ.get("MHPC_RA_LOOKAHEAD", "24"))
 RA_WINDOW = int(os.environ.get("MHPC_RA_WINDOW", "0"))
 SHARE_RCP = os.environ.get("MHPC_SHARE_RCP", "1") == "1"
 RA_FAR = int(os.environ.get("MHPC_RA_FAR", "128"))           # prefetch distance for operands in local memory (0: same as lookahead)
 RA_SMEM = int(os.environ.get("MHPC_RA_SMEM", "108"))      # per-thread shared-memory slots of the second spill level
+RA_ORDER = os.environ.get("MHPC_RA_ORDER", "auto")        # evaluation order of the Jacobian bodies: given | index | unlock | tuned | auto (cheapest of them)
+# (seed, noise) of the best register-pressure list schedule found by an offline search over 40 seeds x 3 noise levels at the default
+# allocator settings (scripts/order_search.py; cost = spill wavefronts, regalloc.spill_cost): 3122 -> 1272 for Dyn_BS_par, the far level
+# of Dyn_FL_par and of the impact maps empty.  `auto` still compares them with the untuned orders under the settings in force.
+TUNED_ORDER = {"Dyn_BS_par": (15, 3.0), "Dyn_FS_par": (15, 3.0), "Dyn_FL_par": (3, 3.0), "Imp_F_par": (21, 0.3), "Imp_B_par": (3, 0.3)}
+RA_STAGE = int(os.environ.get("MHPC_RA_STAGE", "0"))      # per-thread staging slots of the asynchronous far level (0: synchronous local-memory array)
 
 QUAD_OUT = os.environ.get("MHPC_QUAD_OUT", "1") == "1"
 
@@ -206,17 +212,36 @@ def generate(ref: str = DEFAULT_REF, out: str = DEFAULT_OUT, verbose: bool = Tru
         for name in IMPLICIT_FUNCTIONS:
             dev[name] = reordered(dev[name], critical_path_order(dev[name]))
     ra_stats = {}
+    if RA_ORDER != "given":
+        # evaluation order of the Jacobian bodies: of the given order and two register-pressure list schedules, the one whose
+        # allocation moves the fewest spill wavefronts (same DAG, same operations, bit-identical results)
+        for name in REGALLOC_FUNCTIONS:
+            best, best_cost, best_tag = dev[name], None, "given"
+            for tag in (("given", "index", "unlock", "tuned") if RA_ORDER == "auto" else (RA_ORDER,)):
+                if tag == "tuned" and name not in TUNED_ORDER:
+                    continue
+                cand = (dev[name] if tag == "given" else
+                        reordered(dev[name], pressure_order(dev[name], "unlock", noise=TUNED_ORDER[name][1], seed=TUNED_ORDER[name][0])) if tag == "tuned" else
+                        reordered(dev[name], pressure_order(dev[name], tag)))
+                cost = spill_cost(ra_allocate(cand, RA_CAP, RA_LOOKAHEAD, RA_WINDOW, RA_SMEM, RA_FAR, quad_map(name), RA_STAGE)[1])
+                if best_cost is None or cost < best_cost:
+                    best, best_cost, best_tag = cand, cost, tag
+            dev[name] = best
+            ra_stats.setdefault("_order", {})[name] = best_tag
+    order_tags = ra_stats.pop("_order", {})
     for name in REGALLOC_FUNCTIONS:
-        text, st = emit_inc_regalloc(dev[name], RA_CAP, RA_LOOKAHEAD, RA_WINDOW, RA_SMEM, RA_FAR, quad_map(name))
+        text, st = emit_inc_regalloc(dev[name], RA_CAP, RA_LOOKAHEAD, RA_WINDOW, RA_SMEM, RA_FAR, quad_map(name), RA_STAGE)
+        st["order"] = order_tags.get(name, "given")
         write(name + "_ra.inc", text)
         ra_stats[name] = st
     write("gen_check.c", "".join(emit_c(fn, "gen_" + name) for name, fn in fns.items()) +
-          "".join(emit_c_regalloc(fns[name], "genra_" + name, RA_CAP, RA_LOOKAHEAD, RA_WINDOW, RA_SMEM, RA_FAR) for name in REGALLOC_FUNCTIONS) +
-          "".join(emit_c_regalloc(dev[name], "gendev_" + name, RA_CAP, RA_LOOKAHEAD, RA_WINDOW, RA_SMEM, RA_FAR, quad_map(name)) for name in REGALLOC_FUNCTIONS) +
+          "".join(emit_c_regalloc(fns[name], "genra_" + name, RA_CAP, RA_LOOKAHEAD, RA_WINDOW, RA_SMEM, RA_FAR, None, RA_STAGE) for name in REGALLOC_FUNCTIONS) +
+          "".join(emit_c_regalloc(dev[name], "gendev_" + name, RA_CAP, RA_LOOKAHEAD, RA_WINDOW, RA_SMEM, RA_FAR, quad_map(name), RA_STAGE) for name in REGALLOC_FUNCTIONS) +
           "".join(emit_c(dev[name], "gendev_" + name) for name in restated if name not in REGALLOC_FUNCTIONS))
-    write("gen_meta.h", emit_meta_h(metas) + f"#define MHPC_RA_SMEM_SLOTS {RA_SMEM}\n")
+    write("gen_meta.h", emit_meta_h(metas) + f"#define MHPC_RA_SMEM_SLOTS {RA_SMEM}\n#define MHPC_RA_STAGE_SLOTS {RA_STAGE}\n"
+          + f"#define MHPC_RA_FAR_SLOTS {max([st.get('slots', 0) for st in ra_stats.values()] + [1])}\n")
     metas["_source_sha256"] = h.hexdigest()
-    metas["_regalloc"] = {"cap": RA_CAP, "lookahead": RA_LOOKAHEAD, "window": RA_WINDOW, "share_reciprocals": SHARE_RCP, "smem_slots": RA_SMEM, "far_lookahead": RA_FAR, "stats": ra_stats,
+    metas["_regalloc"] = {"cap": RA_CAP, "lookahead": RA_LOOKAHEAD, "window": RA_WINDOW, "share_reciprocals": SHARE_RCP, "smem_slots": RA_SMEM, "stage_slots": RA_STAGE, "far_lookahead": RA_FAR, "stats": ra_stats,
                          "implicit_jacobians": sorted(restated), "ldlt": USE_LDLT,
                          "device_nodes": {name: len(dev[name].nodes) for name in FUNCTIONS},
                          "device_flops": {name: dev[name].flops() for name in FUNCTIONS}}

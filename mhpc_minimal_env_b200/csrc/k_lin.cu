@@ -24,10 +24,64 @@ namespace mhpc {
 namespace {
 
 constexpr int LIN_THREADS = 128;
+#ifndef LIN_MINBLOCKS
+#define LIN_MINBLOCKS 1
+#endif
 #if LIN_CLS <= 4
-constexpr size_t LIN_SMEM = (size_t)MHPC_RA_SMEM_SLOTS * LIN_THREADS * sizeof(double);
+constexpr size_t LIN_SMEM = (size_t)(MHPC_RA_SMEM_SLOTS + MHPC_RA_STAGE_SLOTS) * LIN_THREADS * sizeof(double);
 #else
 constexpr size_t LIN_SMEM = 0;
+#endif
+
+#if LIN_CLS <= 4 && MHPC_RA_STAGE_SLOTS > 0
+// ---- asynchronous far spill level (codegen/regalloc.py, stage_slots > 0) ----
+// Values that fit neither the register file nor the shared-memory slots go to a scratch array in global memory that is
+// indexed by RESIDENT block slot, not by logical thread: (SM id, one of FAR_PER_SM slots, thread) - 148 x 3 x 128 threads x
+// ~130 doubles = 59 MB however large the launch, so it lives in L2 (the knot records leave with an evict-first hint) and the
+// spills cost no DRAM traffic.  A block takes a free slot of its SM when it starts and returns it when it ends; at most
+// LIN_MINBLOCKS blocks of this kernel fit an SM (shared memory), so one of the LIN_MINBLOCKS + 1 slots is always free.
+constexpr int FAR_SM_IDS = 256;                         // %smid values are not promised to be dense: sized generously, only touched rows cost
+constexpr int FAR_PER_SM = LIN_MINBLOCKS + 1;
+constexpr size_t FAR_STRIDE = (size_t)FAR_SM_IDS * FAR_PER_SM * LIN_THREADS;   // elements between consecutive far slots of a thread
+constexpr size_t FAR_DOUBLES = FAR_STRIDE * MHPC_RA_FAR_SLOTS;
+struct FarScratch { double* buf; unsigned* mask; };
+__device__ __forceinline__ int far_acquire(unsigned* mask, int* s_slot) {
+    if (threadIdx.x == 0) {
+        unsigned smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        unsigned* m = mask + smid;
+        int got = -1;
+        while (got < 0) {
+            for (int q = 0; q < FAR_PER_SM && got < 0; ++q) {
+                const unsigned old = atomicOr(m, 1u << q);
+                if (!(old & (1u << q))) got = q;
+            }
+        }
+        *s_slot = (int)smid * FAR_PER_SM + got;
+    }
+    __syncthreads();
+    return *s_slot;
+}
+__device__ __forceinline__ void far_release(unsigned* mask, int slot) {
+    __syncthreads();      // every thread of the block is done with its scratch
+    if (threadIdx.x == 0) atomicAnd(mask + slot / FAR_PER_SM, ~(1u << (slot % FAR_PER_SM)));
+}
+__device__ __forceinline__ void sx_far_st(double* p, double v) { asm volatile("st.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory"); }
+__device__ __forceinline__ double sx_far_ld(const double* p) { double v; asm volatile("ld.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory"); return v; }
+__device__ __forceinline__ void sx_far_issue(unsigned smem_addr, const double* p) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n\tcp.async.commit_group;" ::"r"(smem_addr), "l"(p) : "memory");
+}
+#define SX_FAR_DECL(n) static_assert((n) <= MHPC_RA_FAR_SLOTS, "far scratch: more slots than gen_meta.h promises")
+#define SX_FAR_ST(s, r) sx_far_st(sx_far + (size_t)(s) * FAR_STRIDE, r)
+#define SX_FAR_LD(s) sx_far_ld(sx_far + (size_t)(s) * FAR_STRIDE)
+#define SX_FAR_ISSUE(st_, s) sx_far_issue(sx_stage_a + (unsigned)(st_) * (unsigned)(LIN_THREADS * sizeof(double)), sx_far + (size_t)(s) * FAR_STRIDE)
+#define SX_FAR_WAIT(n) asm volatile("cp.async.wait_group %0;" ::"n"(n) : "memory")
+#define SX_STAGE(st_) sx_sm[(MHPC_RA_SMEM_SLOTS + (st_)) * LIN_THREADS]
+#define SX_FAR_PARAMS , double* sx_far, unsigned sx_stage_a
+#define SX_FAR_ARGS , sx_far, sx_stage_a
+#else
+#define SX_FAR_PARAMS
+#define SX_FAR_ARGS
 #endif
 
 #define REC_AT(e) rec[(e)]
@@ -47,8 +101,20 @@ __device__ __forceinline__ void wb_par_out(double* __restrict__ rec, int j, doub
 // One aligned quad of record elements leaves as a single 32-byte store: the record is AoS (1408 bytes per knot and
 // instance), so a scalar store per element touches a 32-byte sector four times with 8 bytes each - 4x the L2 write
 // transactions and partial-sector merges - while a quad is exactly one full sector per thread.
+#ifndef LIN_ST_HINT
+#define LIN_ST_HINT 2     // the knot records leave with an L2 evict-first policy: they are not read again before the sweep, and the spill
+                          // slab of the resident threads stays in L2 (0: plain stores, 1: .cs; measured 1.149 / 1.14 / 1.126 ms per linearisation)
+#endif
 __device__ __forceinline__ void st_quad(double* p, double a, double b, double c, double d) {
+#if LIN_ST_HINT == 1
+    asm volatile("st.global.cs.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
+#elif LIN_ST_HINT == 2
+    unsigned long long pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    asm volatile("st.global.L2::cache_hint.v4.f64 [%0], {%1, %2, %3, %4}, %5;" ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(d), "l"(pol) : "memory");
+#else
     asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
+#endif
 }
 template <int K, int ROW, int COL>
 __device__ __forceinline__ constexpr int wb_par_elem() {
@@ -80,21 +146,23 @@ __device__ __forceinline__ void imp_par_out4(double* __restrict__ rec, double v0
 // The Jacobian bodies come in the generator-allocated form (codegen/regalloc.py: a fixed file of FP64 register
 // variables + an explicit volatile local spill array with Belady eviction and software prefetch); inputs are read
 // straight from the SoA trajectory (`st`, element stride `es`), outputs go straight to the knot record.
-#define SX_IN(i, j_) ((i) == 0 ? st[(size_t)(j_) * es] : st[(size_t)(14 + (j_)) * es])
+// (a volatile asm load: it stays where the generator put it - far ahead of its consumer - and is never re-executed)
+__device__ __forceinline__ double sx_ld_in(const double* p) { double v; asm volatile("ld.global.nc.f64 %0, [%1];" : "=d"(v) : "l"(p)); return v; }
+#define SX_IN(i, j_) sx_ld_in(st + (size_t)((i) == 0 ? (j_) : 14 + (j_)) * es)
 #define SX_SMEM(s) sx_sm[(s) * LIN_THREADS]     /* second spill level: per-thread shared-memory slots, conflict-free */
 #define SX_OUT(k, nz, row, col, v) wb_par_out<k, row, col>(rec, j, dt, v)
 #define SX_OUT4(e0, k0, n0, r0, c0, v0, k1, n1, r1, c1, v1, k2, n2, r2, c2, v2, k3, n3, r3, c3, v3) \
     wb_par_out4<e0, k0, r0, c0, k1, r1, c1, k2, r2, c2, k3, r3, c3>(rec, dt, v0, v1, v2, v3)
 #if LIN_CLS == 0
-__device__ __forceinline__ void dyn_par(const double* __restrict__ st, size_t es, double* __restrict__ rec, int j, double dt, volatile double* sx_sm) {
+__device__ __forceinline__ void dyn_par(const double* __restrict__ st, size_t es, double* __restrict__ rec, int j, double dt, volatile double* sx_sm SX_FAR_PARAMS) {
 #include "gen/Dyn_BS_par_ra.inc"
 }
 #elif LIN_CLS == 1
-__device__ __forceinline__ void dyn_par(const double* __restrict__ st, size_t es, double* __restrict__ rec, int j, double dt, volatile double* sx_sm) {
+__device__ __forceinline__ void dyn_par(const double* __restrict__ st, size_t es, double* __restrict__ rec, int j, double dt, volatile double* sx_sm SX_FAR_PARAMS) {
 #include "gen/Dyn_FS_par_ra.inc"
 }
 #elif LIN_CLS == 2
-__device__ __forceinline__ void dyn_par(const double* __restrict__ st, size_t es, double* __restrict__ rec, int j, double dt, volatile double* sx_sm) {
+__device__ __forceinline__ void dyn_par(const double* __restrict__ st, size_t es, double* __restrict__ rec, int j, double dt, volatile double* sx_sm SX_FAR_PARAMS) {
 #include "gen/Dyn_FL_par_ra.inc"
 }
 #endif
@@ -104,11 +172,11 @@ __device__ __forceinline__ void dyn_par(const double* __restrict__ st, size_t es
 #define SX_OUT4(e0, k0, n0, r0, c0, v0, k1, n1, r1, c1, v1, k2, n2, r2, c2, v2, k3, n3, r3, c3, v3) \
     imp_par_out4<e0, r0, c0, r1, c1, r2, c2, r3, c3>(rec, v0, v1, v2, v3)
 #if LIN_CLS == 3
-__device__ __forceinline__ void imp_par(const double* __restrict__ st, size_t es, double* __restrict__ rec, int j, volatile double* sx_sm) {
+__device__ __forceinline__ void imp_par(const double* __restrict__ st, size_t es, double* __restrict__ rec, int j, volatile double* sx_sm SX_FAR_PARAMS) {
 #include "gen/Imp_F_par_ra.inc"
 }
 #elif LIN_CLS == 4
-__device__ __forceinline__ void imp_par(const double* __restrict__ st, size_t es, double* __restrict__ rec, int j, volatile double* sx_sm) {
+__device__ __forceinline__ void imp_par(const double* __restrict__ st, size_t es, double* __restrict__ rec, int j, volatile double* sx_sm SX_FAR_PARAMS) {
 #include "gen/Imp_B_par_ra.inc"
 }
 #endif
@@ -131,7 +199,7 @@ __device__ __forceinline__ void ev_out(double* o0, double* o1, double* o2, doubl
     do { ev_out<k0, r0, c0>(o0, o1, o2, o3, v0); ev_out<k1, r1, c1>(o0, o1, o2, o3, v1);         \
          ev_out<k2, r2, c2>(o0, o1, o2, o3, v2); ev_out<k3, r3, c3>(o0, o1, o2, o3, v3); } while (0)
 __device__ __forceinline__ void par_eval_body(const double* __restrict__ st, size_t es, double* o0, double* o1, double* o2, double* o3,
-                                              volatile double* sx_sm) {
+                                              volatile double* sx_sm SX_FAR_PARAMS) {
 #if LIN_CLS == 0
 #include "gen/Dyn_BS_par_ra.inc"
 #elif LIN_CLS == 1
@@ -214,12 +282,8 @@ __device__ inline void wb_cost_partials(const Consts& c, int mode, double dt, co
     st_quad(rec + 172, lyy[0], lyy[1], lyy[2], 0.0);
 }
 
-#ifndef LIN_MINBLOCKS
-#define LIN_MINBLOCKS 1
-#endif
-__global__ void __launch_bounds__(LIN_THREADS, LIN_MINBLOCKS) k_lin(Dev d, Consts c, Opt opt, int mask_mode, const int* __restrict__ knots, int n_pairs) {
-    extern __shared__ __align__(16) double sx_smem_base[];
-    volatile double* sx_sm = sx_smem_base + threadIdx.x;
+__device__ __forceinline__ void lin_body(const Dev& d, const Consts& c, const Opt& opt, int mask_mode, const int* __restrict__ knots, int n_pairs,
+                                         volatile double* sx_sm SX_FAR_PARAMS) {
     (void)sx_sm;
     int i, kk;
     if (n_pairs > 0) {   // non-uniform batch: explicit (knot, instance) work list of this knot class
@@ -259,7 +323,7 @@ __global__ void __launch_bounds__(LIN_THREADS, LIN_MINBLOCKS) k_lin(Dev d, Const
 #if LIN_CLS <= 2
     {
         const double dt = d.dt_wb[i];
-        dyn_par(st, es, rec, j, dt, sx_sm);
+        dyn_par(st, es, rec, j, dt, sx_sm SX_FAR_ARGS);
         double x[14], u[4], y[4];
 #pragma unroll
         for (int e = 0; e < 14; ++e) x[e] = st[e * es];
@@ -277,7 +341,7 @@ __global__ void __launch_bounds__(LIN_THREADS, LIN_MINBLOCKS) k_lin(Dev d, Const
     }
 #elif LIN_CLS <= 4
     {
-        imp_par(st, es, rec, j, sx_sm);
+        imp_par(st, es, rec, j, sx_sm SX_FAR_ARGS);
         double x[14];
 #pragma unroll
         for (int e = 0; e < 14; ++e) x[e] = st[e * es];
@@ -366,17 +430,62 @@ __global__ void __launch_bounds__(LIN_THREADS, LIN_MINBLOCKS) k_lin(Dev d, Const
 #endif
 }
 
+#if LIN_CLS <= 4 && MHPC_RA_STAGE_SLOTS > 0
+#define LIN_FAR_KPARAMS , FarScratch far
+#define LIN_FAR_BEGIN                                                                                            \
+    __shared__ int s_far_slot;                                                                                   \
+    const int far_slot = far_acquire(far.mask, &s_far_slot);                                                     \
+    double* sx_far = far.buf + (size_t)far_slot * LIN_THREADS + threadIdx.x;                                     \
+    const unsigned sx_stage_a = (unsigned)__cvta_generic_to_shared(sx_smem_base + (size_t)MHPC_RA_SMEM_SLOTS * LIN_THREADS + threadIdx.x);
+#define LIN_FAR_END far_release(far.mask, far_slot);
+#else
+#define LIN_FAR_KPARAMS
+#define LIN_FAR_BEGIN
+#define LIN_FAR_END
+#endif
+__global__ void __launch_bounds__(LIN_THREADS, LIN_MINBLOCKS) k_lin(Dev d, Consts c, Opt opt, int mask_mode, const int* __restrict__ knots, int n_pairs LIN_FAR_KPARAMS) {
+    extern __shared__ __align__(16) double sx_smem_base[];
+    volatile double* sx_sm = sx_smem_base + threadIdx.x;
+    LIN_FAR_BEGIN
+    lin_body(d, c, opt, mask_mode, knots, n_pairs, sx_sm SX_FAR_ARGS);
+    LIN_FAR_END
+}
+
 #if LIN_CLS <= 4
 // inputs in the trajectory layout (element-major, stride es: 14 x then 4 u), one evaluation per thread
 __global__ void __launch_bounds__(LIN_THREADS, LIN_MINBLOCKS) k_par_eval(int n, size_t es, const double* __restrict__ st, double* o0, double* o1,
-                                                                         double* o2, double* o3) {
+                                                                         double* o2, double* o3 LIN_FAR_KPARAMS) {
     extern __shared__ __align__(16) double sx_smem_base[];
     volatile double* sx_sm = sx_smem_base + threadIdx.x;
+    LIN_FAR_BEGIN
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= n) return;
-    par_eval_body(st + t, es, o0 + (size_t)t * 196, o1 ? o1 + (size_t)t * 56 : nullptr, o2 ? o2 + (size_t)t * 56 : nullptr,
-                  o3 ? o3 + (size_t)t * 16 : nullptr, sx_sm);
+    if (t < n)
+        par_eval_body(st + t, es, o0 + (size_t)t * 196, o1 ? o1 + (size_t)t * 56 : nullptr, o2 ? o2 + (size_t)t * 56 : nullptr,
+                      o3 ? o3 + (size_t)t * 16 : nullptr, sx_sm SX_FAR_ARGS);
+    LIN_FAR_END
 }
+#endif
+
+#if LIN_CLS <= 4 && MHPC_RA_STAGE_SLOTS > 0
+// one scratch array + slot masks per device for this knot class, allocated at the first launch (a process drives one GPU;
+// tests may touch several)
+FarScratch far_scratch() {
+    static FarScratch per_dev[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    FarScratch& f = per_dev[dev & 63];
+    if (!f.buf) {
+        if (cudaMalloc(&f.buf, FAR_DOUBLES * sizeof(double)) != cudaSuccess || cudaMalloc(&f.mask, FAR_SM_IDS * sizeof(unsigned)) != cudaSuccess) {
+            f.buf = nullptr;
+            return f;      // the launch below fails with an invalid pointer and the caller's cudaGetLastError reports it
+        }
+        cudaMemset(f.mask, 0, FAR_SM_IDS * sizeof(unsigned));
+    }
+    return f;
+}
+#define LIN_FAR_LAUNCH_ARG , far_scratch()
+#else
+#define LIN_FAR_LAUNCH_ARG
 #endif
 
 }  // anonymous namespace
@@ -408,7 +517,7 @@ __global__ void __launch_bounds__(LIN_THREADS, LIN_MINBLOCKS) k_par_eval(int n, 
 #if LIN_CLS <= 4
 void PAR_EVAL_LAUNCH(int n, size_t es, const double* st, double* o0, double* o1, double* o2, double* o3, cudaStream_t s) {
     if (LIN_SMEM > 48 * 1024) cudaFuncSetAttribute(k_par_eval, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LIN_SMEM);
-    k_par_eval<<<(n + LIN_THREADS - 1) / LIN_THREADS, LIN_THREADS, LIN_SMEM, s>>>(n, es, st, o0, o1, o2, o3);
+    k_par_eval<<<(n + LIN_THREADS - 1) / LIN_THREADS, LIN_THREADS, LIN_SMEM, s>>>(n, es, st, o0, o1, o2, o3 LIN_FAR_LAUNCH_ARG);
 }
 #endif
 
@@ -419,11 +528,11 @@ void LIN_LAUNCH(const Dev& d, const Consts& c, const Opt& opt, int mask_mode, co
     if (LIN_SMEM > 48 * 1024) cudaFuncSetAttribute(k_lin, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LIN_SMEM);
     if (n_knots < 0) {   // (knot, instance) pair list of -n_knots entries
         const int n_pairs = -n_knots;
-        k_lin<<<(n_pairs + LIN_THREADS - 1) / LIN_THREADS, LIN_THREADS, LIN_SMEM, s>>>(d, c, opt, mask_mode, knots, n_pairs);
+        k_lin<<<(n_pairs + LIN_THREADS - 1) / LIN_THREADS, LIN_THREADS, LIN_SMEM, s>>>(d, c, opt, mask_mode, knots, n_pairs LIN_FAR_LAUNCH_ARG);
         return;
     }
     dim3 grid((d.n + LIN_THREADS - 1) / LIN_THREADS, n_knots);
-    k_lin<<<grid, LIN_THREADS, LIN_SMEM, s>>>(d, c, opt, mask_mode, knots, 0);
+    k_lin<<<grid, LIN_THREADS, LIN_SMEM, s>>>(d, c, opt, mask_mode, knots, 0 LIN_FAR_LAUNCH_ARG);
 }
 
 }  // namespace mhpc
