@@ -287,10 +287,16 @@ def allocate(fn: SXFunction, cap: int = 104, lookahead: int = 48, window: int = 
     # an input "early" into a register does not work: ptxas sinks the load to its first use to save the register, and the
     # consumer then waits out the whole round trip - ncu showed the long-scoreboard stalls on exactly those consumers.
     if smem_slots >= len(in_of) + 8 and os.environ.get("MHPC_RA_IN_SMEM", "1") == "1":
-        for v in sorted(in_of, key=lambda q: in_of[q]):
-            sm_of[v] = free_sm.pop()
-            out.append(f"SX_SMEM({sm_of[v]}) = SX_IN({in_of[v][0]}, {in_of[v][1]});")
+        ins_sorted = sorted(in_of, key=lambda q: in_of[q])
+        assert len(ins_sorted) <= cap
+        # all loads first (into the still empty register file), then all stores: the includer's loads and the shared-memory
+        # slots are volatile, so the compiler keeps them in program order - load, store, load, store would serialise the round trips
+        for k, v in enumerate(ins_sorted):
+            out.append(f"r{k} = SX_IN({in_of[v][0]}, {in_of[v][1]});")
             stats["in_loads"] = stats.get("in_loads", 0) + 1
+        for k, v in enumerate(ins_sorted):
+            sm_of[v] = free_sm.pop()
+            out.append(f"SX_SMEM({sm_of[v]}) = r{k};")
         in_of.clear()
     far_window = far_lookahead if far_lookahead > lookahead else 0
 

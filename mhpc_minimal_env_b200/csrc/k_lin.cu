@@ -105,13 +105,24 @@ __device__ __forceinline__ void wb_par_out(double* __restrict__ rec, int j, doub
 #define LIN_ST_HINT 2     // the knot records leave with an L2 evict-first policy: they are not read again before the sweep, and the spill
                           // slab of the resident threads stays in L2 (0: plain stores, 1: .cs; measured 1.149 / 1.14 / 1.126 ms per linearisation)
 #endif
-__device__ __forceinline__ void st_quad(double* p, double a, double b, double c, double d) {
+#if LIN_ST_HINT == 2
+// the policy word is made once per thread (k_lin: lin_pol) - createpolicy has the latency of a memory operation
+__device__ __forceinline__ unsigned long long make_evict_first_policy() {
+    unsigned long long pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+#define ST_QUAD_POL , unsigned long long lin_pol
+#define ST_QUAD_ARG , lin_pol
+#else
+#define ST_QUAD_POL
+#define ST_QUAD_ARG
+#endif
+__device__ __forceinline__ void st_quad(double* p, double a, double b, double c, double d ST_QUAD_POL) {
 #if LIN_ST_HINT == 1
     asm volatile("st.global.cs.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
 #elif LIN_ST_HINT == 2
-    unsigned long long pol;
-    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
-    asm volatile("st.global.L2::cache_hint.v4.f64 [%0], {%1, %2, %3, %4}, %5;" ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(d), "l"(pol) : "memory");
+    asm volatile("st.global.L2::cache_hint.v4.f64 [%0], {%1, %2, %3, %4}, %5;" ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(d), "l"(lin_pol) : "memory");
 #else
     asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
 #endif
@@ -125,22 +136,22 @@ __device__ __forceinline__ double wb_par_val(double dt, double v) {
     return K == 0 ? (ROW == COL ? 1.0 : 0.0) + v * dt : K == 1 ? v * dt : v;
 }
 template <int E0, int K0, int R0, int C0, int K1, int R1, int C1, int K2, int R2, int C2, int K3, int R3, int C3>
-__device__ __forceinline__ void wb_par_out4(double* __restrict__ rec, double dt, double v0, double v1, double v2, double v3) {
+__device__ __forceinline__ void wb_par_out4(double* __restrict__ rec, double dt, double v0, double v1, double v2, double v3 ST_QUAD_POL) {
     static_assert((E0 & 3) == 0 && wb_par_elem<K0, R0, C0>() == E0 && wb_par_elem<K1, R1, C1>() == E0 + 1 &&
                   wb_par_elem<K2, R2, C2>() == E0 + 2 && wb_par_elem<K3, R3, C3>() == E0 + 3,
                   "codegen/gen_all.py: wb_record_element disagrees with the record layout");
     st_quad(rec + E0, wb_par_val<K0, R0, C0>(dt, v0), wb_par_val<K1, R1, C1>(dt, v1), wb_par_val<K2, R2, C2>(dt, v2),
-            wb_par_val<K3, R3, C3>(dt, v3));
+            wb_par_val<K3, R3, C3>(dt, v3) ST_QUAD_ARG);
 }
 template <int ROW, int COL>
 __device__ __forceinline__ void imp_par_out(double* __restrict__ rec, int j, double v) {
     if (ROW >= 7) REC_AT(R_AB(ROW - 7, COL - 2)) = v;
 }
 template <int E0, int R0, int C0, int R1, int C1, int R2, int C2, int R3, int C3>
-__device__ __forceinline__ void imp_par_out4(double* __restrict__ rec, double v0, double v1, double v2, double v3) {
+__device__ __forceinline__ void imp_par_out4(double* __restrict__ rec, double v0, double v1, double v2, double v3 ST_QUAD_POL) {
     static_assert((E0 & 3) == 0 && R_AB(R0 - 7, C0 - 2) == E0 && R_AB(R1 - 7, C1 - 2) == E0 + 1 && R_AB(R2 - 7, C2 - 2) == E0 + 2 &&
                   R_AB(R3 - 7, C3 - 2) == E0 + 3, "codegen/gen_all.py: imp_record_element disagrees with the record layout");
-    st_quad(rec + E0, v0, v1, v2, v3);
+    st_quad(rec + E0, v0, v1, v2, v3 ST_QUAD_ARG);
 }
 
 // The Jacobian bodies come in the generator-allocated form (codegen/regalloc.py: a fixed file of FP64 register
@@ -152,17 +163,17 @@ __device__ __forceinline__ double sx_ld_in(const double* p) { double v; asm vola
 #define SX_SMEM(s) sx_sm[(s) * LIN_THREADS]     /* second spill level: per-thread shared-memory slots, conflict-free */
 #define SX_OUT(k, nz, row, col, v) wb_par_out<k, row, col>(rec, j, dt, v)
 #define SX_OUT4(e0, k0, n0, r0, c0, v0, k1, n1, r1, c1, v1, k2, n2, r2, c2, v2, k3, n3, r3, c3, v3) \
-    wb_par_out4<e0, k0, r0, c0, k1, r1, c1, k2, r2, c2, k3, r3, c3>(rec, dt, v0, v1, v2, v3)
+    wb_par_out4<e0, k0, r0, c0, k1, r1, c1, k2, r2, c2, k3, r3, c3>(rec, dt, v0, v1, v2, v3 ST_QUAD_ARG)
 #if LIN_CLS == 0
-__device__ __forceinline__ void dyn_par(const double* __restrict__ st, size_t es, double* __restrict__ rec, int j, double dt, volatile double* sx_sm SX_FAR_PARAMS) {
+__device__ __forceinline__ void dyn_par(const double* __restrict__ st, size_t es, double* __restrict__ rec, int j, double dt, volatile double* sx_sm SX_FAR_PARAMS ST_QUAD_POL) {
 #include "gen/Dyn_BS_par_ra.inc"
 }
 #elif LIN_CLS == 1
-__device__ __forceinline__ void dyn_par(const double* __restrict__ st, size_t es, double* __restrict__ rec, int j, double dt, volatile double* sx_sm SX_FAR_PARAMS) {
+__device__ __forceinline__ void dyn_par(const double* __restrict__ st, size_t es, double* __restrict__ rec, int j, double dt, volatile double* sx_sm SX_FAR_PARAMS ST_QUAD_POL) {
 #include "gen/Dyn_FS_par_ra.inc"
 }
 #elif LIN_CLS == 2
-__device__ __forceinline__ void dyn_par(const double* __restrict__ st, size_t es, double* __restrict__ rec, int j, double dt, volatile double* sx_sm SX_FAR_PARAMS) {
+__device__ __forceinline__ void dyn_par(const double* __restrict__ st, size_t es, double* __restrict__ rec, int j, double dt, volatile double* sx_sm SX_FAR_PARAMS ST_QUAD_POL) {
 #include "gen/Dyn_FL_par_ra.inc"
 }
 #endif
@@ -170,13 +181,13 @@ __device__ __forceinline__ void dyn_par(const double* __restrict__ st, size_t es
 #undef SX_OUT4
 #define SX_OUT(k, nz, row, col, v) imp_par_out<row, col>(rec, j, v)
 #define SX_OUT4(e0, k0, n0, r0, c0, v0, k1, n1, r1, c1, v1, k2, n2, r2, c2, v2, k3, n3, r3, c3, v3) \
-    imp_par_out4<e0, r0, c0, r1, c1, r2, c2, r3, c3>(rec, v0, v1, v2, v3)
+    imp_par_out4<e0, r0, c0, r1, c1, r2, c2, r3, c3>(rec, v0, v1, v2, v3 ST_QUAD_ARG)
 #if LIN_CLS == 3
-__device__ __forceinline__ void imp_par(const double* __restrict__ st, size_t es, double* __restrict__ rec, int j, volatile double* sx_sm SX_FAR_PARAMS) {
+__device__ __forceinline__ void imp_par(const double* __restrict__ st, size_t es, double* __restrict__ rec, int j, volatile double* sx_sm SX_FAR_PARAMS ST_QUAD_POL) {
 #include "gen/Imp_F_par_ra.inc"
 }
 #elif LIN_CLS == 4
-__device__ __forceinline__ void imp_par(const double* __restrict__ st, size_t es, double* __restrict__ rec, int j, volatile double* sx_sm SX_FAR_PARAMS) {
+__device__ __forceinline__ void imp_par(const double* __restrict__ st, size_t es, double* __restrict__ rec, int j, volatile double* sx_sm SX_FAR_PARAMS ST_QUAD_POL) {
 #include "gen/Imp_B_par_ra.inc"
 }
 #endif
@@ -221,7 +232,7 @@ __device__ __forceinline__ void par_eval_body(const double* __restrict__ st, siz
 // running-cost derivatives of a WB step knot, with barrier terms when `reb` (SinglePhase.cpp:219-249)
 __device__ inline void wb_cost_partials(const Consts& c, int mode, double dt, const double* x, const double* u, const double* y,
                                         double pos, double vel, double height, bool reb, const double* par,
-                                        double* __restrict__ rec, int j) {
+                                        double* __restrict__ rec, int j ST_QUAD_POL) {
     const double two_dt = 2 * dt;
     double lx[14], lu[4], lxxq[4], luu[4];
 #pragma unroll
@@ -272,19 +283,22 @@ __device__ inline void wb_cost_partials(const Consts& c, int mode, double dt, co
     }
     static_assert(R_LX == 144 && R_LU == 158 && R_LY == 162 && R_LXXQ == 164 && R_LUU == 168 && R_LYY == 172 && REC == 176,
                   "the eight quads below spell out the cost part of the record");
-    st_quad(rec + 144, lx[0], lx[1], lx[2], lx[3]);
-    st_quad(rec + 148, lx[4], lx[5], lx[6], lx[7]);
-    st_quad(rec + 152, lx[8], lx[9], lx[10], lx[11]);
-    st_quad(rec + 156, lx[12], lx[13], lu[0], lu[1]);
-    st_quad(rec + 160, lu[2], lu[3], ly2[0], ly2[1]);
-    st_quad(rec + 164, lxxq[0], lxxq[1], lxxq[2], lxxq[3]);
-    st_quad(rec + 168, luu[0], luu[1], luu[2], luu[3]);
-    st_quad(rec + 172, lyy[0], lyy[1], lyy[2], 0.0);
+    st_quad(rec + 144, lx[0], lx[1], lx[2], lx[3] ST_QUAD_ARG);
+    st_quad(rec + 148, lx[4], lx[5], lx[6], lx[7] ST_QUAD_ARG);
+    st_quad(rec + 152, lx[8], lx[9], lx[10], lx[11] ST_QUAD_ARG);
+    st_quad(rec + 156, lx[12], lx[13], lu[0], lu[1] ST_QUAD_ARG);
+    st_quad(rec + 160, lu[2], lu[3], ly2[0], ly2[1] ST_QUAD_ARG);
+    st_quad(rec + 164, lxxq[0], lxxq[1], lxxq[2], lxxq[3] ST_QUAD_ARG);
+    st_quad(rec + 168, luu[0], luu[1], luu[2], luu[3] ST_QUAD_ARG);
+    st_quad(rec + 172, lyy[0], lyy[1], lyy[2], 0.0 ST_QUAD_ARG);
 }
 
 __device__ __forceinline__ void lin_body(const Dev& d, const Consts& c, const Opt& opt, int mask_mode, const int* __restrict__ knots, int n_pairs,
                                          volatile double* sx_sm SX_FAR_PARAMS) {
     (void)sx_sm;
+#if LIN_ST_HINT == 2
+    const unsigned long long lin_pol = make_evict_first_policy();
+#endif
     int i, kk;
     if (n_pairs > 0) {   // non-uniform batch: explicit (knot, instance) work list of this knot class
         const int t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -323,7 +337,7 @@ __device__ __forceinline__ void lin_body(const Dev& d, const Consts& c, const Op
 #if LIN_CLS <= 2
     {
         const double dt = d.dt_wb[i];
-        dyn_par(st, es, rec, j, dt, sx_sm SX_FAR_ARGS);
+        dyn_par(st, es, rec, j, dt, sx_sm SX_FAR_ARGS ST_QUAD_ARG);
         double x[14], u[4], y[4];
 #pragma unroll
         for (int e = 0; e < 14; ++e) x[e] = st[e * es];
@@ -331,17 +345,17 @@ __device__ __forceinline__ void lin_body(const Dev& d, const Consts& c, const Op
         for (int e = 0; e < 4; ++e) { u[e] = st[(14 + e) * es]; y[e] = st[(18 + e) * es]; }
 #if LIN_CLS == 2
 #pragma unroll
-        for (int e = R_CB(0, 0); e < R_LX; e += 4) st_quad(rec + e, 0.0, 0.0, 0.0, 0.0);   // C = D = 0 in flight
+        for (int e = R_CB(0, 0); e < R_LX; e += 4) st_quad(rec + e, 0.0, 0.0, 0.0, 0.0 ST_QUAD_ARG);   // C = D = 0 in flight
 #endif
         const bool reb = d.si[(size_t)SI_REB_ON * d.npad + i] != 0;
         double par[6];
 #pragma unroll
         for (int q = 0; q < 6; ++q) par[q] = d.par[par_idx(d, p, PAR_DELTA_T + q, i)];
-        wb_cost_partials(c, mode, dt, x, u, y, pos, vel, height, reb, par, rec, j);
+        wb_cost_partials(c, mode, dt, x, u, y, pos, vel, height, reb, par, rec, j ST_QUAD_ARG);
     }
 #elif LIN_CLS <= 4
     {
-        imp_par(st, es, rec, j, sx_sm SX_FAR_ARGS);
+        imp_par(st, es, rec, j, sx_sm SX_FAR_ARGS ST_QUAD_ARG);
         double x[14];
 #pragma unroll
         for (int e = 0; e < 14; ++e) x[e] = st[e * es];
@@ -418,11 +432,11 @@ __device__ __forceinline__ void lin_body(const Dev& d, const Consts& c, const Op
 #pragma unroll
         for (int e = 0; e < 4; ++e) rlu[e] = (two_dt * c.rbR[mode - 1][e]) * (u[e] - grf_ref(c, e));
         static_assert(R_RA == 0 && R_RB == 2 && R_RLX == 10 && R_RLU == 16 && RB_STEP_LEN == 20, "five quads = one rigid-body step record");
-        st_quad(rec + 0, a2[0] * dt, a2[1] * dt, b8[0] * dt, b8[1] * dt);
-        st_quad(rec + 4, b8[2] * dt, b8[3] * dt, b8[4] * dt, b8[5] * dt);
-        st_quad(rec + 8, b8[6] * dt, b8[7] * dt, rlx[0], rlx[1]);
-        st_quad(rec + 12, rlx[2], rlx[3], rlx[4], rlx[5]);
-        st_quad(rec + 16, rlu[0], rlu[1], rlu[2], rlu[3]);
+        st_quad(rec + 0, a2[0] * dt, a2[1] * dt, b8[0] * dt, b8[1] * dt ST_QUAD_ARG);
+        st_quad(rec + 4, b8[2] * dt, b8[3] * dt, b8[4] * dt, b8[5] * dt ST_QUAD_ARG);
+        st_quad(rec + 8, b8[6] * dt, b8[7] * dt, rlx[0], rlx[1] ST_QUAD_ARG);
+        st_quad(rec + 12, rlx[2], rlx[3], rlx[4], rlx[5] ST_QUAD_ARG);
+        st_quad(rec + 16, rlu[0], rlu[1], rlu[2], rlu[3] ST_QUAD_ARG);
     } else {
 #pragma unroll
         for (int e = 0; e < 6; ++e) REC_AT(R_RPHIX + e) = c.rbQf[e] * (st[e * es] - rb_xref(e, pos, vel, height));
