@@ -203,6 +203,21 @@ static __device__ __forceinline__ void reb_eval(double g, double delta, double& 
     }
 }
 
+// The derivative pair alone (SinglePhase.cpp:303-316) for the cost partials: bz = -1/g exactly as the reference computes it, and
+// bzz = (1/g)^2 from the same quotient instead of a second division 1/(g*g) (<= 1.5 ulp apart; a DDIV is ~20 instructions and
+// the 19 barrier rows of a knot were 10 % of the Jacobian kernels' instructions).
+static __device__ __forceinline__ void reb_eval_partials(double g, double delta, double& bz, double& bzz) {
+    if (g > delta) {
+        const double rg = 1.0 / g;
+        bz = -rg;
+        bzz = rg * rg;
+    } else {
+        const double r = (g - 2 * delta) / (1 * delta);
+        bz = r / delta;
+        bzz = 1.0;  // pow(r, k-2) with k = 2: NOT divided by delta^2
+    }
+}
+
 // Running cost of a WB knot (CostBase.cpp:4-16) plus, when `reb` is set, the barrier value
 // terms of SinglePhase.cpp:236-237 for the 8 torque, 8 joint and (stance) 3 GRF rows.
 static __device__ __forceinline__ double wb_running_cost(const Consts& c, int mode, double dt, const double* x, const double* u, const double* y,
