@@ -61,10 +61,10 @@ SHARE_RCP = os.environ.get("MHPC_SHARE_RCP", "1") == "1"
 RA_FAR = int(os.environ.get("MHPC_RA_FAR", "128"))           # prefetch distance for operands in local memory (0: same as lookahead)
 RA_SMEM = int(os.environ.get("MHPC_RA_SMEM", "108"))      # per-thread shared-memory slots of the second spill level
 RA_ORDER = os.environ.get("MHPC_RA_ORDER", "auto")        # evaluation order of the Jacobian bodies: given | index | unlock | tuned | auto (cheapest of them)
-# (seed, noise) of the best register-pressure list schedule found by an offline search over 40 seeds x 3 noise levels at the default
-# allocator settings (scripts/order_search.py; cost = spill wavefronts, regalloc.spill_cost): 3122 -> 1272 for Dyn_BS_par, the far level
+# (seed, noise) of the best register-pressure list schedule found by an offline search over 700 seeds x 2-3 noise levels at the default
+# allocator settings (scripts/order_search.py; cost = spill wavefronts, regalloc.spill_cost): 3122 -> 868 for Dyn_BS_par, the far level
 # of Dyn_FL_par and of the impact maps empty.  `auto` still compares them with the untuned orders under the settings in force.
-TUNED_ORDER = {"Dyn_BS_par": (15, 3.0), "Dyn_FS_par": (15, 3.0), "Dyn_FL_par": (3, 3.0), "Imp_F_par": (21, 0.3), "Imp_B_par": (3, 0.3)}
+TUNED_ORDER = {"Dyn_BS_par": (394, 100.0), "Dyn_FS_par": (558, 100.0), "Dyn_FL_par": (523, 100.0), "Imp_F_par": (21, 0.3), "Imp_B_par": (3, 0.3)}
 RA_STAGE = int(os.environ.get("MHPC_RA_STAGE", "0"))      # per-thread staging slots of the asynchronous far level (0: synchronous local-memory array)
 
 QUAD_OUT = os.environ.get("MHPC_QUAD_OUT", "1") == "1"

