@@ -159,26 +159,30 @@ __device__ __forceinline__ void imp_par_out4(double* __restrict__ rec, double v0
 // straight from the SoA trajectory (`st`, element stride `es`), outputs go straight to the knot record.
 // (a volatile asm load: it stays where the generator put it - far ahead of its consumer - and is never re-executed)
 __device__ __forceinline__ double sx_ld_in(const double* p) { double v; asm volatile("ld.global.nc.f64 %0, [%1];" : "=d"(v) : "l"(p)); return v; }
-#define SX_IN(i, j_) sx_ld_in(st + (size_t)((i) == 0 ? (j_) : 14 + (j_)) * es)
+#define SX_IN_GLOBAL(i, j_) sx_ld_in(st + (size_t)((i) == 0 ? (j_) : 14 + (j_)) * es)
+// whole-body step knots: the caller has the state and the control in registers already (it needed them for the cost partials)
+#define SX_IN(i, j_) ((i) == 0 ? xin[(j_)] : uin[(j_)])
 #define SX_SMEM(s) sx_sm[(s) * LIN_THREADS]     /* second spill level: per-thread shared-memory slots, conflict-free */
 #define SX_OUT(k, nz, row, col, v) wb_par_out<k, row, col>(rec, j, dt, v)
 #define SX_OUT4(e0, k0, n0, r0, c0, v0, k1, n1, r1, c1, v1, k2, n2, r2, c2, v2, k3, n3, r3, c3, v3) \
     wb_par_out4<e0, k0, r0, c0, k1, r1, c1, k2, r2, c2, k3, r3, c3>(rec, dt, v0, v1, v2, v3 ST_QUAD_ARG)
 #if LIN_CLS == 0
-__device__ __forceinline__ void dyn_par(const double* __restrict__ st, size_t es, double* __restrict__ rec, int j, double dt, volatile double* sx_sm SX_FAR_PARAMS ST_QUAD_POL) {
+__device__ __forceinline__ void dyn_par(const double* xin, const double* uin, double* __restrict__ rec, int j, double dt, volatile double* sx_sm SX_FAR_PARAMS ST_QUAD_POL) {
 #include "gen/Dyn_BS_par_ra.inc"
 }
 #elif LIN_CLS == 1
-__device__ __forceinline__ void dyn_par(const double* __restrict__ st, size_t es, double* __restrict__ rec, int j, double dt, volatile double* sx_sm SX_FAR_PARAMS ST_QUAD_POL) {
+__device__ __forceinline__ void dyn_par(const double* xin, const double* uin, double* __restrict__ rec, int j, double dt, volatile double* sx_sm SX_FAR_PARAMS ST_QUAD_POL) {
 #include "gen/Dyn_FS_par_ra.inc"
 }
 #elif LIN_CLS == 2
-__device__ __forceinline__ void dyn_par(const double* __restrict__ st, size_t es, double* __restrict__ rec, int j, double dt, volatile double* sx_sm SX_FAR_PARAMS ST_QUAD_POL) {
+__device__ __forceinline__ void dyn_par(const double* xin, const double* uin, double* __restrict__ rec, int j, double dt, volatile double* sx_sm SX_FAR_PARAMS ST_QUAD_POL) {
 #include "gen/Dyn_FL_par_ra.inc"
 }
 #endif
 #undef SX_OUT
 #undef SX_OUT4
+#undef SX_IN
+#define SX_IN(i, j_) SX_IN_GLOBAL(i, j_)
 #define SX_OUT(k, nz, row, col, v) imp_par_out<row, col>(rec, j, v)
 #define SX_OUT4(e0, k0, n0, r0, c0, v0, k1, n1, r1, c1, v1, k2, n2, r2, c2, v2, k3, n3, r3, c3, v3) \
     imp_par_out4<e0, r0, c0, r1, c1, r2, c2, r3, c3>(rec, v0, v1, v2, v3 ST_QUAD_ARG)
@@ -227,6 +231,7 @@ __device__ __forceinline__ void par_eval_body(const double* __restrict__ st, siz
 #undef SX_OUT4
 #endif
 #undef SX_IN
+#undef SX_IN_GLOBAL
 #undef SX_SMEM
 
 // running-cost derivatives of a WB step knot, with barrier terms when `reb` (SinglePhase.cpp:219-249)
@@ -327,35 +332,43 @@ __device__ __forceinline__ void lin_body(const Dev& d, const Consts& c, const Op
     else if (wb && term && mode == 2) cls = CLS_IMPF;
     else if (wb && term && mode == 4) cls = CLS_IMPB;
     else cls = CLS_LIGHT;
-    if (!(enabled & (p < nph) & (k < N) & (cls == LIN_CLS))) return;     // (p < nph && k < N: knot_to_phase)
-
-    const int j = i & 31;
-    double* __restrict__ rec = d.lin + lin_base(d, i, kk);
     const int slot = d.si[(size_t)SI_ACC_SLOT * d.npad + i];
-    const double* st = d.st_act + act_idx(d, slot, kk, 0, i);
     const size_t es = d.npad;
     const double vel = d.vel[i], height = d.height[i];
     const double pos = d.pos_ref[(size_t)kk * es + i];
     const int lin_mode = d.si[(size_t)SI_AL_PARTIALS * d.npad + i];  // 2: derivatives of a full forward sweep (AL terms enter Phix/Phixx)
+    // the scalars take part in the predicate (comparisons that hold for every valid batch), so their loads complete HERE, together:
+    // ptxas otherwise sinks each load to its first use deep in the body, where it costs a round trip of its own
+    bool ok = enabled & (p < nph) & (k < N) & (cls == LIN_CLS) & (slot >= 0) & (lin_mode >= 0) & (vel == vel) & (height == height) & (pos == pos);   // (p < nph && k < N: knot_to_phase)
+#if LIN_CLS <= 2
+    const double dt = d.dt_wb[i];
+    const int reb_i = d.si[(size_t)SI_REB_ON * d.npad + i];
+    double par[6];
+#pragma unroll
+    for (int q = 0; q < 6; ++q) { par[q] = d.par[par_idx(d, p, PAR_DELTA_T + q, i)]; ok &= (par[q] == par[q]); }
+    ok &= (dt == dt) & (reb_i >= 0);
+#endif
+    if (!ok) return;
+
+    const int j = i & 31;
+    double* __restrict__ rec = d.lin + lin_base(d, i, kk);
+    const double* st = d.st_act + act_idx(d, slot, kk, 0, i);
 
 #if LIN_CLS <= 2
     {
-        const double dt = d.dt_wb[i];
-        dyn_par(st, es, rec, j, dt, sx_sm SX_FAR_ARGS ST_QUAD_ARG);
+        // second (and last) round trip: state, control and outputs of the knot in one burst.  The cost partials go first - they need
+        // all 22 values and the register file is still empty - and the Jacobian body then takes its inputs from the same registers.
         double x[14], u[4], y[4];
 #pragma unroll
-        for (int e = 0; e < 14; ++e) x[e] = st[e * es];
+        for (int e = 0; e < 14; ++e) x[e] = sx_ld_in(st + (size_t)e * es);
 #pragma unroll
-        for (int e = 0; e < 4; ++e) { u[e] = st[(14 + e) * es]; y[e] = st[(18 + e) * es]; }
+        for (int e = 0; e < 4; ++e) { u[e] = sx_ld_in(st + (size_t)(14 + e) * es); y[e] = sx_ld_in(st + (size_t)(18 + e) * es); }
 #if LIN_CLS == 2
 #pragma unroll
         for (int e = R_CB(0, 0); e < R_LX; e += 4) st_quad(rec + e, 0.0, 0.0, 0.0, 0.0 ST_QUAD_ARG);   // C = D = 0 in flight
 #endif
-        const bool reb = d.si[(size_t)SI_REB_ON * d.npad + i] != 0;
-        double par[6];
-#pragma unroll
-        for (int q = 0; q < 6; ++q) par[q] = d.par[par_idx(d, p, PAR_DELTA_T + q, i)];
-        wb_cost_partials(c, mode, dt, x, u, y, pos, vel, height, reb, par, rec, j ST_QUAD_ARG);
+        wb_cost_partials(c, mode, dt, x, u, y, pos, vel, height, reb_i != 0, par, rec, j ST_QUAD_ARG);
+        dyn_par(x, u, rec, j, dt, sx_sm SX_FAR_ARGS ST_QUAD_ARG);
     }
 #elif LIN_CLS <= 4
     {
