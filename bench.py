@@ -363,7 +363,7 @@ def main():
                            "bound": "fp64", "achieved": exe_bs / (lin_bs_ms * 1e-3) / 1e12, "peak": fp64_peak, "unit": "TFLOP/s",
                            "frac": exe_bs / (lin_bs_ms * 1e-3) / 1e12 / fp64_peak,
                            "reference_formulation_tflops": bs_tflops, "reference_formulation_frac": bs_tflops / fp64_peak,
-                           "traffic": ncu_traffic("r1_lin_bs_ncu_traffic.json"), "algorithmic_bytes": 1352.0 * n_bs_knots * n,
+                           "traffic": ncu_traffic("r2_lin_bs_ncu_traffic.json"), "algorithmic_bytes": 1352.0 * n_bs_knots * n,
                            "hbm_frac_algorithmic": 1352.0 * n_bs_knots * n / (lin_bs_ms * 1e-3) / 1e9 / hbm_peak, "ms_per_launch": lin_bs_ms,
                            "peak_source": "FP64 FMA probe measured live on this GPU (MEASURED_PEAKS.json has no FP64 entry)"}
         roofline_lin_group = {"kernel": "linearisation launch group (k_lin<BS,FS,FL,IMPF,IMPB,light>)", "bound": "fp64",
