@@ -67,7 +67,8 @@ constexpr int BT_BAR = BT_NST * REC + SCR + 14;     // one 8-byte mbarrier per s
 constexpr int BT_NPH = BT_BAR + BT_NST;             // knot counts per phase (ints)
 constexpr size_t BT_SMEM = (size_t)(BT_NPH + MAXP / 2 + 2) * sizeof(double);
 #ifndef BT_MINBLOCKS
-#define BT_MINBLOCKS 16
+#define BT_MINBLOCKS 13   // a hint to ptxas only: 13 ... 16 all compile to 128 registers (16 warps resident per SM) but schedule differently -
+                          // 1.99 / 2.00 / 2.06 / 2.06 ms per sweep; 12 takes 164 registers (2.69 ms), 18 and 20 take 96 (21 warps: 2.09 ms)
 #endif
 constexpr int S_QP = S_QUX;           // Quu as a doubly periodic 7 x 7 table QP[a + 7 b] = Quu(a & 3, b & 3) (the Qux area is unused here)
 constexpr int S_SYM = S_MQ;           // two 8 x 10 transposition areas (the row workspace is idle during step knots)
