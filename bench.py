@@ -353,7 +353,7 @@ def main():
                     "traffic": ncu_traffic("r2_bwsT_ncu_traffic.json"), "algorithmic_bytes": BWS_BYTES_PER_INSTANCE * n,
                     "ms_per_launch": bws_ms, "us_per_knot": 1e3 * bws_ms / 712,
                     "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
-                    "note": "712 dependent knots per instance; ncu (profiles/r2_ncu_summary.md): shared-memory data pipe 49 %, issue slots 48 %, "
+                    "note": "712 dependent knots per instance; ncu (profiles/r2_ncu_summary.md): shared-memory data pipe 51 %, issue slots 45 %, "
                             "FP64 tensor pipe 37 % + FP64 pipe 21 % of peak (stalls: fixed-latency dependencies 34 %, math-pipe throttle 24 %); DMMA and "
                             "DFMA have the same FP64 peak on B200 (profiles/r2_dmma_microbench.txt)"}
         # FP64 kernels: frac = flops the device form EXECUTES / measured DFMA peak.  (The Jacobians are re-derived by implicit
