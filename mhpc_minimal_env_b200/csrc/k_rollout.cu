@@ -123,12 +123,25 @@ __global__ void __launch_bounds__(128) k_rollout(Dev d, Consts c, Opt opt, int m
 #pragma unroll
                 for (int e = 0; e < 14; ++e) { act[b + e * es] = x[e]; dx[e] = x[e] - RO_NOM(e); }
                 // u = u_nom + eps*du + K (x - x_nom)   (SinglePhase.cpp:76)
+                if (STAGED) {   // the four gains of a state are 32 contiguous bytes of the staged record: two 16-byte loads (-7 % on the launch)
+                    const double2* k2 = reinterpret_cast<const double2*>(sg + L::K);
+                    double s[4];
 #pragma unroll
-                for (int r = 0; r < 4; ++r) {
-                    double s = RO_KF(r) * dx[0];
+                    for (int e = 0; e < 14; ++e) {
+                        const double2 ka = k2[2 * e], kb = k2[2 * e + 1];
+                        if (e == 0) { s[0] = ka.x * dx[0]; s[1] = ka.y * dx[0]; s[2] = kb.x * dx[0]; s[3] = kb.y * dx[0]; }
+                        else { s[0] += ka.x * dx[e]; s[1] += ka.y * dx[e]; s[2] += kb.x * dx[e]; s[3] += kb.y * dx[e]; }
+                    }
 #pragma unroll
-                    for (int e = 1; e < 14; ++e) s += RO_KF(r + 4 * e) * dx[e];
-                    u[r] = (RO_UNOM(r) + eps * RO_DUF(r)) + s;
+                    for (int r = 0; r < 4; ++r) u[r] = (RO_UNOM(r) + eps * RO_DUF(r)) + s[r];
+                } else {
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) {
+                        double s = RO_KF(r) * dx[0];
+#pragma unroll
+                        for (int e = 1; e < 14; ++e) s += RO_KF(r + 4 * e) * dx[e];
+                        u[r] = (RO_UNOM(r) + eps * RO_DUF(r)) + s;
+                    }
                 }
                 wb_step(mode, dt, x, u, xn, y);
 #pragma unroll
@@ -183,12 +196,25 @@ __global__ void __launch_bounds__(128) k_rollout(Dev d, Consts c, Opt opt, int m
                 }
 #pragma unroll
                 for (int e = 0; e < 6; ++e) { act[b + e * es] = x[e]; dx[e] = x[e] - RO_NOM(e); }
+                if (STAGED) {
+                    const double2* k2 = reinterpret_cast<const double2*>(sg + L::K);
+                    double s[4];
 #pragma unroll
-                for (int r = 0; r < 4; ++r) {
-                    double s = RO_KF(r) * dx[0];
+                    for (int e = 0; e < 6; ++e) {
+                        const double2 ka = k2[2 * e], kb = k2[2 * e + 1];
+                        if (e == 0) { s[0] = ka.x * dx[0]; s[1] = ka.y * dx[0]; s[2] = kb.x * dx[0]; s[3] = kb.y * dx[0]; }
+                        else { s[0] += ka.x * dx[e]; s[1] += ka.y * dx[e]; s[2] += kb.x * dx[e]; s[3] += kb.y * dx[e]; }
+                    }
 #pragma unroll
-                    for (int e = 1; e < 6; ++e) s += RO_KF(r + 4 * e) * dx[e];
-                    u[r] = (RO_UNOM(r) + eps * RO_DUF(r)) + s;
+                    for (int r = 0; r < 4; ++r) u[r] = (RO_UNOM(r) + eps * RO_DUF(r)) + s[r];
+                } else {
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) {
+                        double s = RO_KF(r) * dx[0];
+#pragma unroll
+                        for (int e = 1; e < 6; ++e) s += RO_KF(r + 4 * e) * dx[e];
+                        u[r] = (RO_UNOM(r) + eps * RO_DUF(r)) + s;
+                    }
                 }
                 rb_step(mode, dt, x, u, fh, xn);
 #pragma unroll
