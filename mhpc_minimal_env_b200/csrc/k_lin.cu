@@ -102,8 +102,9 @@ __device__ __forceinline__ void wb_par_out(double* __restrict__ rec, int j, doub
 // instance), so a scalar store per element touches a 32-byte sector four times with 8 bytes each - 4x the L2 write
 // transactions and partial-sector merges - while a quad is exactly one full sector per thread.
 #ifndef LIN_ST_HINT
-#define LIN_ST_HINT 2     // the knot records leave with an L2 evict-first policy: they are not read again before the sweep, and the spill
-                          // slab of the resident threads stays in L2 (0: plain stores, 1: .cs; measured 1.149 / 1.14 / 1.126 ms per linearisation)
+#define LIN_ST_HINT 1     // the knot records leave as streaming stores (.cs): they are not read again before the sweep, and the spill slab of the
+                          // resident threads stays in L2 (0: plain stores, 2: an explicit L2 evict-first policy; 0.993 / 0.972 / 0.988 ms per
+                          // linearisation for 0 / 1 / 2 at the end of round 2)
 #endif
 #if LIN_ST_HINT == 2
 // the policy word is made once per thread (k_lin: lin_pol) - createpolicy has the latency of a memory operation
