@@ -642,7 +642,12 @@ static int need(mhpc_batch* b) {
 // task writes its K, du, G into a scratch column and its outcome into the task arrays, so no solver state changes.
 static int replay_cost_to_go(mhpc_batch* b, int slot) {
     Dev& d = b->d;
-    if (!d.lad_unres) return fail("get_field: H / Q fields need the ladder scheduler's task arrays (MHPC_LADDER=0 is set)");
+    if (!d.lad_cnt) {   // the ladder scheduler is off (MHPC_LADDER=0): a two-entry task list and one scratch column for the replay alone
+        int rc = dalloc(b, &d.lad_cnt, LAD_CNT_N);
+        rc |= dalloc(b, &d.lad_t_inst, 2); rc |= dalloc(b, &d.lad_t_rung, 2); rc |= dalloc(b, &d.lad_t_reg, 2); rc |= dalloc(b, &d.lad_t_dv, 2);
+        rc |= dalloc(b, &d.lad_gain, (size_t)d.KT * GREC * (GAIN_KNOT_MAJOR ? d.npad : 1));
+        if (rc) return -1;
+    }
     if (!d.ctg_dump) { if (dalloc(b, &d.ctg_dump, (size_t)d.KT * CTGREC)) return -1; }
     double reg = 0.0; int nbws = 0, ok = 0;
     CK(cudaMemcpyAsync(&reg, d.sd + (size_t)SD_REG_USED * d.npad + slot, sizeof(double), cudaMemcpyDeviceToHost, b->stream));
