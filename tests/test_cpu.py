@@ -183,6 +183,33 @@ def _lib_path():
 
 
 @pytest.mark.skipif(not os.path.exists(_lib_path()), reason="libmhpc_b200.so not built (run __graft_entry__.build())")
+def test_register_pressure_order_is_a_cheaper_topological_order():
+    """codegen/regalloc.pressure_order (the evaluation order of the Jacobian bodies on the device) returns a
+    permutation of the DAG's nodes in which every operand precedes its user, and the allocation over it moves fewer spill
+    wavefronts than the allocation over the given order.  (That the re-ordered bodies compute the same numbers bit for bit
+    is part of test_codegen_bit_exact_against_reference_objects: the generated check library is emitted from them.)"""
+    from mhpc_minimal_env_b200.codegen import gen_all as G
+    from mhpc_minimal_env_b200.codegen.emit import reordered
+    from mhpc_minimal_env_b200.codegen.implicit import implicit_jacobian
+    from mhpc_minimal_env_b200.codegen.regalloc import allocate, pressure_order, spill_cost
+    from mhpc_minimal_env_b200.codegen.sxdag import parse_casadi_c
+    src = os.path.join(G.DEFAULT_REF, "CasadiGen", "source")
+    if not os.path.isdir(src):
+        pytest.skip("reference sources not present")
+    primal, jac = parse_casadi_c(os.path.join(src, "Dyn_FL.c")), parse_casadi_c(os.path.join(src, "Dyn_FL_par.c"))
+    fn = implicit_jacobian(primal, jac, G.USE_LDLT)
+    base = spill_cost(allocate(fn, G.RA_CAP, G.RA_LOOKAHEAD, 0, G.RA_SMEM, G.RA_FAR, G.quad_map("Dyn_FL_par"))[1])
+    for tie, noise, seed in (("index", 0.0, 0), ("unlock", 0.0, 0), ("unlock",) + G.TUNED_ORDER["Dyn_FL_par"][::-1]):
+        order = pressure_order(fn, tie, noise=noise, seed=seed)
+        assert sorted(order) == list(range(len(fn.nodes)))
+        pos = {v: k for k, v in enumerate(order)}
+        for v, nd in enumerate(fn.nodes):
+            for p in (nd.a, nd.b):
+                assert p < 0 or pos[p] < pos[v]
+        cost = spill_cost(allocate(reordered(fn, order), G.RA_CAP, G.RA_LOOKAHEAD, 0, G.RA_SMEM, G.RA_FAR, G.quad_map("Dyn_FL_par"))[1])
+        assert cost < base, (tie, noise, seed, cost, base)
+
+
 def test_c_abi_exports_every_declared_symbol():
     hdr = open(os.path.join(ROOT, "include", "mhpc_b200.h")).read()
     declared = sorted(set(re.findall(r"\b(mhpc_[A-Za-z0-9_]+)\s*\(", hdr)))
