@@ -25,9 +25,12 @@ namespace mhpc {
 // short (~0.4 us), so two steps of lead do not cover a DRAM round trip there (ncu: a quarter of the kernel's samples sat
 // on the copy wait and the first reads of the rigid-body loop); five do.
 template <int NXP> struct RoLay;
-template <> struct RoLay<14> { enum { X = 0, U = 14, K = 18, DU = 74, POS = 78, STAGE = 80, DEPTH = 3 }; };
+#ifndef RO_WB_DEPTH
+#define RO_WB_DEPTH 3
+#endif
+template <> struct RoLay<14> { enum { X = 0, U = 14, K = 18, DU = 74, POS = 78, STAGE = 80, DEPTH = RO_WB_DEPTH }; };
 template <> struct RoLay<6> { enum { X = 0, U = 6, K = 10, DU = 34, POS = 38, STAGE = 40, DEPTH = 6 }; };
-constexpr int RO_RING = 240;   // doubles per instance
+constexpr int RO_RING = RO_WB_DEPTH * 80 > 240 ? RO_WB_DEPTH * 80 : 240;   // doubles per instance
 
 // The lanes of a warp address the stages of 32 / n_slots different instances at once; with the stages a multiple of 16
 // doubles apart all of them hit the same bank pair (ncu: 79 % of the shared-memory wavefronts of the 4-trial launch were
@@ -101,8 +104,8 @@ __global__ void __launch_bounds__(128) k_rollout(Dev d, Consts c, Opt opt, int m
             for (int q = 0; q < 6; ++q) par[q] = d.par[par_idx(d, p, PAR_DELTA_T + q, i)];
             if (STAGED) {
                 __syncwarp(grp);
-                stage_knot<14, NL>(d, 0 < N - 1, off, i, w, n_used, stage);
-                stage_knot<14, NL>(d, 1 < N - 1, off + 1, i, w, n_used, stage + RoLay<14>::STAGE);
+#pragma unroll
+                for (int q = 0; q < RoLay<14>::DEPTH - 1; ++q) stage_knot<14, NL>(d, q < N - 1, off + q, i, w, n_used, stage + q * RoLay<14>::STAGE);
             }
             for (int k = 0; k < N - 1; ++k) {
                 const int kk = off + k;
@@ -111,9 +114,9 @@ __global__ void __launch_bounds__(128) k_rollout(Dev d, Consts c, Opt opt, int m
                 typedef RoLay<14> L;
                 const double* sg = stage + (k % L::DEPTH) * L::STAGE;
                 if (STAGED) {
-                    __pipeline_wait_prior(L::DEPTH - 2);   // everything but the newest group (knot k + 1) has landed
+                    __pipeline_wait_prior(L::DEPTH - 2);   // everything but the newest groups (knots k + 1 ..) has landed
                     __syncwarp(grp);
-                    stage_knot<14, NL>(d, k + 2 < N - 1, kk + 2, i, w, n_used, stage + ((k + 2) % L::DEPTH) * L::STAGE);
+                    stage_knot<14, NL>(d, k + L::DEPTH - 1 < N - 1, kk + L::DEPTH - 1, i, w, n_used, stage + ((k + L::DEPTH - 1) % L::DEPTH) * L::STAGE);
                 }
 #define RO_NOM(e) (STAGED ? sg[L::X + (e)] : d.st_nom[b + (size_t)(e) * es])
 #define RO_UNOM(r) (STAGED ? sg[L::U + (r)] : d.st_nom[b + (size_t)(14 + (r)) * es])
